@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE -- ctypes access to the two CPU oracles.
+
+* ``port()``  : oracle/_build/liboracle_port.so, this repo's plain-C restatement
+  (oracle/port/*.c), built by ``make -C oracle port``.
+* ``ref()``   : oracle/_ref/libref_oai.so, the UNMODIFIED reference sources compiled
+  in place from /root/reference by ``make -C oracle ref``.
+  It only exists where it was built (this container) or where the prebuilt .so
+  travelled (the GPU box); ``ref()`` returns None otherwise.
+
+Reference signatures bound here: openair1/PHY/CODING/defs.h:132,152,239-253,362,
+470-484,499-513.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = os.path.join(_HERE, "_build", "liboracle_port.so")
+_REF = os.path.join(_HERE, "_ref", "libref_oai.so")
+
+_port = None
+_ref = None
+_ref_tried = False
+
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+u32ref = C.POINTER(C.c_uint32)
+
+
+def build(ref_too=True):
+    """Compile the oracle libraries (called from __graft_entry__.build())."""
+    subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
+    if ref_too:
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def port():
+    global _port
+    if _port is not None:
+        return _port
+    if not os.path.exists(_PORT):
+        build(ref_too=False)
+    L = C.CDLL(_PORT)
+    L.orc_qpp_index.argtypes = [C.c_int]
+    L.orc_qpp_f1.argtypes = [C.c_int]
+    L.orc_qpp_f2.argtypes = [C.c_int]
+    L.orc_qpp_K.argtypes = [C.c_int]
+    L.orc_qpp_table.argtypes = [C.c_int, u16p]
+    for f in ("orc_crc24a", "orc_crc24b", "orc_crc16", "orc_crc8"):
+        getattr(L, f).argtypes = [u8p, C.c_int]
+        getattr(L, f).restype = C.c_uint32
+    L.orc_lte_segmentation.argtypes = [C.c_uint32] + [u32ref] * 6
+    L.orc_generate_dummy_w.argtypes = [C.c_uint32, u8p, C.c_uint8]
+    L.orc_generate_dummy_w.restype = C.c_uint32
+    L.orc_lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, i16p, u8p, i16p, C.c_uint8,
+                                                 C.c_uint32] + [C.c_uint8] * 7 + [u32ref]
+    L.orc_sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, i16p]
+    L.orc_sub_block_deinterleaving_turbo.restype = None
+    L.orc_turbo_encode.argtypes = [u8p, C.c_int, u8p]
+    L.orc_turbo_encode.restype = None
+    L.orc_sub_block_interleaving_turbo.argtypes = [C.c_uint32, u8p, u8p]
+    L.orc_sub_block_interleaving_turbo.restype = C.c_uint32
+    L.orc_lte_rate_matching_turbo.argtypes = [C.c_uint32, C.c_uint32, u8p, u8p, C.c_uint8, C.c_uint32] + [C.c_uint8] * 6
+    L.orc_lte_rate_matching_turbo.restype = C.c_uint32
+    L.orc_turbo_decoder16.argtypes = [i16p, u8p, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8]
+    L.orc_turbo_decoder16.restype = C.c_uint8
+    L.orc_turbo_decoder8.argtypes = [i16p, u8p, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8]
+    L.orc_turbo_decoder8.restype = C.c_uint8
+    L.orc_log_map16.argtypes = [i16p, i16p, i16p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_log_map16.restype = None
+    L.orc_turbo_decoder16_batch.argtypes = [i16p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_uint16,
+                                            C.c_uint8, C.c_uint8, C.c_int]
+    L.orc_turbo_decoder16_batch.restype = None
+    _port = L
+    return L
+
+
+def ref():
+    """The compiled reference, initialised (crcTableInit, init_td16, init_td8), or None."""
+    global _ref, _ref_tried
+    if _ref is not None or _ref_tried:
+        return _ref
+    _ref_tried = True
+    if not os.path.exists(_REF):
+        if os.path.isdir("/root/reference/openair1/PHY/CODING"):
+            build(ref_too=True)
+        if not os.path.exists(_REF):
+            return None
+    L = C.CDLL(_REF)
+    stats = [C.c_void_p] * 7
+    for f in ("ref_phy_threegpplte_turbo_decoder16", "ref_phy_threegpplte_turbo_decoder8"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16,
+                                  C.c_uint8, C.c_uint8, C.c_uint8] + stats
+        getattr(L, f).restype = C.c_uint8
+    L.ref_threegpplte_turbo_encoder.argtypes = [u8p, C.c_uint16, C.c_void_p, C.c_uint8, C.c_uint16, C.c_uint16]
+    L.ref_threegpplte_turbo_encoder.restype = None
+    for f in ("ref_crc24a", "ref_crc24b", "ref_crc16", "ref_crc8"):
+        getattr(L, f).argtypes = [u8p, C.c_int]
+        getattr(L, f).restype = C.c_uint32
+    L.ref_lte_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [u32ref] * 6
+    L.ref_generate_dummy_w.argtypes = [C.c_uint32, u8p, C.c_uint8]
+    L.ref_generate_dummy_w.restype = C.c_uint32
+    L.ref_lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, i16p, u8p, i16p, C.c_uint8,
+                                                 C.c_uint32] + [C.c_uint8] * 7 + [u32ref]
+    L.ref_sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, i16p]
+    L.ref_sub_block_deinterleaving_turbo.restype = None
+    L.ref_sub_block_interleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, u8p]
+    L.ref_sub_block_interleaving_turbo.restype = C.c_uint32
+    L.ref_lte_rate_matching_turbo.argtypes = [C.c_uint32, C.c_uint32, u8p, u8p, C.c_uint8, C.c_uint32] + [C.c_uint8] * 8
+    L.ref_lte_rate_matching_turbo.restype = C.c_uint32
+    L.log_map16.argtypes = [C.c_void_p] * 7 + [C.c_ushort, C.c_ubyte, C.c_ubyte, C.c_int] + [C.c_void_p] * 4
+    L.log_map16.restype = None
+    L.ref_crcTableInit()
+    L.ref_init_td16()
+    L.ref_init_td8()
+    _ref = L
+    return L
+
+
+# ---- helpers shared by the tests -------------------------------------------------
+
+def aligned(n, dtype, align=64):
+    """Zeroed 1-D array whose data pointer is `align`-byte aligned (the reference
+    decoders use aligned SSE loads on y)."""
+    itemsize = np.dtype(dtype).itemsize
+    raw = np.zeros(n * itemsize + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * itemsize].view(dtype)
+
+
+_STATS = None
+
+
+def _stats():
+    global _STATS
+    if _STATS is None:
+        _STATS = [np.zeros(16, dtype=np.int64) for _ in range(7)]
+    return [s.ctypes.data for s in _STATS]
+
+
+def ref_decode16(y, n, max_it, crc_type, F=0, which=16):
+    """Run the compiled reference decoder on one block; returns (bytes[n/8], ret)."""
+    L = ref()
+    yy = aligned(3 * n + 12 + 64, np.int16)      # slack: TD8 reads past the end
+    yy[:3 * n + 12] = y[:3 * n + 12]
+    out = aligned(n // 8 + 64, np.uint8)
+    fn = L.ref_phy_threegpplte_turbo_decoder16 if which == 16 else L.ref_phy_threegpplte_turbo_decoder8
+    p = port()
+    idx = p.orc_qpp_index(n)
+    f1 = p.orc_qpp_f1(idx) if idx >= 0 else 0
+    f2 = p.orc_qpp_f2(idx) if idx >= 0 else 0
+    r = fn(yy.ctypes.data, out.ctypes.data, n, f1, f2, max_it, crc_type, F, *_stats())
+    return out[:n // 8].copy(), int(r)
+
+
+def port_decode16(y, n, max_it, crc_type, F=0):
+    L = port()
+    yy = np.ascontiguousarray(y[:3 * n + 12], dtype=np.int16)
+    out = np.zeros(n // 8 + 4, dtype=np.uint8)
+    r = L.orc_turbo_decoder16(yy, out, n, max_it, crc_type, F)
+    return out[:n // 8].copy(), int(r)
