@@ -1,0 +1,167 @@
+/*
+ * oai_turbo_b200.h -- C ABI of the B200-native LTE channel-decoding engine.
+ *
+ * Drop-in boundary for the turbo-decoding hot path of OpenAirInterface
+ * (erlgo/openair4G).  Section 1 exports the reference's own entry points with the
+ * reference's exact signatures, so ulsch_decoding.c / dlsch_decoding.c link against
+ * this library instead of openair1/PHY/CODING/{3gpplte_turbo_decoder_sse_16bit.c,
+ * 3gpplte_turbo_decoder_sse_8bit.c,lte_rate_matching.c}.  Section 2 is the new
+ * batched, stream-ordered submit call that replaces the per-code-block loops
+ * (ulsch_decoding.c:1222-1369, dlsch_decoding.c:303-453).  Section 3 is the
+ * device-resident form used by the throughput harness (inputs already in HBM).
+ *
+ * All work runs on the GPU (hand-written sm_100a kernels).  There is no CPU
+ * fallback: every entry point fails loudly (return code + message on stderr) when
+ * no CUDA device is usable.
+ */
+#ifndef OAI_TURBO_B200_H
+#define OAI_TURBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same layout as the reference's x86 time_stats_t (openair1/PHY/TOOLS/time_meas.h:43-52).
+ * Callers pass seven of them to the decoder; this library never dereferences them
+ * (the reference only touches them when its global opp_enabled != 0). */
+#ifndef OAI_TIME_STATS_T_DEFINED
+#define OAI_TIME_STATS_T_DEFINED
+typedef struct {
+  long long in, diff, diff_now, p_time, diff_square, max;
+  int trials;
+} oai_time_stats_t;
+#endif
+
+#define OAI_CRC24_A 0   /* openair1/PHY/CODING/defs.h:45-48 */
+#define OAI_CRC24_B 1
+#define OAI_CRC16   2
+#define OAI_CRC8    3
+#define OAI_LTE_NULL 2  /* openair1/PHY/CODING/defs.h:53 */
+
+/* ------------------------------------------------------------------------------------
+ * 1. Reference entry points (exact signatures)
+ * ---------------------------------------------------------------------------------- */
+
+/* openair1/PHY/CODING/defs.h:362,367 ; impl 3gpplte_turbo_decoder_sse_16bit.c:886-943,
+ * 3gpplte_turbo_decoder_sse_8bit.c:834-892.  Creates the process-wide GPU context
+ * (QPP tables for the 188 block sizes in HBM, CRC tables, streams, staging buffers).
+ * Not thread-safe, call once (like the reference); the decode calls are re-entrant. */
+void init_td16(void);
+void free_td16(void);
+void init_td8(void);
+void free_td8(void);
+
+/* openair1/PHY/CODING/defs.h:470-484 ; impl 3gpplte_turbo_decoder_sse_16bit.c:945-1385.
+ * y: int16[3n+12] = (s,p1,p2) x n, then (x,z) x 3 of encoder 1 and of encoder 2.
+ * decoded_bytes: n/8 bytes, MSB first.  Returns iterations used (2..max), max+1 when the
+ * CRC never passed, 255 on crc_type > 3 or n not one of the 188 sizes.  f1/f2 are
+ * accepted and ignored, like the reference (it looks n up, :1011-1018).
+ * Bit-exact (bytes and return value) to the reference for every int16 input. */
+unsigned char phy_threegpplte_turbo_decoder16(short *y, unsigned char *decoded_bytes,
+    unsigned short n, unsigned short f1, unsigned short f2, unsigned char max_iterations,
+    unsigned char crc_type, unsigned char F,
+    oai_time_stats_t *init_stats, oai_time_stats_t *alpha_stats, oai_time_stats_t *beta_stats,
+    oai_time_stats_t *gamma_stats, oai_time_stats_t *ext_stats, oai_time_stats_t *intl1_stats,
+    oai_time_stats_t *intl2_stats);
+
+/* openair1/PHY/CODING/defs.h:499-513 ; impl 3gpplte_turbo_decoder_sse_8bit.c:894-1657.
+ * Parity domain: n >= 256 and n % 16 == 0 (outside it the reference
+ * itself overruns its buffers); other sizes return 255. */
+unsigned char phy_threegpplte_turbo_decoder8(short *y, unsigned char *decoded_bytes,
+    unsigned short n, unsigned short f1, unsigned short f2, unsigned char max_iterations,
+    unsigned char crc_type, unsigned char F,
+    oai_time_stats_t *init_stats, oai_time_stats_t *alpha_stats, oai_time_stats_t *beta_stats,
+    oai_time_stats_t *gamma_stats, oai_time_stats_t *ext_stats, oai_time_stats_t *intl1_stats,
+    oai_time_stats_t *intl2_stats);
+
+/* openair1/PHY/CODING/defs.h:152 ; impl lte_rate_matching.c:293-382.  Marks (never
+ * clears) the NULL positions of the 3*Kpi circular buffer; returns RTC. */
+uint32_t generate_dummy_w(uint32_t D, uint8_t *w, uint8_t F);
+
+/* openair1/PHY/CODING/defs.h:239-253 ; impl lte_rate_matching.c:688-831.  w is the
+ * caller-owned HARQ soft buffer (host memory, authoritative on every call): it is
+ * read, accumulated into with int16 wrap-around, and written back.  Returns 0, or -1
+ * when Kmimo, Mdlharq, C, Qm or Nl is zero. */
+int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t *w, uint8_t *dummy_w,
+    int16_t *soft_input, uint8_t C, uint32_t Nsoft, uint8_t Mdlharq, uint8_t Kmimo,
+    uint8_t rvidx, uint8_t clear, uint8_t Qm, uint8_t Nl, uint8_t r, uint32_t *E_out);
+
+/* openair1/PHY/CODING/defs.h:132 ; impl lte_rate_matching.c:193-243.  Writes d[-3*ND ..
+ * 3*D+2] (callers pass &d[r][96], dlsch_decoding.c:380). */
+void sub_block_deinterleaving_turbo(uint32_t D, int16_t *d, int16_t *w);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Batched submit (new): all code blocks of a subframe / of many subframes and cells
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct oai_turbo_batch oai_turbo_batch_t;   /* opaque, one per in-flight batch */
+
+/* One code block.  With dematch_enable == 0, `in` is the decoder input y (int16[3K+12],
+ * what the reference passes as &d[r][96]).  With dematch_enable != 0, `in` is this
+ * block's slice of the rate-matched soft bits e (int16[E]) and the fused front end
+ * (generate_dummy_w + lte_rate_matching_turbo_rx + sub_block_deinterleaving_turbo)
+ * runs on the GPU first; `w` is the host HARQ buffer int16[3*Kpi] (read unless clear,
+ * written back), may be NULL when clear != 0 and the caller does not keep it. */
+typedef struct {
+  const int16_t *in;
+  uint8_t  *decoded_bytes;     /* K/8 bytes out (host) */
+  uint8_t  *status;            /* 1 byte out: the decoder's return value */
+  uint16_t  K;
+  uint8_t   max_iterations;
+  uint8_t   crc_type;
+  uint8_t   F;
+  uint8_t   llr8;              /* 0: 16-bit decoder, 1: 8-bit decoder */
+  uint8_t   decode_enable;     /* 0: front end only (dlsch_decoding.c:417 err_flag) */
+  uint8_t   dematch_enable;
+  /* front-end parameters (lte_rate_matching_turbo_rx arguments) */
+  int16_t  *w;
+  uint32_t  G;
+  uint32_t  Nsoft;
+  uint8_t   C, r, rvidx, clear, Qm, Nl, Mdlharq, Kmimo;
+  uint32_t  tb_id;             /* blocks with equal tb_id form one transport block */
+} oai_cb_desc_t;
+
+#define OAI_BATCH_DL_STOP_AFTER_FAILURE 1u  /* dlsch_decoding.c:417,448-451: within a
+        transport block, blocks after the first failing one report status 0xFE ("not
+        decoded") and their decoded_bytes are zeroed */
+
+/* Copies descriptors and inputs to the GPU and launches the whole pipeline on the
+ * batch's stream; returns immediately (0) or a negative error.  gpu < 0: current device. */
+int oai_turbo_submit_batch(const oai_cb_desc_t *cbs, int ncb, unsigned flags, int gpu,
+                           oai_turbo_batch_t **handle);
+/* Blocks until the batch is finished, scatters decoded_bytes/status/w back to the
+ * host pointers of the descriptors and frees the handle. */
+int oai_turbo_wait(oai_turbo_batch_t *handle);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Device-resident decode (throughput mode: inputs already in HBM)
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct oai_turbo_dev_plan oai_turbo_dev_plan_t;
+
+/* Plans a batch of ncb equal-parameter code blocks whose inputs y live in device
+ * memory at y_dev + i*y_stride (int16 units), outputs at out_dev + i*out_stride bytes
+ * and status_dev[i].  Workspace is allocated once here. */
+int oai_turbo_dev_plan_create(int ncb, uint16_t K, uint8_t max_iterations, uint8_t crc_type,
+                              uint8_t llr8, oai_turbo_dev_plan_t **plan);
+/* Enqueues one full decode of the batch on `stream` (a cudaStream_t passed as void*);
+ * no host synchronisation.  Returns the number of kernels launched, or < 0. */
+int oai_turbo_dev_decode(oai_turbo_dev_plan_t *plan, const int16_t *y_dev, long y_stride,
+                         uint8_t *out_dev, long out_stride, uint8_t *status_dev, void *stream);
+void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t *plan);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Introspection
+ * ---------------------------------------------------------------------------------- */
+const char *oai_turbo_b200_version(void);
+/* last error message of the calling thread ("" if none) */
+const char *oai_turbo_b200_last_error(void);
+/* number of kernels this library has launched since load (all threads) */
+unsigned long long oai_turbo_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAI_TURBO_B200_H */

@@ -1,0 +1,163 @@
+"""ctypes mirror of include/oai_turbo_b200.h -- same names, argument meaning and return
+codes as the reference's C entry points (openair1/PHY/CODING/defs.h:132,152,239-253,362,
+367,470-484,499-513), plus the batched and device-resident calls.
+
+No CPU fallback: if the CUDA library is missing this module raises at import.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+CRC24_A, CRC24_B, CRC16, CRC8 = 0, 1, 2, 3
+LTE_NULL = 2
+STATUS_NOT_DECODED = 0xFE
+BATCH_DL_STOP_AFTER_FAILURE = 1
+
+if not os.path.exists(_build.LIB):
+    raise ImportError(
+        "openair4g_b200: CUDA library %s is not built (run `python -m openair4g_b200.build` or "
+        "__graft_entry__.build()); there is no CPU fallback" % _build.LIB)
+
+lib = C.CDLL(_build.LIB)
+LIB_PATH = _build.LIB
+
+EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_turbo_decoder16",
+           "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
+           "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
+           "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
+           "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count"]
+
+
+class CbDesc(C.Structure):
+    """oai_cb_desc_t"""
+    _fields_ = [("in_", C.c_void_p), ("decoded_bytes", C.c_void_p), ("status", C.c_void_p),
+                ("K", C.c_uint16), ("max_iterations", C.c_uint8), ("crc_type", C.c_uint8),
+                ("F", C.c_uint8), ("llr8", C.c_uint8), ("decode_enable", C.c_uint8),
+                ("dematch_enable", C.c_uint8), ("w", C.c_void_p), ("G", C.c_uint32),
+                ("Nsoft", C.c_uint32), ("C", C.c_uint8), ("r", C.c_uint8), ("rvidx", C.c_uint8),
+                ("clear", C.c_uint8), ("Qm", C.c_uint8), ("Nl", C.c_uint8), ("Mdlharq", C.c_uint8),
+                ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32)]
+
+
+_stats7 = [C.c_void_p] * 7
+for _f in ("phy_threegpplte_turbo_decoder16", "phy_threegpplte_turbo_decoder8"):
+    getattr(lib, _f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint8,
+                                 C.c_uint8, C.c_uint8] + _stats7
+    getattr(lib, _f).restype = C.c_uint8
+lib.generate_dummy_w.argtypes = [C.c_uint32, C.c_void_p, C.c_uint8]
+lib.generate_dummy_w.restype = C.c_uint32
+lib.lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint8,
+                                           C.c_uint32] + [C.c_uint8] * 7 + [C.POINTER(C.c_uint32)]
+lib.lte_rate_matching_turbo_rx.restype = C.c_int
+lib.sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+lib.sub_block_deinterleaving_turbo.restype = None
+lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
+lib.oai_turbo_wait.argtypes = [C.c_void_p]
+lib.oai_turbo_dev_plan_create.argtypes = [C.c_int, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.POINTER(C.c_void_p)]
+lib.oai_turbo_dev_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+lib.oai_turbo_dev_plan_destroy.argtypes = [C.c_void_p]
+lib.oai_turbo_dev_plan_destroy.restype = None
+lib.oai_turbo_b200_version.restype = C.c_char_p
+lib.oai_turbo_b200_last_error.restype = C.c_char_p
+lib.oai_turbo_b200_launch_count.restype = C.c_ulonglong
+
+
+def last_error():
+    return lib.oai_turbo_b200_last_error().decode()
+
+
+def launch_count():
+    return int(lib.oai_turbo_b200_launch_count())
+
+
+def init_td16():
+    lib.init_td16()
+
+
+def init_td8():
+    lib.init_td8()
+
+
+def _decode_one(fn, y, n, f1, f2, max_iterations, crc_type, F, decoded_bytes):
+    y = np.ascontiguousarray(y, dtype=np.int16)
+    assert y.size >= 3 * n + 12
+    if decoded_bytes is None:
+        decoded_bytes = np.zeros(n // 8 + 4, dtype=np.uint8)
+    ret = fn(y.ctypes.data, decoded_bytes.ctypes.data, n, f1, f2, max_iterations, crc_type, F, *([None] * 7))
+    return int(ret), decoded_bytes[: n // 8]
+
+
+def phy_threegpplte_turbo_decoder16(y, n, f1=0, f2=0, max_iterations=4, crc_type=CRC24_B, F=0, decoded_bytes=None):
+    """Returns (ret, decoded_bytes[n/8]); ret as the reference: iterations used, max+1 on
+    failure, 255 on illegal arguments."""
+    return _decode_one(lib.phy_threegpplte_turbo_decoder16, y, n, f1, f2, max_iterations, crc_type, F, decoded_bytes)
+
+
+def phy_threegpplte_turbo_decoder8(y, n, f1=0, f2=0, max_iterations=4, crc_type=CRC24_B, F=0, decoded_bytes=None):
+    return _decode_one(lib.phy_threegpplte_turbo_decoder8, y, n, f1, f2, max_iterations, crc_type, F, decoded_bytes)
+
+
+def decode_batch(blocks, flags=0, gpu=-1):
+    """blocks: list of dicts {y, K, max_iterations, crc_type, F=0, tb_id=0, llr8=0, decode_enable=1}.
+    One submit + wait; returns (list of uint8 arrays, list of status ints)."""
+    n = len(blocks)
+    descs = (CbDesc * n)()
+    keep, outs = [], []
+    status = np.full(n, 255, dtype=np.uint8)
+    for i, b in enumerate(blocks):
+        y = np.ascontiguousarray(b["y"], dtype=np.int16)
+        out = np.zeros(b["K"] // 8 + 4, dtype=np.uint8)
+        keep.append(y)
+        outs.append(out)
+        d = descs[i]
+        d.in_ = y.ctypes.data
+        d.decoded_bytes = out.ctypes.data
+        d.status = status.ctypes.data + i
+        d.K = b["K"]
+        d.max_iterations = b["max_iterations"]
+        d.crc_type = b["crc_type"]
+        d.F = b.get("F", 0)
+        d.llr8 = b.get("llr8", 0)
+        d.decode_enable = b.get("decode_enable", 1)
+        d.tb_id = b.get("tb_id", 0)
+    h = C.c_void_p()
+    rc = lib.oai_turbo_submit_batch(descs, n, flags, gpu, C.byref(h))
+    if rc != 0:
+        raise RuntimeError("oai_turbo_submit_batch failed (%d): %s" % (rc, last_error()))
+    if h.value:
+        rc = lib.oai_turbo_wait(h)
+        if rc != 0:
+            raise RuntimeError("oai_turbo_wait failed (%d): %s" % (rc, last_error()))
+    return [o[: b["K"] // 8] for o, b in zip(outs, blocks)], [int(s) for s in status]
+
+
+class DevPlan:
+    """Device-resident batch of equal-K code blocks (throughput mode).  Pointers are raw
+    device addresses (e.g. torch tensor .data_ptr()), stream a cudaStream_t handle."""
+
+    def __init__(self, ncb, K, max_iterations, crc_type, llr8=0):
+        self._h = C.c_void_p()
+        rc = lib.oai_turbo_dev_plan_create(ncb, K, max_iterations, crc_type, llr8, C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("oai_turbo_dev_plan_create failed (%d): %s" % (rc, last_error()))
+        self.ncb, self.K = ncb, K
+
+    def decode(self, y_ptr, y_stride, out_ptr, out_stride, status_ptr, stream=0):
+        rc = lib.oai_turbo_dev_decode(self._h, y_ptr, y_stride, out_ptr, out_stride, status_ptr, stream)
+        if rc < 0:
+            raise RuntimeError("oai_turbo_dev_decode failed (%d): %s" % (rc, last_error()))
+        return rc
+
+    def close(self):
+        if self._h:
+            lib.oai_turbo_dev_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,455 @@
+// Host side of the B200 LTE turbo-decoding engine: GPU context, batch plans, and the C ABI
+// declared in include/oai_turbo_b200.h.  No torch, no CPU compute path: every entry point
+// launches the sm_100a kernels in td16_map.cuh / td16_xchg.cuh (and friends) or fails.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/oai_turbo_b200.h"
+#include "td_common.cuh"
+#include "td16_map.cuh"
+#include "td16_xchg.cuh"
+
+namespace oai {
+
+static const uint16_t kQpp[188][2] = {
+#include "qpp_table.inc"
+};
+
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "[oai_turbo_b200] ERROR: %s\n", g_err);
+  return code;
+}
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) return fail(-100, "%s -> %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// K -> row of the 188-entry table (same bucketing as dlsch_decoding.c:314-325); -1 if illegal
+static int qpp_index(int K) {
+  if (K < 40 || K > 6144 || (K & 7)) return -1;
+  int kb = K >> 3;
+  if (kb <= 64) return kb - 5;
+  if (kb <= 128) return (K & 15) ? -1 : 59 + ((kb - 64) >> 1);
+  if (kb <= 256) return (K & 31) ? -1 : 91 + ((kb - 128) >> 2);
+  return (K & 63) ? -1 : 123 + ((kb - 256) >> 3);
+}
+static int qpp_K(int idx) {
+  if (idx < 60) return 40 + 8 * idx;
+  if (idx < 92) return 512 + 16 * (idx - 59);
+  if (idx < 124) return 1024 + 32 * (idx - 91);
+  return 2048 + 64 * (idx - 123);
+}
+
+// ---- per-device context: read-only tables ------------------------------------------
+struct DevCtx {
+  int dev = -1;
+  uint16_t* pi_pool = nullptr;        // all 188 QPP tables, ascending K
+  uint32_t pi_off[188];
+  u32* crc_xp = nullptr;              // [4][768]
+  bool ok = false;
+};
+static DevCtx g_ctx[16];
+static std::mutex g_ctx_mu;
+
+static u32 gf_xtimes(u32 r, u32 poly, int w) {
+  u32 top = r & (1u << (w - 1));
+  r = (r << 1) & ((w == 32) ? 0xffffffffu : ((1u << w) - 1));
+  return top ? (r ^ poly) : r;
+}
+
+static int ctx_get(int dev, DevCtx** out) {
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= 16) return fail(-2, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DevCtx& c = g_ctx[dev];
+  if (!c.ok) {
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
+    CU(cudaSetDevice(dev));
+    std::vector<uint16_t> pool;
+    for (int i = 0; i < 188; ++i) {
+      int K = qpp_K(i);
+      c.pi_off[i] = (uint32_t)pool.size();
+      uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
+      for (uint64_t j = 0; j < (uint64_t)K; ++j) pool.push_back((uint16_t)((f1 * j + f2 * j * j) % (uint64_t)K));
+    }
+    CU(cudaMalloc(&c.pi_pool, pool.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(c.pi_pool, pool.data(), pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    // x^(8m+w) mod P for the four CRCs (polynomials: crc_byte.c:53-57)
+    std::vector<u32> xp(4 * 768);
+    const u32 polys[4] = {0x864cfbu, 0x800063u, 0x1021u, 0x9Bu};
+    const int ws[4] = {24, 24, 16, 8};
+    for (int t = 0; t < 4; ++t) {
+      u32 r = 1;
+      for (int i = 0; i < ws[t]; ++i) r = gf_xtimes(r, polys[t], ws[t]);    // x^w
+      for (int m = 0; m < 768; ++m) {
+        xp[t * 768 + m] = r;
+        for (int i = 0; i < 8; ++i) r = gf_xtimes(r, polys[t], ws[t]);
+      }
+    }
+    CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
+    CU(cudaMemcpy(c.crc_xp, xp.data(), xp.size() * sizeof(u32), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(k_map16<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * MAP_THREADS * 16));
+    c.dev = dev;
+    c.ok = true;
+    CU(cudaSetDevice(prev));
+  }
+  *out = &c;
+  return 0;
+}
+
+// ---- a batch of code blocks resident on one GPU ---------------------------------------
+constexpr int CKPT_S = 16;
+constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
+
+struct Batch {
+  DevCtx* ctx = nullptr;
+  int cap = 0, n = 0, A = 0, max_iter = 0;
+  long slot_hw = 0, ckpt_words = 0;
+  CbMeta* d_meta = nullptr;
+  CbState* d_state = nullptr;
+  int16_t* d_ws = nullptr;
+  u32* d_ckpt = nullptr;
+  std::vector<CbMeta> h_meta;
+
+  int alloc(DevCtx* c, int ncb, int Kmax) {
+    ctx = c;
+    cap = ncb;
+    int W = Kmax / 8;
+    A = c4_words(W) * 2;
+    slot_hw = (long)ARR_COUNT * A;
+    ckpt_words = (long)((W + CKPT_S - 1) / CKPT_S + 1) * 32;
+    CU(cudaMalloc(&d_meta, sizeof(CbMeta) * ncb));
+    CU(cudaMalloc(&d_state, sizeof(CbState) * ncb));
+    CU(cudaMalloc(&d_ws, sizeof(int16_t) * slot_hw * ncb));
+    CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
+    CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
+    CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
+    return 0;
+  }
+  void release() {
+    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt);
+    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr;
+  }
+  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
+    h_meta = m;
+    n = (int)m.size();
+    max_iter = 0;
+    for (auto& x : m) if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter);
+    CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  // enqueue the whole 16-bit decode; returns #kernels launched or <0
+  int decode16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
+    int launches = 0;
+    XchgArgs x;
+    x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
+    x.pi_pool = ctx->pi_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
+    x.status_out = status_dev; x.iter = 0;
+    MapArgs mp;
+    mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
+    mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B;
+    const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
+    const size_t map_smem = (size_t)CKPT_S * 2 * MAP_THREADS * 16;
+    auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter) {
+      mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter;
+      k_map16<CKPT_S><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
+      ++launches;
+    };
+    k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
+    ++launches;
+    map(ARR_S0, ARR_P1, ARR_EXT, 0, 1);                          // reference :1199
+    for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
+      x.iter = it;
+      k_x1_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it);                     // :1236
+      k_x2_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      launches += 2;
+      if (it < max_iter) map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1);   // :1354-1356
+    }
+    g_launches += launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-101, "kernel launch failed: %s", cudaGetErrorString(e));
+    return launches;
+  }
+};
+
+static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long in_off, long out_off, CbMeta* m) {
+  int idx = qpp_index(K);
+  if (idx < 0) return -1;
+  m->K = (uint16_t)K; m->W = (uint16_t)(K >> 3);
+  m->max_iter = (uint8_t)max_it; m->crc_type = (uint8_t)crc; m->F = (uint8_t)F; m->flags = dec ? 1 : 0;
+  m->pi_off = c->pi_off[idx];
+  m->in_off_lo = (uint32_t)((unsigned long long)in_off & 0xffffffffu);
+  m->in_off_hi = (uint32_t)((unsigned long long)in_off >> 32);
+  m->out_off = (uint32_t)out_off;
+  return 0;
+}
+
+
+// ---- host-buffer batches: pinned staging + one stream per batch object ---------------
+struct HostBatch {
+  Batch b;
+  cudaStream_t st = nullptr;
+  int dev = -1;
+  int cap_blocks = 0, cap_K = 0;
+  size_t cap_in = 0, cap_out = 0;
+  int16_t* h_in = nullptr;  int16_t* d_in = nullptr;
+  uint8_t* h_out = nullptr; uint8_t* d_out = nullptr;
+  uint8_t* h_status = nullptr; uint8_t* d_status = nullptr;
+  // bookkeeping of the submitted batch
+  std::vector<oai_cb_desc_t> descs;
+  std::vector<int> order;          // GPU block i <-> descriptor order[i]
+  std::vector<uint32_t> out_off;
+  unsigned flags = 0;
+
+  int ensure(int gpu, int nblk, int Kmax, size_t in_hw, size_t out_bytes) {
+    DevCtx* c;
+    int rc = ctx_get(gpu, &c);
+    if (rc) return rc;
+    if (dev != c->dev) { release(); dev = c->dev; }
+    CU(cudaSetDevice(dev));
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (nblk > cap_blocks || Kmax > cap_K) {
+      b.release();
+      cap_blocks = std::max(nblk, cap_blocks); cap_K = std::max(Kmax, cap_K);
+      rc = b.alloc(c, cap_blocks, cap_K);
+      if (rc) return rc;
+      if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); }
+      CU(cudaMallocHost(&h_status, cap_blocks));
+      CU(cudaMalloc(&d_status, cap_blocks));
+    }
+    b.ctx = c;
+    if (in_hw > cap_in) {
+      if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); }
+      cap_in = in_hw;
+      CU(cudaMallocHost(&h_in, cap_in * sizeof(int16_t)));
+      CU(cudaMalloc(&d_in, cap_in * sizeof(int16_t)));
+    }
+    if (out_bytes > cap_out) {
+      if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); }
+      cap_out = out_bytes;
+      CU(cudaMallocHost(&h_out, cap_out));
+      CU(cudaMalloc(&d_out, cap_out));
+    }
+    return 0;
+  }
+  void release() {
+    b.release();
+    if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); h_in = nullptr; d_in = nullptr; }
+    if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); h_out = nullptr; d_out = nullptr; }
+    if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
+    if (st) { cudaStreamDestroy(st); st = nullptr; }
+    cap_blocks = cap_K = 0; cap_in = cap_out = 0;
+  }
+
+  int submit(const oai_cb_desc_t* cbs, int ncb, unsigned fl, int gpu) {
+    descs.assign(cbs, cbs + ncb);
+    flags = fl;
+    order.clear();
+    int Kmax = 40;
+    for (int i = 0; i < ncb; ++i) {
+      const oai_cb_desc_t& d = descs[i];
+      if (d.crc_type > 3 || qpp_index(d.K) < 0) { if (d.status) *d.status = 255; continue; }   // TD16:1003-1018
+      if (d.llr8) return fail(-3, "8-bit decoder not built yet");
+      if (d.dematch_enable) return fail(-3, "fused dematch front end not built yet");
+      if (!d.decode_enable) { if (d.status) *d.status = 0xFE; continue; }
+      order.push_back(i);
+      Kmax = std::max<int>(Kmax, d.K);
+    }
+    // equal-K blocks next to each other: a warp of the MAP kernel carries 8 blocks
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return descs[a].K < descs[c].K; });
+    const int n = (int)order.size();
+    if (n == 0) return 0;
+    size_t in_hw = 0, out_b = 0;
+    std::vector<size_t> in_off(n);
+    out_off.resize(n);
+    for (int i = 0; i < n; ++i) {
+      const oai_cb_desc_t& d = descs[order[i]];
+      in_off[i] = in_hw;  in_hw += ((size_t)3 * d.K + 12 + 7) & ~(size_t)7;
+      out_off[i] = (uint32_t)out_b; out_b += ((size_t)(d.K >> 3) + 15) & ~(size_t)15;
+    }
+    int rc = ensure(gpu, n, Kmax, in_hw, out_b);
+    if (rc) return rc;
+    std::vector<CbMeta> meta(n);
+    for (int i = 0; i < n; ++i) {
+      const oai_cb_desc_t& d = descs[order[i]];
+      memcpy(h_in + in_off[i], d.in, sizeof(int16_t) * (3 * (size_t)d.K + 12));
+      make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, 1, (long)in_off[i], (long)out_off[i], &meta[i]);
+    }
+    CU(cudaMemcpyAsync(d_in, h_in, in_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    rc = b.set_meta(meta, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(d_out, 0, out_b, st));
+    rc = b.decode16(d_in, d_out, d_status, st);
+    if (rc < 0) return rc;
+    CU(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+
+  int wait() {
+    const int n = (int)order.size();
+    if (n) CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+      const oai_cb_desc_t& d = descs[order[i]];
+      // the reference leaves decoded_bytes untouched when max_iterations < 2 (no hard decision, TD16:1267)
+      if (d.decoded_bytes && d.max_iterations >= 2) memcpy(d.decoded_bytes, h_out + out_off[i], d.K >> 3);
+      if (d.status) *d.status = h_status[i];
+    }
+    if (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) {
+      // dlsch_decoding.c:400,417,448-451: after the first failing block of a transport block the
+      // remaining ones are not decoded and their c[r] stays zeroed
+      for (size_t i = 0; i < descs.size(); ++i) {
+        const oai_cb_desc_t& d = descs[i];
+        if (!d.status) continue;
+        bool after_fail = false;
+        for (size_t j = 0; j < i; ++j)
+          if (descs[j].tb_id == d.tb_id && descs[j].status && *descs[j].status != 0xFE &&
+              *descs[j].status >= 1 + descs[j].max_iterations) { after_fail = true; break; }
+        if (after_fail) { *d.status = 0xFE; if (d.decoded_bytes) memset(d.decoded_bytes, 0, d.K >> 3); }
+      }
+    }
+    return 0;
+  }
+};
+
+}  // namespace oai
+
+using namespace oai;
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+struct oai_turbo_dev_plan {
+  Batch b;
+  int ncb; uint16_t K; uint8_t max_it, crc, llr8;
+  long y_stride = -1, out_stride = -1;
+};
+
+extern "C" {
+
+const char* oai_turbo_b200_version(void) { return "oai_turbo_b200 0.1 (sm_100a)"; }
+const char* oai_turbo_b200_last_error(void) { return g_err; }
+unsigned long long oai_turbo_b200_launch_count(void) { return g_launches.load(); }
+
+int oai_turbo_dev_plan_create(int ncb, uint16_t K, uint8_t max_iterations, uint8_t crc_type, uint8_t llr8,
+                              oai_turbo_dev_plan_t** plan) {
+  if (!plan || ncb <= 0) return fail(-1, "bad arguments");
+  if (llr8) return fail(-3, "8-bit decoder not built yet");
+  if (qpp_index(K) < 0 || crc_type > 3) return fail(-1, "illegal K=%d or crc_type=%d", (int)K, (int)crc_type);
+  DevCtx* c;
+  int rc = ctx_get(-1, &c);
+  if (rc) return rc;
+  oai_turbo_dev_plan* p = new oai_turbo_dev_plan();
+  p->ncb = ncb; p->K = K; p->max_it = max_iterations; p->crc = crc_type; p->llr8 = llr8;
+  rc = p->b.alloc(c, ncb, K);
+  if (rc) { p->b.release(); delete p; return rc; }
+  *plan = p;
+  return 0;
+}
+
+int oai_turbo_dev_decode(oai_turbo_dev_plan_t* p, const int16_t* y_dev, long y_stride, uint8_t* out_dev,
+                         long out_stride, uint8_t* status_dev, void* stream) {
+  if (!p) return fail(-1, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->y_stride != y_stride || p->out_stride != out_stride) {
+    std::vector<CbMeta> m(p->ncb);
+    for (int i = 0; i < p->ncb; ++i)
+      make_meta(p->b.ctx, p->K, p->max_it, p->crc, 0, 1, (long)i * y_stride, (long)i * out_stride, &m[i]);
+    int rc = p->b.set_meta(m, st);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));      // h_meta is pageable; done once per plan
+    p->y_stride = y_stride; p->out_stride = out_stride;
+  }
+  return p->b.decode16(y_dev, out_dev, status_dev, st);
+}
+
+
+struct oai_turbo_batch { HostBatch hb; };
+
+int oai_turbo_submit_batch(const oai_cb_desc_t* cbs, int ncb, unsigned flags, int gpu, oai_turbo_batch_t** handle) {
+  if (!cbs || ncb <= 0 || !handle) return fail(-1, "bad arguments");
+  oai_turbo_batch* h = new oai_turbo_batch();
+  int rc = h->hb.submit(cbs, ncb, flags, gpu);
+  if (rc) { h->hb.release(); delete h; return rc; }
+  *handle = h;
+  return 0;
+}
+
+int oai_turbo_wait(oai_turbo_batch_t* h) {
+  if (!h) return fail(-1, "null handle");
+  int rc = h->hb.wait();
+  h->hb.release();
+  delete h;
+  return rc;
+}
+
+void init_td16(void) {
+  DevCtx* c;
+  if (ctx_get(-1, &c)) fprintf(stderr, "[oai_turbo_b200] init_td16: no usable CUDA device -- decoder calls will fail\n");
+}
+void free_td16(void) {}
+void init_td8(void) { init_td16(); }
+void free_td8(void) {}
+
+// one cached single-block batch per calling thread: the call is re-entrant like the reference
+// (all scratch is per call there, TD16:967-979) and pays no allocation after the first use
+static thread_local HostBatch* t_single = nullptr;
+
+unsigned char phy_threegpplte_turbo_decoder16(short* y, unsigned char* decoded_bytes, unsigned short n,
+    unsigned short f1, unsigned short f2, unsigned char max_iterations, unsigned char crc_type, unsigned char F,
+    oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*,
+    oai_time_stats_t*, oai_time_stats_t*) {
+  (void)f1; (void)f2;
+  if (crc_type > 3) { fprintf(stderr, "Illegal crc length!\n"); return 255; }          // TD16:1003-1006
+  if (qpp_index(n) < 0) { fprintf(stderr, "Illegal frame length!\n"); return 255; }    // TD16:1015-1018
+  if (!t_single) t_single = new HostBatch();
+  oai_cb_desc_t d;
+  memset(&d, 0, sizeof(d));
+  uint8_t status = 255;
+  d.in = y; d.decoded_bytes = decoded_bytes; d.status = &status; d.K = n; d.max_iterations = max_iterations;
+  d.crc_type = crc_type; d.F = F; d.decode_enable = 1;
+  if (t_single->submit(&d, 1, 0, -1) || t_single->wait()) {
+    fprintf(stderr, "[oai_turbo_b200] phy_threegpplte_turbo_decoder16: GPU path failed (%s); there is no CPU fallback\n", g_err);
+    return 255;
+  }
+  return status;
+}
+
+unsigned char phy_threegpplte_turbo_decoder8(short*, unsigned char*, unsigned short, unsigned short, unsigned short,
+    unsigned char, unsigned char, unsigned char, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*,
+    oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*) {
+  fail(-3, "phy_threegpplte_turbo_decoder8: 8-bit decoder not built yet");
+  return 255;
+}
+
+uint32_t generate_dummy_w(uint32_t, uint8_t*, uint8_t) { fail(-3, "generate_dummy_w: not built yet"); return 0; }
+int lte_rate_matching_turbo_rx(uint32_t, uint32_t, int16_t*, uint8_t*, int16_t*, uint8_t, uint32_t, uint8_t, uint8_t,
+                               uint8_t, uint8_t, uint8_t, uint8_t, uint8_t, uint32_t*) {
+  return fail(-3, "lte_rate_matching_turbo_rx: not built yet");
+}
+void sub_block_deinterleaving_turbo(uint32_t, int16_t*, int16_t*) { fail(-3, "sub_block_deinterleaving_turbo: not built yet"); }
+
+void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t* p) {
+  if (!p) return;
+  p->b.release();
+  delete p;
+}
+
+}  // extern "C"

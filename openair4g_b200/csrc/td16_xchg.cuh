@@ -1,0 +1,274 @@
+// Per-block exchange kernels of the 16-bit decoder: one CTA per code block, arrays staged
+// in shared memory so that every HBM access is a coalesced 128-bit load/store and the
+// QPP permutation happens on chip.
+//
+//   k_demux16 : y (s,p1,p2 triples + 12 tail LLRs) -> S0/P1/P2 in C4 lane layout, tail
+//               metrics for the beta start of lane 7, max|y|
+//               (reference: 3gpplte_turbo_decoder_sse_16bit.c:1055-1189, 474-520)
+//   k_x1_16   : [ext = (ext (-) s1) (+) s0 ;] s2 = ext o pi            (:1354-1375, 1209-1231)
+//   k_x2_16   : s1 = (ext2 o pi^-1 (-) ext) (+) s0 ; hard decision, CRC, early exit
+//               (:1241-1351)
+// (+)/(-) are int16 saturating, always computed exactly here (SatArith) -- only the MAP
+// recursions have a guarded non-saturating fast path.
+#pragma once
+#include "td_common.cuh"
+
+namespace oai {
+
+constexpr int XCHG_THREADS = 256;
+
+struct XchgArgs {
+  const CbMeta* meta;
+  CbState* state;
+  int16_t* ws;
+  long slot_hw;
+  int A;                        // halfwords per array (multiple of 32)
+  int nblk;
+  const uint16_t* pi_pool;      // QPP tables, pi[i] = (f1*i + f2*i*i) mod K
+  const u32* crc_xp;            // [4][768]: x^(8m+w) mod P, per CRC type
+  const int16_t* in_base;       // batch input (device)
+  uint8_t* out_base;            // batch output (device)
+  uint8_t* status_out;          // batch status bytes (device), written when a block finishes
+  int iter;                     // iteration_cnt of the reference loop (1..max)
+};
+
+__device__ __forceinline__ int blk_max_reduce(int v, int* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int x = (threadIdx.x < (XCHG_THREADS >> 5)) ? red[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (threadIdx.x == 0) red[0] = x;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ int absmax2(u32 x) { return max(abs(lo16(x)), abs(hi16(x))); }
+
+// position p -> halfword index in the C4 layout; magic = floor(2^32/W)+1
+__device__ __forceinline__ int pos_hw(int p, int W, u32 magic) {
+  int lane = (int)__umulhi((u32)p, magic);
+  return c4_hw(p - lane * W, lane);
+}
+
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
+  extern __shared__ int16_t sm[];
+  __shared__ int red[XCHG_THREADS / 32];
+  const int blk = blockIdx.x;
+  if (blk >= p.nblk) return;
+  const CbMeta m = p.meta[blk];
+  CbState* st = &p.state[blk];
+  if (!(m.flags & 1)) { if (threadIdx.x == 0) st->status = 0xFE; return; }
+  const int K = m.K, W = m.W, A = p.A;
+  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  const int16_t* y = p.in_base + (((long)m.in_off_hi << 32) | m.in_off_lo);
+  int16_t* s0 = sm, *p1 = sm + A, *p2 = sm + 2 * A;
+  for (int i = threadIdx.x; i < 3 * A / 2; i += XCHG_THREADS) reinterpret_cast<u32*>(sm)[i] = 0;
+  __syncthreads();
+  int mx = 0;
+  for (int i = threadIdx.x; i < 3 * K + 12; i += XCHG_THREADS) {
+    int v = y[i];
+    mx = max(mx, abs(v));
+    if (i < 3 * K) {
+      int pos = i / 3, c = i - 3 * pos;
+      int h = pos_hw(pos, W, magic);
+      (c == 0 ? s0 : (c == 1 ? p1 : p2))[h] = (int16_t)v;
+    }
+  }
+  __syncthreads();
+  int16_t* slot = p.ws + (long)blk * p.slot_hw;
+  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
+    reinterpret_cast<uint4*>(slot + (long)ARR_S0 * A)[i] = reinterpret_cast<uint4*>(s0)[i];
+    reinterpret_cast<uint4*>(slot + (long)ARR_P1 * A)[i] = reinterpret_cast<uint4*>(p1)[i];
+    reinterpret_cast<uint4*>(slot + (long)ARR_P2 * A)[i] = reinterpret_cast<uint4*>(p2)[i];
+  }
+  mx = blk_max_reduce(mx, red);
+  if (threadIdx.x < 2) {
+    // tail-bit beta start metrics in WRAPPING int16 (reference :474-520); the gamma of
+    // the tail uses the saturating add/sub + >>1 of compute_gamma16 (:160-161)
+    const int16_t* tl = y + 3 * K + 6 * threadIdx.x;       // (x,z) x 3 of encoder 1 / 2
+    int16_t m11[3], m10[3];
+    for (int i = 0; i < 3; ++i) {
+      m11[i] = (int16_t)(sat16i((int)tl[2 * i] + tl[2 * i + 1]) >> 1);
+      m10[i] = (int16_t)(sat16i((int)tl[2 * i] - tl[2 * i + 1]) >> 1);
+    }
+    int16_t b0 = (int16_t)(-m11[2]), b1 = m11[2];
+    int16_t b0_2 = (int16_t)(b0 - m11[1]), b1_2 = (int16_t)(b0 + m11[1]);
+    int16_t b2_2 = (int16_t)(b1 + m10[1]), b3_2 = (int16_t)(b1 - m10[1]);
+    int16_t t[8];
+    t[0] = (int16_t)(b0_2 - m11[0]); t[1] = (int16_t)(b0_2 + m11[0]);
+    t[2] = (int16_t)(b1_2 + m10[0]); t[3] = (int16_t)(b1_2 - m10[0]);
+    t[4] = (int16_t)(b2_2 - m10[0]); t[5] = (int16_t)(b2_2 + m10[0]);
+    t[6] = (int16_t)(b3_2 + m11[0]); t[7] = (int16_t)(b3_2 - m11[0]);
+    int16_t bm = t[0];
+    for (int i = 1; i < 8; ++i) bm = (bm > t[i]) ? bm : t[i];
+    for (int i = 0; i < 8; ++i) st->T[threadIdx.x][i] = (int16_t)(t[i] - bm);
+  }
+  if (threadIdx.x == 0) {
+    st->max_in = mx;
+    st->max_sys = mx;
+    // `while (iteration_cnt++ < max_iterations)` with max 0 returns 1 (reference :1201,1384)
+    st->status = (m.max_iter == 0) ? 1 : 0;
+    if (m.max_iter == 0 && p.status_out) p.status_out[blk] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
+  extern __shared__ int16_t sm[];
+  __shared__ int red[XCHG_THREADS / 32];
+  const int blk = blockIdx.x;
+  if (blk >= p.nblk) return;
+  const CbMeta m = p.meta[blk];
+  CbState* st = &p.state[blk];
+  if (st->status != 0 || p.iter > m.max_iter) return;
+  const int K = m.K, W = m.W, A = p.A;
+  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  int16_t* slot = p.ws + (long)blk * p.slot_hw;
+  uint4* gext = reinterpret_cast<uint4*>(slot + (long)ARR_EXT * A);
+  uint4* gsys = reinterpret_cast<uint4*>(slot + (long)ARR_SYS * A);
+  const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)ARR_S0 * A);
+  int16_t* in = sm, *out = sm + A;
+  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
+    uint4 e = gext[i];
+    if (p.iter > 1) {           // ext = (ext (-) s1) (+) s0, reference :1354-1375
+      uint4 s1 = gsys[i], s0 = gs0[i];
+      e.x = __vaddss2(__vsubss2(e.x, s1.x), s0.x);
+      e.y = __vaddss2(__vsubss2(e.y, s1.y), s0.y);
+      e.z = __vaddss2(__vsubss2(e.z, s1.z), s0.z);
+      e.w = __vaddss2(__vsubss2(e.w, s1.w), s0.w);
+      gext[i] = e;
+    }
+    reinterpret_cast<uint4*>(in)[i] = e;
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const uint16_t* pi = p.pi_pool + m.pi_off;
+  int mx = 0;
+  for (int i = threadIdx.x; i < K; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
+    int v = in[pos_hw(pi[i], W, magic)];
+    out[pos_hw(i, W, magic)] = (int16_t)v;
+    mx = max(mx, abs(v));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) gsys[i] = reinterpret_cast<uint4*>(out)[i];
+  mx = blk_max_reduce(mx, red);
+  if (threadIdx.x == 0) st->max_sys = mx;
+}
+
+// ------------------------------------------------------------------------------------
+// GF(2) helpers for the parallel CRC: registers are right-aligned w-bit values.
+__device__ __forceinline__ u32 crc_byte_times(u32 byte, u32 xp, u32 poly, u32 topbit, u32 mask) {
+  // byte(x) * xp mod P, Horner over the 8 bits (MSB first)
+  u32 r = 0;
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {
+    r = ((r << 1) & mask) ^ ((r & topbit) ? poly : 0u);
+    if ((byte >> j) & 1u) r ^= xp;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
+  extern __shared__ int16_t sm[];
+  __shared__ int red[XCHG_THREADS / 32];
+  __shared__ u32 xred[XCHG_THREADS / 32];
+  __shared__ uint8_t sbytes[768 + 8];
+  const int blk = blockIdx.x;
+  if (blk >= p.nblk) return;
+  const CbMeta m = p.meta[blk];
+  CbState* st = &p.state[blk];
+  if (st->status != 0 || p.iter > m.max_iter) return;
+  const int K = m.K, W = m.W, A = p.A;
+  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  int16_t* slot = p.ws + (long)blk * p.slot_hw;
+  const uint4* gext2 = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT2 * A);
+  const uint4* gext = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT * A);
+  const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)ARR_S0 * A);
+  uint4* gsys = reinterpret_cast<uint4*>(slot + (long)ARR_SYS * A);
+  int16_t* in = sm, *nat = sm + A;
+  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
+    reinterpret_cast<uint4*>(in)[i] = gext2[i];
+    reinterpret_cast<uint4*>(nat)[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const uint16_t* pi = p.pi_pool + m.pi_off;
+  for (int i = threadIdx.x; i < K; i += XCHG_THREADS)        // ext2 back to natural order
+    nat[pos_hw(pi[i], W, magic)] = in[pos_hw(i, W, magic)];
+  __syncthreads();
+  int mx = 0;
+  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {   // s1 = (ext2 (-) ext) (+) s0, :1241-1265
+    uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i], r;
+    r.x = __vaddss2(__vsubss2(d.x, e.x), s0.x);
+    r.y = __vaddss2(__vsubss2(d.y, e.y), s0.y);
+    r.z = __vaddss2(__vsubss2(d.z, e.z), s0.z);
+    r.w = __vaddss2(__vsubss2(d.w, e.w), s0.w);
+    gsys[i] = r;
+    mx = max(max(mx, absmax2(r.x)), max(max(absmax2(r.y), absmax2(r.z)), absmax2(r.w)));
+  }
+  mx = blk_max_reduce(mx, red);
+  if (threadIdx.x == 0) st->max_sys = mx;
+
+  bool pass = false;
+  if (p.iter > 1) {                                            // :1267-1351
+    const int nb = K >> 3;
+    uint8_t* outp = p.out_base + m.out_off;
+    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) {     // bit = ext2 > 0, MSB first
+      u32 v = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v = (v << 1) | (nat[pos_hw(8 * b + q, W, magic)] > 0 ? 1u : 0u);
+      sbytes[b] = (uint8_t)v;
+      outp[b] = (uint8_t)v;
+    }
+    __syncthreads();
+    // CRC over `bits` bits starting at byte f0 (CRC24A skips the F filler bits, :1312-1313)
+    const int ct = m.crc_type;
+    const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
+    const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
+    const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
+    const int f0 = (ct == 0) ? (m.F >> 3) : 0;
+    const int bits = K - w - ((ct == 0) ? m.F : 0);
+    const int full = bits >> 3, resbit = bits & 7;
+    const u32* xp = p.crc_xp + ct * 768;
+    u32 acc = 0;
+    for (int b = threadIdx.x; b < full; b += XCHG_THREADS)
+      acc ^= crc_byte_times(sbytes[f0 + b], xp[full - 1 - b], poly, topbit, mask);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) xred[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 crc = 0;
+      for (int i = 0; i < XCHG_THREADS / 32; ++i) crc ^= xred[i];
+      for (int j = 0; j < resbit; ++j) {                       // residual bits, crc_byte.c:130-131
+        u32 bit = (sbytes[f0 + full] >> (7 - j)) & 1u;
+        u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
+        crc = (crc << 1) & mask;
+        if (top) crc ^= poly;
+      }
+      u32 old;
+      if (w == 24) old = ((u32)sbytes[nb - 3] << 16) | ((u32)sbytes[nb - 2] << 8) | sbytes[nb - 1];
+      else if (w == 16) old = ((u32)sbytes[nb - 1] << 8) | sbytes[nb - 2];   // no byte swap, :1329-1333
+      else old = sbytes[nb - 1];
+      red[0] = (crc == old && crc != 0) ? 1 : 0;               // :1348
+    }
+    __syncthreads();
+    pass = red[0] != 0;
+  }
+  if (threadIdx.x == 0) {
+    int s = 0;
+    if (pass) s = p.iter;
+    else if (p.iter >= m.max_iter) s = m.max_iter + 1;
+    if (s) {
+      st->status = s;
+      if (p.status_out) p.status_out[blk] = (uint8_t)s;
+    }
+  }
+}
+
+}  // namespace oai

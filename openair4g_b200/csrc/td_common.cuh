@@ -1,0 +1,71 @@
+// Shared device-side definitions for the B200 turbo-decoding kernels.
+//
+// Data layout in HBM ("C4 lane layout").  The reference decoder splits the K trellis
+// positions of a code block into 8 SIMD lanes of W=K/8 steps (lane l covers positions
+// [l*W,(l+1)*W), 3gpplte_turbo_decoder_sse_16bit.c:921-932).  We keep that split --
+// it defines the bit-exact result -- but store every per-position int16 array so that
+// the thread that owns lanes (2t,2t+1) of a block finds 4 consecutive steps of its
+// two lanes in one 16-byte word group:
+//     word(k,t)     = (k>>2)*16 + t*4 + (k&3)            (uint32 index, 2 lanes packed)
+//     halfword(k,l) = 2*word(k,l>>1) + (l&1)
+// so a 4-thread group reads 64 contiguous bytes per 4 steps with one LDG.128 each.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oai {
+
+typedef uint32_t u32;
+
+// ---- per-block metadata (device) ---------------------------------------------------
+struct CbMeta {
+  uint16_t K;          // block size (one of the 188 QPP sizes)
+  uint16_t W;          // K/8 steps per lane
+  uint8_t  max_iter;
+  uint8_t  crc_type;
+  uint8_t  F;
+  uint8_t  flags;      // bit0: decode enabled
+  uint32_t pi_off;     // offset of this K's QPP table in the uint16 table pool
+  uint32_t in_off_lo;  // input offset (int16 units) from the batch input base
+  uint32_t in_off_hi;
+  uint32_t out_off;    // output offset (bytes) from the batch output base
+};
+
+// per-block dynamic state (device)
+struct CbState {
+  int16_t  T[2][8];    // beta start metrics of lane 7 for MAP1 / MAP2 (tail bits)
+  int32_t  max_in;     // max |y| over the 3K+12 inputs
+  int32_t  max_sys;    // max |systematic input| of the next MAP pass
+  int32_t  status;     // 0 = active, otherwise the decoder's return value
+  int32_t  pad;
+};
+
+// workspace arrays of one block slot, each `A` halfwords long
+enum { ARR_S0 = 0, ARR_P1 = 1, ARR_P2 = 2, ARR_SYS = 3, ARR_EXT = 4, ARR_EXT2 = 5, ARR_COUNT = 6 };
+
+__host__ __device__ inline int c4_words(int W) { return ((W + 3) >> 2) << 4; }      // uint32 words per array
+__host__ __device__ inline int c4_word(int k, int t) { return ((k >> 2) << 4) + (t << 2) + (k & 3); }
+__host__ __device__ inline int c4_hw(int k, int lane) { return (c4_word(k, lane >> 1) << 1) + (lane & 1); }
+
+// ---- packed int16x2 arithmetic policies ---------------------------------------------
+// SatArith: the reference's arithmetic (_mm_adds_epi16/_mm_subs_epi16/_mm_max_epi16).
+// WrapArith: plain two's-complement halfword ops (VIADD.16x2 / VIMNMX.S16x2 on sm_100a);
+// identical results whenever no intermediate leaves the int16 range, which the
+// per-pass guard (see DESIGN.md "fast-path guard") proves before this policy is chosen.
+struct SatArith {
+  static __device__ __forceinline__ u32 add(u32 a, u32 b) { return __vaddss2(a, b); }
+  static __device__ __forceinline__ u32 sub(u32 a, u32 b) { return __vsubss2(a, b); }
+};
+struct WrapArith {
+  static __device__ __forceinline__ u32 add(u32 a, u32 b) { return __vadd2(a, b); }
+  static __device__ __forceinline__ u32 sub(u32 a, u32 b) { return __vsub2(a, b); }
+};
+__device__ __forceinline__ u32 vmax(u32 a, u32 b) { return __vmaxs2(a, b); }
+// per-halfword arithmetic shift right by one (_mm_srai_epi16(x,1))
+__device__ __forceinline__ u32 vsra1(u32 x) { return ((x >> 1) & 0x7fff7fffu) | (x & 0x80008000u); }
+__device__ __forceinline__ u32 pack2(int lo, int hi) { return ((u32)lo & 0xffffu) | ((u32)hi << 16); }
+__device__ __forceinline__ int lo16(u32 x) { return (int)(int16_t)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(u32 x) { return (int)(int16_t)(x >> 16); }
+__device__ __forceinline__ int sat16i(int v) { return max(-32768, min(32767, v)); }
+
+}  // namespace oai
