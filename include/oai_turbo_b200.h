@@ -160,6 +160,13 @@ const char *oai_turbo_b200_version(void);
 const char *oai_turbo_b200_last_error(void);
 /* number of kernels this library has launched since load (all threads) */
 unsigned long long oai_turbo_b200_launch_count(void);
+/* Kernel-level test hook: one max-log-MAP pass (the reference's log_map16,
+ * 3gpplte_turbo_decoder_sse_16bit.c:84-119) of a single block on the GPU.  y as for the
+ * decoder; the systematic input is y's systematic stream, the parity stream p1 (term=0,
+ * tail from y[3K..3K+5]) or p2 (term=1, tail from y[3K+6..3K+11]).  policy 0: guard decides,
+ * 1: force the non-saturating fast path, 2: force the exact saturating path.
+ * ext_out: K int16 in the reference's lane layout [step*8 + lane]. */
+int oai_turbo_debug_map16(const int16_t *y, uint16_t K, int term, int policy, int16_t *ext_out);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,8 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
-           "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count"]
+           "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
+           "oai_turbo_debug_map16"]
 
 
 class CbDesc(C.Structure):
@@ -60,6 +61,7 @@ lib.oai_turbo_dev_plan_create.argtypes = [C.c_int, C.c_uint16, C.c_uint8, C.c_ui
 lib.oai_turbo_dev_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
 lib.oai_turbo_dev_plan_destroy.argtypes = [C.c_void_p]
 lib.oai_turbo_dev_plan_destroy.restype = None
+lib.oai_turbo_debug_map16.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_void_p]
 lib.oai_turbo_b200_version.restype = C.c_char_p
 lib.oai_turbo_b200_last_error.restype = C.c_char_p
 lib.oai_turbo_b200_launch_count.restype = C.c_ulonglong
@@ -132,6 +134,16 @@ def decode_batch(blocks, flags=0, gpu=-1):
         if rc != 0:
             raise RuntimeError("oai_turbo_wait failed (%d): %s" % (rc, last_error()))
     return [o[: b["K"] // 8] for o, b in zip(outs, blocks)], [int(s) for s in status]
+
+
+def debug_map16(y, K, term, policy=0):
+    """One MAP pass on the GPU (kernel-level test hook); returns ext[K] in the reference lane layout."""
+    y = np.ascontiguousarray(y, dtype=np.int16)
+    ext = np.zeros(K, dtype=np.int16)
+    rc = lib.oai_turbo_debug_map16(y.ctypes.data, K, term, policy, ext.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oai_turbo_debug_map16 failed (%d): %s" % (rc, last_error()))
+    return ext
 
 
 class DevPlan:

@@ -446,6 +446,50 @@ int lte_rate_matching_turbo_rx(uint32_t, uint32_t, int16_t*, uint8_t*, int16_t*,
 }
 void sub_block_deinterleaving_turbo(uint32_t, int16_t*, int16_t*) { fail(-3, "sub_block_deinterleaving_turbo: not built yet"); }
 
+// Kernel-level test hook: one MAP pass (demux + k_map16) on a single block; the systematic
+// input is the channel systematic stream, the parity stream is p1 (term=0) or p2 (term=1).
+// policy: 0 = guard decides, 1 = force the non-saturating fast path, 2 = force the exact path.
+// ext_out: K values in the reference's lane layout [step*8 + lane].
+int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, int16_t* ext_out) {
+  if (qpp_index(K) < 0) return fail(-1, "illegal K");
+  HostBatch hb;
+  size_t in_hw = ((size_t)3 * K + 12 + 7) & ~(size_t)7;
+  int rc = hb.ensure(-1, 1, K, in_hw, 1024);
+  if (rc) return rc;
+  memcpy(hb.h_in, y, sizeof(int16_t) * (3 * (size_t)K + 12));
+  std::vector<CbMeta> meta(1);
+  make_meta(hb.b.ctx, K, 1, 1, 0, 1, 0, 0, &meta[0]);
+  CU(cudaMemcpyAsync(hb.d_in, hb.h_in, in_hw * sizeof(int16_t), cudaMemcpyHostToDevice, hb.st));
+  rc = hb.b.set_meta(meta, hb.st);
+  if (rc) return rc;
+  Batch& b = hb.b;
+  XchgArgs x;
+  x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
+  x.pi_pool = b.ctx->pi_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
+  x.status_out = nullptr; x.iter = 0;
+  k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
+  MapArgs mp;
+  mp.meta = b.d_meta; mp.state = b.d_state; mp.ws = b.d_ws; mp.slot_hw = b.slot_hw; mp.A = b.A;
+  mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1;
+  mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
+  mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1;
+  k_map16<CKPT_S><<<1, MAP_THREADS, (size_t)CKPT_S * 2 * MAP_THREADS * 16, hb.st>>>(mp);
+  g_launches += 2;
+  std::vector<int16_t> tmp(b.A);
+  CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));
+  CU(cudaStreamSynchronize(hb.st));
+  if (getenv("OAI_TURBO_DEBUG_T")) {
+    CbState stt;
+    cudaMemcpy(&stt, b.d_state, sizeof(stt), cudaMemcpyDeviceToHost);
+    for (int q = 0; q < 2; ++q) { fprintf(stderr, "T[%d]:", q); for (int i = 0; i < 8; ++i) fprintf(stderr, " %d", stt.T[q][i]); fprintf(stderr, "  max_in %d\n", stt.max_in); }
+  }
+  const int W = K / 8;
+  for (int k = 0; k < W; ++k)
+    for (int l = 0; l < 8; ++l) ext_out[k * 8 + l] = tmp[c4_hw(k, l)];
+  hb.release();
+  return 0;
+}
+
 void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t* p) {
   if (!p) return;
   p->b.release();

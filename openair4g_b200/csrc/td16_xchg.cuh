@@ -92,22 +92,26 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
     // tail-bit beta start metrics in WRAPPING int16 (reference :474-520); the gamma of
     // the tail uses the saturating add/sub + >>1 of compute_gamma16 (:160-161)
     const int16_t* tl = y + 3 * K + 6 * threadIdx.x;       // (x,z) x 3 of encoder 1 / 2
-    int16_t m11[3], m10[3];
+    // all values are kept as 32-bit ints and wrapped to int16 explicitly (w16): nvcc 12.9 turned
+    // an int16_t max chain here into VIMNMX3.S16x2 on half-extended registers and picked a
+    // wrong maximum for some inputs
+    auto w16 = [](int v) { return (v << 16) >> 16; };
+    int m11[3], m10[3];
     for (int i = 0; i < 3; ++i) {
-      m11[i] = (int16_t)(sat16i((int)tl[2 * i] + tl[2 * i + 1]) >> 1);
-      m10[i] = (int16_t)(sat16i((int)tl[2 * i] - tl[2 * i + 1]) >> 1);
+      m11[i] = sat16i((int)tl[2 * i] + (int)tl[2 * i + 1]) >> 1;
+      m10[i] = sat16i((int)tl[2 * i] - (int)tl[2 * i + 1]) >> 1;
     }
-    int16_t b0 = (int16_t)(-m11[2]), b1 = m11[2];
-    int16_t b0_2 = (int16_t)(b0 - m11[1]), b1_2 = (int16_t)(b0 + m11[1]);
-    int16_t b2_2 = (int16_t)(b1 + m10[1]), b3_2 = (int16_t)(b1 - m10[1]);
-    int16_t t[8];
-    t[0] = (int16_t)(b0_2 - m11[0]); t[1] = (int16_t)(b0_2 + m11[0]);
-    t[2] = (int16_t)(b1_2 + m10[0]); t[3] = (int16_t)(b1_2 - m10[0]);
-    t[4] = (int16_t)(b2_2 - m10[0]); t[5] = (int16_t)(b2_2 + m10[0]);
-    t[6] = (int16_t)(b3_2 + m11[0]); t[7] = (int16_t)(b3_2 - m11[0]);
-    int16_t bm = t[0];
-    for (int i = 1; i < 8; ++i) bm = (bm > t[i]) ? bm : t[i];
-    for (int i = 0; i < 8; ++i) st->T[threadIdx.x][i] = (int16_t)(t[i] - bm);
+    int b0 = w16(-m11[2]), b1 = m11[2];
+    int b0_2 = w16(b0 - m11[1]), b1_2 = w16(b0 + m11[1]);
+    int b2_2 = w16(b1 + m10[1]), b3_2 = w16(b1 - m10[1]);
+    int t[8];
+    t[0] = w16(b0_2 - m11[0]); t[1] = w16(b0_2 + m11[0]);
+    t[2] = w16(b1_2 + m10[0]); t[3] = w16(b1_2 - m10[0]);
+    t[4] = w16(b2_2 - m10[0]); t[5] = w16(b2_2 + m10[0]);
+    t[6] = w16(b3_2 + m11[0]); t[7] = w16(b3_2 - m11[0]);
+    int bm = t[0];
+    for (int i = 1; i < 8; ++i) bm = max(bm, t[i]);
+    for (int i = 0; i < 8; ++i) st->T[threadIdx.x][i] = (int16_t)w16(t[i] - bm);
   }
   if (threadIdx.x == 0) {
     st->max_in = mx;
