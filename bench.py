@@ -1,0 +1,323 @@
+#!/usr/bin/env python3
+"""Headline benchmark: turbo-decoded information Mbit/s at K=6144, 6 iterations (BASELINE.json).
+
+One "step" = one full decode of a batch of code blocks (demux, 12 MAP passes, QPP exchanges,
+hard decision + CRC per iteration) on every GPU.  See DESIGN.md "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
+  python bench.py --impl reference ...                             # the reference's own CPU decoder
+  torchrun ... bench.py --gpus N ...                               # one rank per GPU, weak scaling
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_BITS = 6144
+MAX_ITER = 6
+CRC_TYPE = 1           # CRC24B
+METRIC = "turbo_decoded_info_mbit_per_s_K6144_6iter"
+WORKLOAD = ("isolated turbo-decoder batch (BASELINE configs[2]): K=6144, max_iterations=6, CRC24B early exit "
+            "enabled, noise regime (uniform +-16 int16 LLRs, CRC never passes -> exactly 6 iterations / 12 MAP passes)")
+
+
+def algorithmic_bytes_per_block(K):
+    return 2 * (3 * K + 12) + K // 8 + 1      # read y once, write bytes + status
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/): the reference decoder on host cores
+# ---------------------------------------------------------------------------------------
+def cpu_decode_rate(y_blocks, total_blocks, threads):
+    """Decodes `total_blocks` code blocks (cycling over the distinct inputs y_blocks) on
+    `threads` host threads with the compiled reference (oracle/_ref) when present, else the
+    oracle port.  Returns (Mbit/s, kind, seconds, per-block results of the distinct inputs)."""
+    import numpy as np
+    from oracle import loader
+    R = loader.ref()
+    nd = y_blocks.shape[0]
+    results = [None] * nd
+    if R is not None:
+        kind = "reference"
+        loader.ref_decode_batch(y_blocks[:1], K_BITS, MAX_ITER, CRC_TYPE)      # warm tables outside the timing
+        out, ret, dt = loader.ref_decode_batch(y_blocks, K_BITS, MAX_ITER, CRC_TYPE, total=total_blocks, threads=threads)
+        total_blocks = max(total_blocks, nd)
+        results = [(out[i], int(ret[i])) for i in range(nd)]
+    else:
+        kind = "port"
+        P = loader.port()
+        reps = (total_blocks + nd - 1) // nd
+        total_blocks = reps * nd
+        stride = y_blocks.shape[1]
+        out = np.zeros((nd, K_BITS // 8 + 8), dtype=np.uint8)
+        ret = np.zeros(nd, dtype=np.uint8)
+        yy = np.ascontiguousarray(y_blocks)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            P.orc_turbo_decoder16_batch(yy, stride, out, out.shape[1], ret, nd, K_BITS, MAX_ITER, CRC_TYPE, threads)
+        dt = time.perf_counter() - t0
+        results = [(out[i, :K_BITS // 8].copy(), int(ret[i])) for i in range(nd)]
+    return total_blocks * K_BITS / dt / 1e6, kind, dt, results
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU decoder, all host threads, bounded sample per step."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    threads = host_threads()
+    rng = np.random.default_rng(1234)
+    nd = 64
+    y = rng.integers(-16, 17, size=(nd, 3 * K_BITS + 12)).astype(np.int16)
+    per_step = max(threads * 16, 256)
+    for _ in range(args.warmup):
+        cpu_decode_rate(y, max(threads, 64), threads)
+    t_tot, kind = 0.0, "port"
+    for _ in range(args.steps):
+        _, kind, dt, _ = cpu_decode_rate(y, per_step, threads)
+        t_tot += dt
+    val = args.steps * per_step * K_BITS / t_tot / 1e6
+    sample = "%d blocks/step (K=6144, noise regime, 6 iterations) on %d host threads" % (per_step, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mbit/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "blocks_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# this repo's engine
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from openair4g_b200 import capi
+    capi.init_td16()
+
+    B, K = args.blocks, K_BITS
+    row = 3 * K + 12
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1000 + rank)
+    y_dev = torch.randint(-16, 17, (B, row), dtype=torch.int16, device="cuda", generator=g)
+    out_dev = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
+    st_dev = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        return plan.decode(y_dev.data_ptr(), row, out_dev.data_ptr(), K // 8, st_dev.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    plan.profile(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    prof_ms, prof_cnt = plan.profile(False, fetch=True)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    st = st_dev.cpu().numpy()
+    if not (st == MAX_ITER + 1).all():
+        raise SystemExit("bench.py: noise-regime blocks must all run the full 6 iterations (status 7); got %s"
+                         % np.unique(st))
+    value = world * B * K * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory in, host memory out) ----
+    Be = args.e2e_blocks
+    y_pin = torch.empty((Be, row), dtype=torch.int16).pin_memory()
+    y_pin.copy_(y_dev[:Be].cpu())
+    call = capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE)
+    for _ in range(2):
+        call.run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_h, st_h = call.run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    e2e_val = world * Be * K * args.steps / dt / 1e6
+    same = bool((out_h == out_dev[:Be].cpu().numpy()).all() and (st_h == st[:Be]).all())
+    if not same:
+        raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_map16: one MAP pass over all blocks per launch) ----
+    peak, peak_src = measured_peaks()
+    n_map = prof_cnt[1]
+    map_ms = prof_ms[1] / max(n_map, 1)
+    bytes_per_launch = B * algorithmic_bytes_per_block(K) / (2.0 * MAX_ITER)
+    achieved = bytes_per_launch / (map_ms * 1e-3) / 1e9 if n_map else 0.0
+    kernel_ms_total = sum(prof_ms)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_map16", "avg_launch_ms": map_ms, "launches_timed": n_map,
+                "share_of_step": prof_ms[1] / kernel_ms_total if kernel_ms_total else None,
+                "kernel_ms": {"demux": prof_ms[0], "map": prof_ms[1], "x1": prof_ms[2], "x2": prof_ms[3]},
+                "peak_source": peak_src,
+                "note": "algorithmic bytes per launch = blocks x (2(3K+12)+K/8+1)/12; the kernel is bound by "
+                        "integer-SIMD issue, not HBM (see int_simd)"}
+    # integer-SIMD view: SURVEY 8(d) counts 123 int16 ops / info bit / MAP pass
+    ops = B * K * 123.0
+    int_peak = 148 * 64 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None   # 64 lanes/clk/SM x 2 halfwords
+    int_simd = {"achieved_int16_gops": ops / (map_ms * 1e-3) / 1e9 if n_map else None,
+                "paper_peak_int16_gops": int_peak / 1e9 if int_peak else None,
+                "note": "paper peak = 148 SM x 64 INT lanes x 2 halfwords x sampled SM clock"}
+    if int_simd["achieved_int16_gops"] and int_simd["paper_peak_int16_gops"]:
+        int_simd["frac"] = int_simd["achieved_int16_gops"] / int_simd["paper_peak_int16_gops"]
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = host_threads()
+        nd = 64
+        ys = y_dev[:nd].cpu().numpy()
+        total = args.cpu_blocks
+        val, kind, secs, res = cpu_decode_rate(ys, total, threads)
+        ok = all(r is not None and r[1] == int(st[i]) and (r[0] == out_dev[i].cpu().numpy()).all() for i, r in enumerate(res))
+        cpu = {"value": val, "unit": "Mbit/s", "cores": threads, "kind": kind,
+               "sample": "%d blocks of the same workload (first %d distinct inputs of the GPU batch, cycled) in %.2f s; "
+                         "GPU output bit-exact vs this CPU run: %s" % (total, nd, secs, ok)}
+        if not ok:
+            raise SystemExit("bench.py: GPU result differs from the CPU reference on the sampled blocks")
+
+    line = {"metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "blocks_per_gpu_per_step": B, "e2e_blocks_per_gpu_per_step": Be,
+                       "l2": "inputs larger than L2 (%.0f MB of LLRs per GPU per step, workspace %.0f MB)"
+                             % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6),
+                       "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks"},
+            "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
+                    "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
+                    "api": "oai_turbo_submit_batch + oai_turbo_wait, pinned host input, host output"},
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=16384, help="code blocks per GPU per step (device-resident)")
+    ap.add_argument("--e2e-blocks", type=int, default=4096, help="code blocks per GPU per step (host-buffer API)")
+    ap.add_argument("--cpu-blocks", type=int, default=8192, help="bounded CPU-baseline sample (blocks)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

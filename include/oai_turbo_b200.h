@@ -151,6 +151,11 @@ int oai_turbo_dev_plan_create(int ncb, uint16_t K, uint8_t max_iterations, uint8
 int oai_turbo_dev_decode(oai_turbo_dev_plan_t *plan, const int16_t *y_dev, long y_stride,
                          uint8_t *out_dev, long out_stride, uint8_t *status_dev, void *stream);
 void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t *plan);
+/* Per-launch CUDA-event timing of a plan (used by bench.py for the roofline figures).
+ * enable != 0 switches it on for subsequent decodes.  When ms4/count4 are non-NULL the
+ * totals accumulated so far, per kernel class {demux, MAP, exchange-1, exchange-2}, are
+ * returned and reset; the plan's stream must be idle when this is called. */
+int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t *plan, int enable, double *ms4, long *count4);
 
 /* ------------------------------------------------------------------------------------
  * 4. Introspection

@@ -28,6 +28,7 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
+           "oai_turbo_dev_plan_profile",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
            "oai_turbo_debug_map16"]
 
@@ -59,6 +60,7 @@ lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
 lib.oai_turbo_dev_plan_create.argtypes = [C.c_int, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.POINTER(C.c_void_p)]
 lib.oai_turbo_dev_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+lib.oai_turbo_dev_plan_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 lib.oai_turbo_dev_plan_destroy.argtypes = [C.c_void_p]
 lib.oai_turbo_dev_plan_destroy.restype = None
 lib.oai_turbo_debug_map16.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_void_p]
@@ -146,6 +148,40 @@ def debug_map16(y, K, term, policy=0):
     return ext
 
 
+class HostBatchCall:
+    """A prepared oai_turbo_submit_batch call over equal-parameter blocks laid out back to
+    back in ONE host buffer (ideally page-locked): descriptors are built once, run() is
+    submit + wait.  y_host: int16 array [n, 3K+12]; returns views of the result buffers."""
+
+    def __init__(self, y_host, K, max_iterations, crc_type, F=0, flags=0, gpu=-1):
+        n = y_host.shape[0]
+        assert y_host.dtype == np.int16 and y_host.shape[1] == 3 * K + 12 and y_host.flags["C_CONTIGUOUS"]
+        self.y, self.n, self.K, self.flags, self.gpu = y_host, n, K, flags, gpu
+        self.out = np.zeros((n, K // 8), dtype=np.uint8)
+        self.status = np.zeros(n, dtype=np.uint8)
+        self.descs = (CbDesc * n)()
+        base, ob, sb = y_host.ctypes.data, self.out.ctypes.data, self.status.ctypes.data
+        row = (3 * K + 12) * 2
+        for i in range(n):
+            d = self.descs[i]
+            d.in_ = base + i * row
+            d.decoded_bytes = ob + i * (K // 8)
+            d.status = sb + i
+            d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable = K, max_iterations, crc_type, F, 1
+        self.h2d_bytes = n * row
+        self.d2h_bytes = n * (K // 8 + 1)
+
+    def run(self):
+        h = C.c_void_p()
+        rc = lib.oai_turbo_submit_batch(self.descs, self.n, self.flags, self.gpu, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("oai_turbo_submit_batch failed (%d): %s" % (rc, last_error()))
+        rc = lib.oai_turbo_wait(h)
+        if rc != 0:
+            raise RuntimeError("oai_turbo_wait failed (%d): %s" % (rc, last_error()))
+        return self.out, self.status
+
+
 class DevPlan:
     """Device-resident batch of equal-K code blocks (throughput mode).  Pointers are raw
     device addresses (e.g. torch tensor .data_ptr()), stream a cudaStream_t handle."""
@@ -162,6 +198,16 @@ class DevPlan:
         if rc < 0:
             raise RuntimeError("oai_turbo_dev_decode failed (%d): %s" % (rc, last_error()))
         return rc
+
+    def profile(self, enable, fetch=False):
+        """Switch per-launch event timing on/off; with fetch=True returns and resets
+        ({demux,map,x1,x2} ms totals, launch counts).  Synchronise the stream first."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_long * 4)()
+        rc = lib.oai_turbo_dev_plan_profile(self._h, 1 if enable else 0, ms if fetch else None, cnt if fetch else None)
+        if rc != 0:
+            raise RuntimeError("oai_turbo_dev_plan_profile failed: " + last_error())
+        return (list(ms), list(cnt)) if fetch else None
 
     def close(self):
         if self._h:

@@ -117,7 +117,38 @@ static int ctx_get(int dev, DevCtx** out) {
 constexpr int CKPT_S = 16;
 constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
 
+// optional per-launch CUDA-event timing (bench.py's roofline leg): class 0 demux, 1 map, 2 x1, 3 x2
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;          // pairs
+  std::vector<int> cls;
+  size_t used = 0;
+  double ms[4] = {0, 0, 0, 0};
+  long count[4] = {0, 0, 0, 0};
+  void begin(int c, cudaStream_t st) {
+    if (!on) return;
+    if (used + 2 > ev.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); }
+    cls.push_back(c);
+    cudaEventRecord(ev[used], st);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  void collect() {                        // call after the stream is synchronised
+    for (size_t i = 0; i < used; i += 2) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) { ms[cls[i / 2]] += t; count[cls[i / 2]]++; }
+    }
+    used = 0; cls.clear();
+  }
+  void reset() { collect(); for (int i = 0; i < 4; ++i) { ms[i] = 0; count[i] = 0; } }
+  ~Profiler() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
 struct Batch {
+  Profiler prof;
   DevCtx* ctx = nullptr;
   int cap = 0, n = 0, A = 0, max_iter = 0;
   long slot_hw = 0, ckpt_words = 0;
@@ -168,17 +199,25 @@ struct Batch {
     const size_t map_smem = (size_t)CKPT_S * 2 * MAP_THREADS * 16;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter;
+      prof.begin(1, st);
       k_map16<CKPT_S><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
+      prof.end(st);
       ++launches;
     };
+    prof.begin(0, st);
     k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
+    prof.end(st);
     ++launches;
     map(ARR_S0, ARR_P1, ARR_EXT, 0, 1);                          // reference :1199
     for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
       x.iter = it;
+      prof.begin(2, st);
       k_x1_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      prof.end(st);
       map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it);                     // :1236
+      prof.begin(3, st);
       k_x2_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      prof.end(st);
       launches += 2;
       if (it < max_iter) map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1);   // :1354-1356
     }
@@ -281,7 +320,7 @@ struct HostBatch {
     out_off.resize(n);
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
-      in_off[i] = in_hw;  in_hw += ((size_t)3 * d.K + 12 + 7) & ~(size_t)7;
+      in_off[i] = in_hw;  in_hw += (size_t)3 * d.K + 12;
       out_off[i] = (uint32_t)out_b; out_b += ((size_t)(d.K >> 3) + 15) & ~(size_t)15;
     }
     int rc = ensure(gpu, n, Kmax, in_hw, out_b);
@@ -289,10 +328,23 @@ struct HostBatch {
     std::vector<CbMeta> meta(n);
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
-      memcpy(h_in + in_off[i], d.in, sizeof(int16_t) * (3 * (size_t)d.K + 12));
       make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, 1, (long)in_off[i], (long)out_off[i], &meta[i]);
     }
-    CU(cudaMemcpyAsync(d_in, h_in, in_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
+    // page-locked caller memory is copied from directly, pageable memory through the pinned stage
+    for (int i = 0; i < n;) {
+      const int16_t* base = descs[order[i]].in;
+      size_t len = (size_t)3 * descs[order[i]].K + 12;
+      int j = i + 1;
+      while (j < n && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
+      cudaPointerAttributes at;
+      bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      const int16_t* src = base;
+      if (!pinned) { memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i]; }
+      CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+      i = j;
+    }
     rc = b.set_meta(meta, st);
     if (rc) return rc;
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
@@ -383,9 +435,18 @@ int oai_turbo_dev_decode(oai_turbo_dev_plan_t* p, const int16_t* y_dev, long y_s
 
 struct oai_turbo_batch { HostBatch hb; };
 
+// finished batch objects keep their device workspace, pinned staging and stream and are reused
+static std::mutex g_pool_mu;
+static std::vector<oai_turbo_batch*> g_pool;
+
 int oai_turbo_submit_batch(const oai_cb_desc_t* cbs, int ncb, unsigned flags, int gpu, oai_turbo_batch_t** handle) {
   if (!cbs || ncb <= 0 || !handle) return fail(-1, "bad arguments");
-  oai_turbo_batch* h = new oai_turbo_batch();
+  oai_turbo_batch* h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool.empty()) { h = g_pool.back(); g_pool.pop_back(); }
+  }
+  if (!h) h = new oai_turbo_batch();
   int rc = h->hb.submit(cbs, ncb, flags, gpu);
   if (rc) { h->hb.release(); delete h; return rc; }
   *handle = h;
@@ -395,10 +456,13 @@ int oai_turbo_submit_batch(const oai_cb_desc_t* cbs, int ncb, unsigned flags, in
 int oai_turbo_wait(oai_turbo_batch_t* h) {
   if (!h) return fail(-1, "null handle");
   int rc = h->hb.wait();
-  h->hb.release();
-  delete h;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (rc == 0 && g_pool.size() < 16) g_pool.push_back(h);
+  else { h->hb.release(); delete h; }
   return rc;
 }
+
+int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4);
 
 void init_td16(void) {
   DevCtx* c;
@@ -487,6 +551,19 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   for (int k = 0; k < W; ++k)
     for (int l = 0; l < 8; ++l) ext_out[k * 8 + l] = tmp[c4_hw(k, l)];
   hb.release();
+  return 0;
+}
+
+// enable/disable per-launch event timing; when ms4/count4 are given, first returns and resets the
+// accumulated totals per kernel class {demux, map, x1, x2} (the stream must be idle)
+int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4) {
+  if (!p) return fail(-1, "null plan");
+  p->b.prof.collect();
+  if (ms4 && count4) {
+    for (int i = 0; i < 4; ++i) { ms4[i] = p->b.prof.ms[i]; count4[i] = p->b.prof.count[i]; }
+    p->b.prof.reset();
+  }
+  p->b.prof.on = enable != 0;
   return 0;
 }
 

@@ -111,6 +111,8 @@ def ref():
     L.ref_sub_block_interleaving_turbo.restype = C.c_uint32
     L.ref_lte_rate_matching_turbo.argtypes = [C.c_uint32, C.c_uint32, u8p, u8p, C.c_uint8, C.c_uint32] + [C.c_uint8] * 8
     L.ref_lte_rate_matching_turbo.restype = C.c_uint32
+    L.ref_td_batch.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p] + [C.c_int] * 7
+    L.ref_td_batch.restype = None
     L.log_map16.argtypes = [C.c_void_p] * 7 + [C.c_ushort, C.c_ubyte, C.c_ubyte, C.c_int] + [C.c_void_p] * 4
     L.log_map16.restype = None
     L.ref_crcTableInit()
@@ -162,3 +164,23 @@ def port_decode16(y, n, max_it, crc_type, F=0):
     out = np.zeros(n // 8 + 4, dtype=np.uint8)
     r = L.orc_turbo_decoder16(yy, out, n, max_it, crc_type, F)
     return out[:n // 8].copy(), int(r)
+
+
+def ref_decode_batch(y_blocks, n, max_it, crc_type, total=None, threads=1, which=16):
+    """Compiled reference over many blocks on `threads` pthreads.  y_blocks: [nd, >=3n+12] int16.
+    `total` >= nd decodes are run (cycling over the nd inputs; only the first pass stores results).
+    Returns (out[nd, n/8], ret[nd], seconds)."""
+    import time
+    L = ref()
+    nd = y_blocks.shape[0]
+    stride = ((3 * n + 12 + 64 + 7) // 8) * 8
+    yy = aligned(nd * stride, np.int16).reshape(nd, stride)
+    yy[:, :3 * n + 12] = y_blocks[:, :3 * n + 12]
+    ostride = ((n // 8 + 64 + 15) // 16) * 16
+    out = aligned(nd * ostride, np.uint8).reshape(nd, ostride)
+    ret = np.zeros(nd, dtype=np.uint8)
+    t0 = time.perf_counter()
+    L.ref_td_batch(yy.ctypes.data, stride, out.ctypes.data, ostride, ret.ctypes.data, nd,
+                   max(total or nd, nd), n, max_it, crc_type, which, threads)
+    dt = time.perf_counter() - t0
+    return out[:, :n // 8].copy(), ret, dt
