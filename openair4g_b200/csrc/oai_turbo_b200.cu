@@ -104,7 +104,7 @@ static int ctx_get(int dev, DevCtx** out) {
     }
     CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
     CU(cudaMemcpy(c.crc_xp, xp.data(), xp.size() * sizeof(u32), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(k_map16<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * MAP_THREADS * 16));
+    CU(cudaFuncSetAttribute(k_map16<MAP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAP_SMEM_BYTES));
     c.dev = dev;
     c.ok = true;
     CU(cudaSetDevice(prev));
@@ -114,7 +114,7 @@ static int ctx_get(int dev, DevCtx** out) {
 }
 
 // ---- a batch of code blocks resident on one GPU ---------------------------------------
-constexpr int CKPT_S = 16;
+constexpr int CKPT_S = MAP_SEG;
 constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
 
 // optional per-launch CUDA-event timing (bench.py's roofline leg): class 0 demux, 1 map, 2 x1, 3 x2
@@ -196,7 +196,7 @@ struct Batch {
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B;
     const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
-    const size_t map_smem = (size_t)CKPT_S * 2 * MAP_THREADS * 16;
+    const size_t map_smem = MAP_SMEM_BYTES;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter;
       prof.begin(1, st);
@@ -537,7 +537,7 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
   mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1;
-  k_map16<CKPT_S><<<1, MAP_THREADS, (size_t)CKPT_S * 2 * MAP_THREADS * 16, hb.st>>>(mp);
+  k_map16<CKPT_S><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
   g_launches += 2;
   std::vector<int16_t> tmp(b.A);
   CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));

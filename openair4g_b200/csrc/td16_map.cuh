@@ -30,7 +30,10 @@
 
 namespace oai {
 
-constexpr int MAP_THREADS = 128;     // 32 code blocks per CTA
+constexpr int MAP_THREADS = 64;      // 16 code blocks per CTA
+constexpr int MAP_SEG = 16;          // checkpoint distance S (steps)
+// dynamic shared memory per CTA: per segment step and thread 32 B of alpha + 8 B of branch constants
+constexpr int MAP_SMEM_BYTES = MAP_SEG * MAP_THREADS * 40;
 constexpr int RERUN_STEPS = 5;       // L>>3, reference :171,189
 constexpr int NEG_INIT = -128;       // -MAX/2, reference :79,201
 
@@ -46,7 +49,7 @@ struct MapArgs {
   int sys_arr, par_arr, out_arr;
   int term;              // 0: first constituent decoder, 1: second
   int iter;              // blocks with max_iter < iter are finished (skipped)
-  int guard_b;           // fast path allowed when max_sys + max_in <= guard_b
+  int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
 };
 
 template <class AR>
@@ -240,6 +243,264 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   }
 }
 
+
+// =====================================================================================
+// Fast path: non-saturating DPX arithmetic (VIADDMNMX.S16x2 / VIADD.16x2), used only
+// when the per-pass guard proves that (a) the reference itself never saturates in this
+// pass, so its result equals exact integer arithmetic, and (b) nothing below leaves the
+// int16 range (DESIGN.md "fast-path guard").  Under (a) the a-posteriori LLR
+//     ext = max_{u=1}(alpha+gamma+beta) - max_{u=0}(alpha+gamma+beta)
+// is invariant to adding any per-(step,lane) constant to all alpha states, to all beta
+// states, or to all four branch metrics of a step.  We use that freedom three ways:
+//   * branch metrics are shifted by +m11:  {+m11,-m11,+m10,-m10} -> {X,0,Y,Z} with
+//     X = 2*m11, Y = m11+m10, Z = m11-m10, so half of the add-compare-selects are a single
+//     VIADDMNMX (max(a+X, b)) and the other half VIADD + VIADDMNMX: 12 instead of 24
+//     instructions per recursion step;
+//   * with s' = s - ((s^p)&1):  X = s'+p, Y = s', Z = p exactly (m11,m10 are floor halves
+//     of s+p and s-p, which have equal parity) -- 3 ALU instructions per step;
+//   * metrics are not max-normalised every step: every P steps state 0 is subtracted from
+//     all states (P from the guard so that the drift P*M stays inside int16).
+// =====================================================================================
+struct FC { u32 X, Y, Z; };
+
+__device__ __forceinline__ u32 vaddmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
+
+__device__ __forceinline__ FC fconst(u32 s, u32 p) {
+  FC c;
+  u32 bit = (s ^ p) & 0x00010001u;
+  c.Y = __vadd2(s, bit * 0xffffu);       // s - bit per halfword (IMAD on the FMA pipe + VIADD.16x2)
+  c.X = __vadd2(c.Y, p);
+  c.Z = p;
+  return c;
+}
+
+__device__ __forceinline__ void alpha_fast(u32 (&a)[8], const FC& c) {
+  u32 t2 = __vadd2(a[2], c.Z), t3 = __vadd2(a[3], c.Z), t4 = __vadd2(a[4], c.Z), t5 = __vadd2(a[5], c.Z);
+  u32 n0 = vaddmax(a[1], c.X, a[0]);     // max(a1+m11, a0-m11) + m11
+  u32 n4 = vaddmax(a[0], c.X, a[1]);
+  u32 n3 = vaddmax(a[6], c.X, a[7]);
+  u32 n7 = vaddmax(a[7], c.X, a[6]);
+  u32 n1 = vaddmax(a[2], c.Y, t3);       // max(a3-m10, a2+m10) + m11
+  u32 n5 = vaddmax(a[3], c.Y, t2);
+  u32 n2 = vaddmax(a[5], c.Y, t4);
+  u32 n6 = vaddmax(a[4], c.Y, t5);
+  a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; a[4] = n4; a[5] = n5; a[6] = n6; a[7] = n7;
+}
+
+__device__ __forceinline__ void beta_fast(u32 (&b)[8], const FC& c) {
+  u32 t1 = __vadd2(b[1], c.Z), t2 = __vadd2(b[2], c.Z), t5 = __vadd2(b[5], c.Z), t6 = __vadd2(b[6], c.Z);
+  u32 n0 = vaddmax(b[4], c.X, b[0]);     // max(b4+m11, b0-m11) + m11
+  u32 n1 = vaddmax(b[0], c.X, b[4]);
+  u32 n6 = vaddmax(b[3], c.X, b[7]);
+  u32 n7 = vaddmax(b[7], c.X, b[3]);
+  u32 n2 = vaddmax(b[1], c.Y, t5);       // max(b5-m10, b1+m10) + m11
+  u32 n3 = vaddmax(b[5], c.Y, t1);
+  u32 n4 = vaddmax(b[6], c.Y, t2);
+  u32 n5 = vaddmax(b[2], c.Y, t6);
+  b[0] = n0; b[1] = n1; b[2] = n2; b[3] = n3; b[4] = n4; b[5] = n5; b[6] = n6; b[7] = n7;
+}
+
+// max(m10+m10g, m11+m11g) - max(m01-m10g, m00-m11g) with both maxima shifted by +m11
+__device__ __forceinline__ u32 ext_fast(const u32 (&a)[8], const u32 (&b)[8], const FC& c) {
+  u32 m00 = vaddmax(a[7], b[3], vaddmax(a[6], b[7], vaddmax(a[1], b[4], __vadd2(a[0], b[0]))));
+  u32 m11 = vaddmax(a[7], b[7], vaddmax(a[6], b[3], vaddmax(a[1], b[0], __vadd2(a[0], b[4]))));
+  u32 m01 = vaddmax(a[5], b[6], vaddmax(a[4], b[2], vaddmax(a[3], b[1], __vadd2(a[2], b[5]))));
+  u32 m10 = vaddmax(a[5], b[2], vaddmax(a[4], b[6], vaddmax(a[3], b[5], __vadd2(a[2], b[1]))));
+  u32 u = vaddmax(m10, c.Y, __vadd2(m11, c.X));
+  u32 v = vaddmax(m01, c.Z, m00);
+  return __vsub2(u, v);
+}
+
+// subtract state 0 from all states (any uniform shift is allowed, see above)
+__device__ __forceinline__ void renorm(u32 (&a)[8]) {
+  u32 n = __vneg2(a[0]);
+  a[0] = 0;
+#pragma unroll
+  for (int s = 1; s < 8; ++s) a[s] = __vadd2(a[s], n);
+}
+
+template <int S>
+struct FastSmem {
+  uint4* a0; uint4* a1; uint2* cc;
+  __device__ __forceinline__ FastSmem(unsigned char* base) {
+    a0 = reinterpret_cast<uint4*>(base);
+    a1 = a0 + S * MAP_THREADS;
+    cc = reinterpret_cast<uint2*>(a1 + S * MAP_THREADS);
+  }
+  __device__ __forceinline__ void put(int e, int tid, const u32 (&a)[8]) const {
+    a0[e * MAP_THREADS + tid] = make_uint4(a[0], a[1], a[2], a[3]);
+    a1[e * MAP_THREADS + tid] = make_uint4(a[4], a[5], a[6], a[7]);
+  }
+  __device__ __forceinline__ void get(int e, int tid, u32 (&a)[8]) const {
+    uint4 x = a0[e * MAP_THREADS + tid], y = a1[e * MAP_THREADS + tid];
+    a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
+  }
+  __device__ __forceinline__ void putc(int e, int tid, const FC& c) const { cc[e * MAP_THREADS + tid] = make_uint2(c.Y, c.Z); }
+  __device__ __forceinline__ FC getc(int e, int tid) const {
+    uint2 v = cc[e * MAP_THREADS + tid];
+    FC c; c.Y = v.x; c.Z = v.y; c.X = __vadd2(v.x, v.y);
+    return c;
+  }
+};
+
+__device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
+
+// Fast MAP pass.  pmask = P-1, P = renormalisation period (power of two, <= S).
+template <int S>
+__device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, u32* __restrict__ ext,
+                              u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, unsigned char* smem,
+                              int tid, int pmask) {
+  static_assert(S == 16, "segment = 4 chunks of 4 steps");
+  const FastSmem<S> sm(smem);
+  const int nseg = (W + S - 1) / S, nchunk = (W + 3) >> 2;
+  const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
+  const uint4* par4 = reinterpret_cast<const uint4*>(par);
+  u32 a[8];
+
+  // ---- forward sweep: alpha pass 1, checkpoints every S steps, loads one chunk ahead ---
+#pragma unroll
+  for (int s = 0; s < 8; ++s) a[s] = pack2(NEG_INIT, NEG_INIT);
+  if (t == 0) a[0] = pack2(0, NEG_INIT);
+  {
+    uint4 s4 = __ldg(sys4), p4 = __ldg(par4);
+    for (int c = 0; c < nchunk; ++c) {
+      uint4 sn = s4, pn = p4;
+      if (c + 1 < nchunk) { sn = __ldg(sys4 + (c + 1) * 4); pn = __ldg(par4 + (c + 1) * 4); }
+      if ((c & 3) == 0) ckpt_put(ck + (c >> 2) * 32, a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = c * 4 + q;
+        if (k < W) {
+          if ((k & pmask) == 0 && q != 0) renorm(a);
+          alpha_fast(a, fconst(pick4(s4, q), pick4(p4, q)));
+        }
+      }
+      if (((c * 4 + 4) & pmask) == 0) renorm(a);               // keeps checkpoints normalised
+      s4 = sn; p4 = pn;
+    }
+  }
+
+  // ---- alpha re-run seed ------------------------------------------------------------
+  u32 seed[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    u32 prev = __shfl_sync(gmask, a[s], (t + 3) & 3, 4);
+    if (t == 0) prev = pack2(0, (s == 0) ? 0 : NEG_INIT);
+    seed[s] = __byte_perm(prev, a[s], 0x5432);
+  }
+  ckpt_put(ck + nseg * 32, seed);
+  if (W <= RERUN_STEPS) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) a[s] = seed[s];
+    for (int k = 0; k < W; ++k) {
+      if ((k & pmask) == 0) renorm(a);
+      alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+    }
+  }
+
+  // ---- beta start -------------------------------------------------------------------
+  u32 b[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    b[s] = a[s];
+    if (t == 3) b[s] = (a[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
+  }
+
+  // ---- backward sweep, pass 1: per segment recompute alpha (+ branch constants) into shared
+  // memory, then beta + ext backwards.  The next segment's inputs are fetched while the
+  // current one is processed.
+  uint4 sb[4], pb[4];
+  auto fetch = [&](int seg) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = seg * 4 + j;
+      if (c < nchunk) { sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4); }
+    }
+  };
+  fetch(nseg - 1);
+  for (int seg = nseg - 1; seg >= 0; --seg) {
+    const int k0 = seg * S, k1 = min(W, k0 + S);
+    ckpt_get(ck + seg * 32, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = j * 4 + q, k = k0 + e;
+        if (k < k1) {
+          if ((k & pmask) == 0 && e != 0) renorm(a);
+          const FC c = fconst(pick4(sb[j], q), pick4(pb[j], q));
+          sm.put(e, tid, a);
+          sm.putc(e, tid, c);
+          alpha_fast(a, c);
+        }
+      }
+    }
+    if (seg == 0) {          // alpha[0..5] come from the re-run chain
+#pragma unroll
+      for (int s = 0; s < 8; ++s) a[s] = seed[s];
+      for (int k = 0; k <= RERUN_STEPS && k < k1; ++k) {
+        if ((k & pmask) == 0) renorm(a);
+        sm.put(k, tid, a);
+        if (k < RERUN_STEPS) alpha_fast(a, sm.getc(k, tid));
+      }
+    }
+    if (seg > 0) fetch(seg - 1);
+    u32 e4[4] = {0, 0, 0, 0};
+    for (int k = k1 - 1; k >= k0; --k) {
+      const FC c = sm.getc(k - k0, tid);
+      if (k <= W - 7) {
+        sm.get(k - k0, tid, a);
+        const u32 x = ext_fast(a, b, c);
+        if ((k | 3) <= W - 7) {                   // whole chunk belongs to pass 1: one 128-bit store
+          e4[k & 3] = x;
+          if ((k & 3) == 0) *reinterpret_cast<uint4*>(ext + (k >> 2) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+        } else {
+          ext[c4_word(k, 0)] = x;
+        }
+      }
+      beta_fast(b, c);
+      if ((k & pmask) == 0) renorm(b);
+    }
+  }
+
+  // ---- beta re-run over the last 5 steps, ext for the last 6 ------------------------------
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    u32 next = __shfl_sync(gmask, b[s], (t + 1) & 3, 4);
+    if (t == 3) next = (u32)(uint16_t)Tv[s];
+    b[s] = __byte_perm(b[s], next, 0x5432);
+  }
+  {
+    const int kk0 = max(W - 6, 0);
+    const int sa = kk0 / S;
+    ckpt_get(ck + sa * 32, a);
+    for (int k = sa * S; k < W; ++k) {
+      if ((k & pmask) == 0 && k != sa * S) renorm(a);
+      const FC c = fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
+      if (k >= kk0) { sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c); }
+      if (k + 1 < W) alpha_fast(a, c);
+    }
+    if (kk0 <= RERUN_STEPS) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) a[s] = seed[s];
+      for (int k = 0; k <= RERUN_STEPS && k < W; ++k) {
+        if ((k & pmask) == 0) renorm(a);
+        if (k >= kk0) sm.put(k - kk0, tid, a);
+        if (k < RERUN_STEPS) alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+      }
+    }
+    for (int k = W - 1; k >= kk0; --k) {
+      const FC c = sm.getc(k - kk0, tid);
+      sm.get(k - kk0, tid, a);
+      ext[c4_word(k, 0)] = ext_fast(a, b, c);
+      if (k >= W - RERUN_STEPS) {
+        beta_fast(b, c);
+        if ((k & pmask) == 0) renorm(b);
+      }
+    }
+  }
+}
+
 template <int S>
 __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
   extern __shared__ uint4 abuf[];
@@ -248,18 +509,29 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
   const int blk = gt >> 2, t = gt & 3;
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
 
-  bool active = false, fast = true;
-  int W = 0;
+  bool active = false;
+  int W = 0, P = 64;           // P: largest renormalisation period this block's guard allows (0: exact path)
   if (blk < p.nblk) {
     const CbMeta m = p.meta[blk];
     const CbState* st = &p.state[blk];
     active = (st->status == 0) && (m.flags & 1) && (p.iter <= m.max_iter);
     W = m.W;
-    if (active) fast = (st->max_sys + st->max_in) <= p.guard_b;
+    if (active) {
+      // M bounds every branch constant |X|,|Y|,|Z| of this pass (tails included via max_in)
+      const int B = max(st->max_sys, st->max_in) + st->max_in;
+      const int M = B + 1;
+      if (B > p.guard_b) P = 0;
+      else {
+        // no wrap needs (11 + 2P) * M + 276 <= 32767  (DESIGN.md "fast-path guard")
+        const int pmax = (32491 / M - 11) >> 1;
+        P = pmax >= 16 ? 16 : (pmax >= 8 ? 8 : (pmax >= 4 ? 4 : (pmax >= 2 ? 2 : (pmax >= 1 ? 1 : 0))));
+      }
+    }
   }
-  // a warp carries 8 blocks; the exact (saturating) policy is always valid, so one hot
-  // block switches its whole warp to it
-  const bool warp_fast = __all_sync(0xffffffffu, fast);
+  // a warp carries 8 blocks: it runs the most conservative choice of its blocks (a shorter
+  // period, or the exact saturating policy, is valid for every block)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) P = min(P, __shfl_xor_sync(0xffffffffu, P, o));
   if (!active) return;
 
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
@@ -269,8 +541,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
   u32* ck = p.ckpt + (long)blk * p.ckpt_words + t * 8;
   const int16_t* Tv = p.state[blk].T[p.term];
 
-  if (warp_fast) map_pass<WrapArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
-  else           map_pass<SatArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
+  if (P > 0) map_pass_fast<S>(sys, par, ext, ck, W, t, gmask, Tv, reinterpret_cast<unsigned char*>(abuf), tid, P - 1);
+  else       map_pass<SatArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
 }
 
 }  // namespace oai
