@@ -345,38 +345,61 @@ struct FastSmem {
 
 __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
 
-// Fast MAP pass.  pmask = P-1, P = renormalisation period (power of two, <= S).
-template <int S>
+// Fast MAP pass.  PM = P-1 with P the renormalisation period (1, 4 or 16 steps; compile time so
+// that the unrolled steady-state code has no data-dependent branches).
+//
+// Structure per 16-step segment (4 chunks of 4 steps, one LDG.128 per chunk and stream):
+//   forward : alpha in registers, checkpoint at the segment start
+//   backward: reload checkpoint, recompute alpha -> shared memory (+ the step's branch
+//             constants), then beta / ext from the segment end to its start.
+// The register that held chunk j is refilled with chunk j of the NEXT segment as soon as it has
+// been consumed, so global loads run a whole segment ahead of their use.
+template <int S, int PM>
 __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, u32* __restrict__ ext,
                               u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, unsigned char* smem,
-                              int tid, int pmask) {
+                              int tid) {
   static_assert(S == 16, "segment = 4 chunks of 4 steps");
   const FastSmem<S> sm(smem);
   const int nseg = (W + S - 1) / S, nchunk = (W + 3) >> 2;
   const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
   const uint4* par4 = reinterpret_cast<const uint4*>(par);
   u32 a[8];
+  uint4 sb[4], pb[4];
 
-  // ---- forward sweep: alpha pass 1, checkpoints every S steps, loads one chunk ahead ---
+  // ---- forward sweep ------------------------------------------------------------------
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = pack2(NEG_INIT, NEG_INIT);
   if (t == 0) a[0] = pack2(0, NEG_INIT);
-  {
-    uint4 s4 = __ldg(sys4), p4 = __ldg(par4);
-    for (int c = 0; c < nchunk; ++c) {
-      uint4 sn = s4, pn = p4;
-      if (c + 1 < nchunk) { sn = __ldg(sys4 + (c + 1) * 4); pn = __ldg(par4 + (c + 1) * 4); }
-      if ((c & 3) == 0) ckpt_put(ck + (c >> 2) * 32, a);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = __ldg(par4 + j * 4); }
+  const int nfull = W / S;                                     // segments with all 16 steps
+  for (int seg = 0; seg < nfull; ++seg) {
+    ckpt_put(ck + seg * 32, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int k = c * 4 + q;
-        if (k < W) {
-          if ((k & pmask) == 0 && q != 0) renorm(a);
-          alpha_fast(a, fconst(pick4(s4, q), pick4(p4, q)));
+        if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
+        alpha_fast(a, fconst(pick4(sb[j], q), pick4(pb[j], q)));
+      }
+      const int cn = (seg + 1) * 4 + j;
+      if (cn < nchunk) { sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4); }
+    }
+    renorm(a);                                                 // checkpoints are stored normalised
+  }
+  if (nfull < nseg) {                                          // partial last segment
+    ckpt_put(ck + nfull * 32, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = j * 4 + q;
+        if (nfull * S + e < W) {
+          if ((e & PM) == 0 && e != 0) renorm(a);
+          alpha_fast(a, fconst(pick4(sb[j], q), pick4(pb[j], q)));
         }
       }
-      if (((c * 4 + 4) & pmask) == 0) renorm(a);               // keeps checkpoints normalised
-      s4 = sn; p4 = pn;
     }
   }
 
@@ -393,7 +416,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #pragma unroll
     for (int s = 0; s < 8; ++s) a[s] = seed[s];
     for (int k = 0; k < W; ++k) {
-      if ((k & pmask) == 0) renorm(a);
+      if ((k & PM) == 0) renorm(a);
       alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
     }
   }
@@ -406,60 +429,81 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     if (t == 3) b[s] = (a[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
   }
 
-  // ---- backward sweep, pass 1: per segment recompute alpha (+ branch constants) into shared
-  // memory, then beta + ext backwards.  The next segment's inputs are fetched while the
-  // current one is processed.
-  uint4 sb[4], pb[4];
-  auto fetch = [&](int seg) {
+  // ---- backward sweep, pass 1 -----------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = seg * 4 + j;
-      if (c < nchunk) { sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4); }
-    }
-  };
-  fetch(nseg - 1);
+  for (int j = 0; j < 4; ++j) {
+    const int c = (nseg - 1) * 4 + j;
+    if (c < nchunk) { sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4); }
+  }
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
+    const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
     ckpt_get(ck + seg * 32, a);
+    if (steady) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = j * 4 + q, k = k0 + e;
-        if (k < k1) {
-          if ((k & pmask) == 0 && e != 0) renorm(a);
+        for (int q = 0; q < 4; ++q) {
+          const int e = j * 4 + q;
+          if ((e & PM) == 0 && e != 0) renorm(a);
           const FC c = fconst(pick4(sb[j], q), pick4(pb[j], q));
           sm.put(e, tid, a);
           sm.putc(e, tid, c);
-          alpha_fast(a, c);
+          if (e != S - 1) alpha_fast(a, c);
         }
+        if (seg > 0) { sb[j] = __ldg(sys4 + ((seg - 1) * 4 + j) * 4); pb[j] = __ldg(par4 + ((seg - 1) * 4 + j) * 4); }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = j * 4 + q;
+          if (k0 + e < k1) {
+            if ((e & PM) == 0 && e != 0) renorm(a);
+            const FC c = fconst(pick4(sb[j], q), pick4(pb[j], q));
+            sm.put(e, tid, a);
+            sm.putc(e, tid, c);
+            alpha_fast(a, c);
+          }
+        }
+        if (seg > 0) { sb[j] = __ldg(sys4 + ((seg - 1) * 4 + j) * 4); pb[j] = __ldg(par4 + ((seg - 1) * 4 + j) * 4); }
       }
     }
     if (seg == 0) {          // alpha[0..5] come from the re-run chain
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
       for (int k = 0; k <= RERUN_STEPS && k < k1; ++k) {
-        if ((k & pmask) == 0) renorm(a);
+        if ((k & PM) == 0) renorm(a);
         sm.put(k, tid, a);
         if (k < RERUN_STEPS) alpha_fast(a, sm.getc(k, tid));
       }
     }
-    if (seg > 0) fetch(seg - 1);
-    u32 e4[4] = {0, 0, 0, 0};
-    for (int k = k1 - 1; k >= k0; --k) {
-      const FC c = sm.getc(k - k0, tid);
-      if (k <= W - 7) {
-        sm.get(k - k0, tid, a);
-        const u32 x = ext_fast(a, b, c);
-        if ((k | 3) <= W - 7) {                   // whole chunk belongs to pass 1: one 128-bit store
-          e4[k & 3] = x;
-          if ((k & 3) == 0) *reinterpret_cast<uint4*>(ext + (k >> 2) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
-        } else {
-          ext[c4_word(k, 0)] = x;
+    if (steady) {
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        u32 e4[4];
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+          const int e = j * 4 + q;
+          const FC c = sm.getc(e, tid);
+          sm.get(e, tid, a);
+          e4[q] = ext_fast(a, b, c);
+          beta_fast(b, c);
+          if ((e & PM) == 0) renorm(b);
         }
+        *reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
       }
-      beta_fast(b, c);
-      if ((k & pmask) == 0) renorm(b);
+    } else {
+      for (int k = k1 - 1; k >= k0; --k) {
+        const FC c = sm.getc(k - k0, tid);
+        if (k <= W - 7) {
+          sm.get(k - k0, tid, a);
+          ext[c4_word(k, 0)] = ext_fast(a, b, c);
+        }
+        beta_fast(b, c);
+        if ((k & PM) == 0) renorm(b);
+      }
     }
   }
 
@@ -475,7 +519,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     const int sa = kk0 / S;
     ckpt_get(ck + sa * 32, a);
     for (int k = sa * S; k < W; ++k) {
-      if ((k & pmask) == 0 && k != sa * S) renorm(a);
+      if ((k & PM) == 0 && k != sa * S) renorm(a);
       const FC c = fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
       if (k >= kk0) { sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c); }
       if (k + 1 < W) alpha_fast(a, c);
@@ -484,7 +528,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
       for (int k = 0; k <= RERUN_STEPS && k < W; ++k) {
-        if ((k & pmask) == 0) renorm(a);
+        if ((k & PM) == 0) renorm(a);
         if (k >= kk0) sm.put(k - kk0, tid, a);
         if (k < RERUN_STEPS) alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
       }
@@ -495,7 +539,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       ext[c4_word(k, 0)] = ext_fast(a, b, c);
       if (k >= W - RERUN_STEPS) {
         beta_fast(b, c);
-        if ((k & pmask) == 0) renorm(b);
+        if ((k & PM) == 0) renorm(b);
       }
     }
   }
@@ -524,7 +568,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
       else {
         // no wrap needs (11 + 2P) * M + 276 <= 32767  (DESIGN.md "fast-path guard")
         const int pmax = (32491 / M - 11) >> 1;
-        P = pmax >= 16 ? 16 : (pmax >= 8 ? 8 : (pmax >= 4 ? 4 : (pmax >= 2 ? 2 : (pmax >= 1 ? 1 : 0))));
+        P = pmax >= 16 ? 16 : (pmax >= 4 ? 4 : (pmax >= 1 ? 1 : 0));
       }
     }
   }
@@ -541,8 +585,11 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
   u32* ck = p.ckpt + (long)blk * p.ckpt_words + t * 8;
   const int16_t* Tv = p.state[blk].T[p.term];
 
-  if (P > 0) map_pass_fast<S>(sys, par, ext, ck, W, t, gmask, Tv, reinterpret_cast<unsigned char*>(abuf), tid, P - 1);
-  else       map_pass<SatArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
+  unsigned char* smem = reinterpret_cast<unsigned char*>(abuf);
+  if (P >= 16)     map_pass_fast<S, 15>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
+  else if (P >= 4) map_pass_fast<S, 3>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
+  else if (P >= 1) map_pass_fast<S, 0>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
+  else             map_pass<SatArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
 }
 
 }  // namespace oai
