@@ -47,24 +47,41 @@ class ClockSampler:
 
     def __init__(self, dev):
         self.p = None
+        self.lines = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
         except Exception:
             self.p = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def wait_first(self, timeout=10.0):
+        t0 = time.perf_counter()
+        while self.p is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
+        time.sleep(0.12)                       # let the sample that covers the end of the region arrive
         self.p.terminate()
-        try:
-            out = self.p.communicate(timeout=5)[0]
-        except Exception:
-            out = ""
+        t_mark = getattr(self, "t_mark", 0.0)
+        sel = [l for (ts, l) in self.lines if t_mark <= ts <= t_end + 0.12]
+        if not sel:
+            sel = [l for (_, l) in self.lines[-1:]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
+        for line in sel:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -197,9 +214,13 @@ def run_b200(args):
     barrier()
     plan.profile(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     launches0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -306,7 +327,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks", type=int, default=16384, help="code blocks per GPU per step (device-resident)")
+    ap.add_argument("--blocks", type=int, default=23680,
+                    help="code blocks per GPU per step (device-resident); 23680 = 2 full waves of the MAP kernel "
+                         "(148 SMs x 5 resident CTAs x 16 blocks)")
     ap.add_argument("--e2e-blocks", type=int, default=4096, help="code blocks per GPU per step (host-buffer API)")
     ap.add_argument("--cpu-blocks", type=int, default=8192, help="bounded CPU-baseline sample (blocks)")
     ap.add_argument("--no-cpu", action="store_true")

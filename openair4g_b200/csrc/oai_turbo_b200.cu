@@ -58,8 +58,9 @@ static int qpp_K(int idx) {
 // ---- per-device context: read-only tables ------------------------------------------
 struct DevCtx {
   int dev = -1;
-  uint16_t* pi_pool = nullptr;        // all 188 QPP tables, ascending K
-  uint32_t pi_off[188];
+  uint16_t* pi_pool = nullptr;        // H tables of all 188 K (natural position -> C4 halfword index)
+  uint16_t* t_pool = nullptr;         // T tables (layout order -> C4 index of the QPP image)
+  uint32_t pi_off[188], t_off[188];
   u32* crc_xp = nullptr;              // [4][768]
   bool ok = false;
 };
@@ -81,15 +82,27 @@ static int ctx_get(int dev, DevCtx** out) {
     int prev = 0;
     CU(cudaGetDevice(&prev));
     CU(cudaSetDevice(dev));
-    std::vector<uint16_t> pool;
+    std::vector<uint16_t> pool, tpool;
     for (int i = 0; i < 188; ++i) {
-      int K = qpp_K(i);
+      const int K = qpp_K(i), W = K / 8, A = c4_words(W) * 2;
       c.pi_off[i] = (uint32_t)pool.size();
-      uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
-      for (uint64_t j = 0; j < (uint64_t)K; ++j) pool.push_back((uint16_t)((f1 * j + f2 * j * j) % (uint64_t)K));
+      c.t_off[i] = (uint32_t)tpool.size();
+      const uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
+      std::vector<uint16_t> H(K), T(A);
+      for (int j = 0; j < K; ++j) H[j] = (uint16_t)c4_hw(j % W, j / W);
+      for (int h = 0; h < A; ++h) T[h] = (uint16_t)h;                       // padding maps to itself
+      for (uint64_t j = 0; j < (uint64_t)K; ++j) {
+        const uint64_t pj = (f1 * j + f2 * j * j) % (uint64_t)K;           // pi(j), 36.212 5.1.3.2.3
+        T[H[j]] = H[pj];
+      }
+      pool.insert(pool.end(), H.begin(), H.end());
+      while (pool.size() & 7) pool.push_back(0);
+      tpool.insert(tpool.end(), T.begin(), T.end());                         // A is a multiple of 32
     }
     CU(cudaMalloc(&c.pi_pool, pool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.pi_pool, pool.data(), pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.t_pool, tpool.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(c.t_pool, tpool.data(), tpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     // x^(8m+w) mod P for the four CRCs (polynomials: crc_byte.c:53-57)
     std::vector<u32> xp(4 * 768);
     const u32 polys[4] = {0x864cfbu, 0x800063u, 0x1021u, 0x9Bu};
@@ -190,15 +203,15 @@ struct Batch {
     int launches = 0;
     XchgArgs x;
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
-    x.pi_pool = ctx->pi_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
+    x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
     x.status_out = status_dev; x.iter = 0;
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B;
     const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
     const size_t map_smem = MAP_SMEM_BYTES;
-    auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter) {
-      mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter;
+    auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
+      mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter; mp.upd = upd;
       prof.begin(1, st);
       k_map16<CKPT_S><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
       prof.end(st);
@@ -208,18 +221,18 @@ struct Batch {
     k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
     prof.end(st);
     ++launches;
-    map(ARR_S0, ARR_P1, ARR_EXT, 0, 1);                          // reference :1199
+    map(ARR_S0, ARR_P1, ARR_EXT, 0, 1, 0);                       // reference :1199
     for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
       x.iter = it;
       prof.begin(2, st);
-      k_x1_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      k_x1_16<<<n, XCHG_THREADS, A * sizeof(int16_t), st>>>(x);
       prof.end(st);
-      map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it);                     // :1236
+      map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it, 0);                  // :1236
       prof.begin(3, st);
-      k_x2_16<<<n, XCHG_THREADS, 2 * A * sizeof(int16_t), st>>>(x);
+      k_x2_16<<<n, XCHG_THREADS, A * sizeof(int16_t), st>>>(x);
       prof.end(st);
       launches += 2;
-      if (it < max_iter) map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1);   // :1354-1356
+      if (it < max_iter) map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1, 1);   // :1354-1375 (feedback fused)
     }
     g_launches += launches;
     cudaError_t e = cudaGetLastError();
@@ -234,6 +247,7 @@ static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long
   m->K = (uint16_t)K; m->W = (uint16_t)(K >> 3);
   m->max_iter = (uint8_t)max_it; m->crc_type = (uint8_t)crc; m->F = (uint8_t)F; m->flags = dec ? 1 : 0;
   m->pi_off = c->pi_off[idx];
+  m->t_off = c->t_off[idx];
   m->in_off_lo = (uint32_t)((unsigned long long)in_off & 0xffffffffu);
   m->in_off_hi = (uint32_t)((unsigned long long)in_off >> 32);
   m->out_off = (uint32_t)out_off;
@@ -529,14 +543,14 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   Batch& b = hb.b;
   XchgArgs x;
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
-  x.pi_pool = b.ctx->pi_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
+  x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
   x.status_out = nullptr; x.iter = 0;
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
   MapArgs mp;
   mp.meta = b.d_meta; mp.state = b.d_state; mp.ws = b.d_ws; mp.slot_hw = b.slot_hw; mp.A = b.A;
   mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
-  mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1;
+  mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1; mp.upd = 0;
   k_map16<CKPT_S><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
   g_launches += 2;
   std::vector<int16_t> tmp(b.A);

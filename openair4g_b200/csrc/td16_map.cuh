@@ -32,8 +32,9 @@ namespace oai {
 
 constexpr int MAP_THREADS = 64;      // 16 code blocks per CTA
 constexpr int MAP_SEG = 16;          // checkpoint distance S (steps)
-// dynamic shared memory per CTA: per segment step and thread 32 B of alpha + 8 B of branch constants
-constexpr int MAP_SMEM_BYTES = MAP_SEG * MAP_THREADS * 40;
+// dynamic shared memory per CTA: per segment step and thread 32 B of alpha, 8 B of branch constants
+// and 4 B for the feedback term s0 - sys
+constexpr int MAP_SMEM_BYTES = MAP_SEG * MAP_THREADS * 44;
 constexpr int RERUN_STEPS = 5;       // L>>3, reference :171,189
 constexpr int NEG_INIT = -128;       // -MAX/2, reference :79,201
 
@@ -50,6 +51,7 @@ struct MapArgs {
   int term;              // 0: first constituent decoder, 1: second
   int iter;              // blocks with max_iter < iter are finished (skipped)
   int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
+  int upd;               // 1: write ext = (ext (-) sys) (+) s0 (the feedback step, reference :1354-1375)
 };
 
 template <class AR>
@@ -137,8 +139,14 @@ __device__ __forceinline__ void ckpt_get(const u32* c, u32 (&a)[8]) {
 //   ck: this thread's checkpoint area: slot i at ck + i*32 words (8 words used per thread,
 //       threads interleaved by the caller through the base pointer)
 template <class AR, int S>
-__device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ par, u32* __restrict__ ext,
-                         u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, uint4* abuf, int tid) {
+__device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0, bool upd,
+                         u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, uint4* abuf,
+                         int tid) {
+  // feedback step fused into the output: ext = (ext (-) sys) (+) s0 with the reference's saturation
+  auto fb = [&](u32 x, int k) -> u32 {
+    if (!upd) return x;
+    return __vaddss2(__vsubss2(x, __ldg(sys + c4_word(k, 0))), __ldg(s0 + c4_word(k, 0)));
+  };
   const int nseg = (W + S - 1) / S;
   u32 a[8];
 
@@ -205,7 +213,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
       Gam<AR> g = gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
       if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
         abuf_get(abuf, k - k0, tid, a);
-        ext[c4_word(k, 0)] = ext_step<AR>(a, b, g);
+        ext[c4_word(k, 0)] = fb(ext_step<AR>(a, b, g), k);
       }
       beta_step<AR>(b, g);
     }
@@ -237,7 +245,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     for (int k = W - 1; k >= kk0; --k) {
       Gam<AR> g = gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
       abuf_get(abuf, k - kk0, tid, a);
-      ext[c4_word(k, 0)] = ext_step<AR>(a, b, g);
+      ext[c4_word(k, 0)] = fb(ext_step<AR>(a, b, g), k);
       if (k >= W - RERUN_STEPS) beta_step<AR>(b, g);             // loopval=(n-40)>>3, reference :585
     }
   }
@@ -262,6 +270,8 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
 //     all states (P from the guard so that the drift P*M stays inside int16).
 // =====================================================================================
 struct FC { u32 X, Y, Z; };
+
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ u32 vaddmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
 
@@ -321,12 +331,15 @@ __device__ __forceinline__ void renorm(u32 (&a)[8]) {
 
 template <int S>
 struct FastSmem {
-  uint4* a0; uint4* a1; uint2* cc;
+  uint4* a0; uint4* a1; uint2* cc; u32* dd;
   __device__ __forceinline__ FastSmem(unsigned char* base) {
     a0 = reinterpret_cast<uint4*>(base);
     a1 = a0 + S * MAP_THREADS;
     cc = reinterpret_cast<uint2*>(a1 + S * MAP_THREADS);
+    dd = reinterpret_cast<u32*>(cc + S * MAP_THREADS);
   }
+  __device__ __forceinline__ void putd(int e, int tid, u32 d) const { dd[e * MAP_THREADS + tid] = d; }
+  __device__ __forceinline__ u32 getd(int e, int tid) const { return dd[e * MAP_THREADS + tid]; }
   __device__ __forceinline__ void put(int e, int tid, const u32 (&a)[8]) const {
     a0[e * MAP_THREADS + tid] = make_uint4(a[0], a[1], a[2], a[3]);
     a1[e * MAP_THREADS + tid] = make_uint4(a[4], a[5], a[6], a[7]);
@@ -354,17 +367,19 @@ __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.
 //             constants), then beta / ext from the segment end to its start.
 // The register that held chunk j is refilled with chunk j of the NEXT segment as soon as it has
 // been consumed, so global loads run a whole segment ahead of their use.
-template <int S, int PM>
-__device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, u32* __restrict__ ext,
-                              u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, unsigned char* smem,
-                              int tid) {
+template <int S, int PM, bool UPD>
+__device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0,
+                              u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv,
+                              unsigned char* smem, int tid) {
   static_assert(S == 16, "segment = 4 chunks of 4 steps");
+  constexpr int PF = 3;                                        // L2 prefetch distance in segments
   const FastSmem<S> sm(smem);
   const int nseg = (W + S - 1) / S, nchunk = (W + 3) >> 2;
   const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
   const uint4* par4 = reinterpret_cast<const uint4*>(par);
+  const uint4* s04 = reinterpret_cast<const uint4*>(s0);
   u32 a[8];
-  uint4 sb[4], pb[4];
+  uint4 sb[4], pb[4], zb[4];
 
   // ---- forward sweep ------------------------------------------------------------------
 #pragma unroll
@@ -375,6 +390,10 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = __ldg(par4 + j * 4); }
   const int nfull = W / S;                                     // segments with all 16 steps
   for (int seg = 0; seg < nfull; ++seg) {
+    {                                                          // thread t warms L2 with chunk t of segment seg+PF
+      const int cp = (seg + PF) * 4 + t;
+      if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t); }
+    }
     ckpt_put(ck + seg * 32, a);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -433,12 +452,22 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = (nseg - 1) * 4 + j;
-    if (c < nchunk) { sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4); }
+    if (c < nchunk) {
+      sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4);
+      if (UPD) zb[j] = __ldg(s04 + c * 4);
+    }
   }
+  ckpt_get(ck + (nseg - 1) * 32, a);
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
     const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
-    ckpt_get(ck + seg * 32, a);
+    if (seg >= PF) {                              // warm L2 for segment seg-PF (inputs + checkpoint)
+      const int cp = (seg - PF) * 4 + t;
+      l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t);
+      if (UPD) l2_prefetch(s04 + cp * 4 - t);
+      if (t == 0) l2_prefetch(ck + (seg - PF) * 32);
+    }
+    // a holds the checkpoint of this segment (fetched during the previous segment's beta phase)
     if (steady) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -446,12 +475,18 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         for (int q = 0; q < 4; ++q) {
           const int e = j * 4 + q;
           if ((e & PM) == 0 && e != 0) renorm(a);
-          const FC c = fconst(pick4(sb[j], q), pick4(pb[j], q));
+          const u32 sv = pick4(sb[j], q);
+          const FC c = fconst(sv, pick4(pb[j], q));
           sm.put(e, tid, a);
           sm.putc(e, tid, c);
+          if (UPD) sm.putd(e, tid, __vsub2(pick4(zb[j], q), sv));
           if (e != S - 1) alpha_fast(a, c);
         }
-        if (seg > 0) { sb[j] = __ldg(sys4 + ((seg - 1) * 4 + j) * 4); pb[j] = __ldg(par4 + ((seg - 1) * 4 + j) * 4); }
+        if (seg > 0) {
+          const int cn = (seg - 1) * 4 + j;
+          sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4);
+          if (UPD) zb[j] = __ldg(s04 + cn * 4);
+        }
       }
     } else {
 #pragma unroll
@@ -461,13 +496,19 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
           const int e = j * 4 + q;
           if (k0 + e < k1) {
             if ((e & PM) == 0 && e != 0) renorm(a);
-            const FC c = fconst(pick4(sb[j], q), pick4(pb[j], q));
+            const u32 sv = pick4(sb[j], q);
+            const FC c = fconst(sv, pick4(pb[j], q));
             sm.put(e, tid, a);
             sm.putc(e, tid, c);
+            if (UPD) sm.putd(e, tid, __vsub2(pick4(zb[j], q), sv));
             alpha_fast(a, c);
           }
         }
-        if (seg > 0) { sb[j] = __ldg(sys4 + ((seg - 1) * 4 + j) * 4); pb[j] = __ldg(par4 + ((seg - 1) * 4 + j) * 4); }
+        if (seg > 0) {
+          const int cn = (seg - 1) * 4 + j;
+          sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4);
+          if (UPD) zb[j] = __ldg(s04 + cn * 4);
+        }
       }
     }
     if (seg == 0) {          // alpha[0..5] come from the re-run chain
@@ -479,6 +520,12 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (k < RERUN_STEPS) alpha_fast(a, sm.getc(k, tid));
       }
     }
+    // next segment's checkpoint: in flight during this segment's beta phase
+    uint4 cka = make_uint4(0, 0, 0, 0), ckb = cka;
+    if (seg > 0) {
+      cka = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[0];
+      ckb = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[1];
+    }
     if (steady) {
 #pragma unroll
       for (int j = 3; j >= 0; --j) {
@@ -489,6 +536,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
           const FC c = sm.getc(e, tid);
           sm.get(e, tid, a);
           e4[q] = ext_fast(a, b, c);
+          if (UPD) e4[q] = __vadd2(e4[q], sm.getd(e, tid));
           beta_fast(b, c);
           if ((e & PM) == 0) renorm(b);
         }
@@ -499,12 +547,15 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         const FC c = sm.getc(k - k0, tid);
         if (k <= W - 7) {
           sm.get(k - k0, tid, a);
-          ext[c4_word(k, 0)] = ext_fast(a, b, c);
+          u32 x = ext_fast(a, b, c);
+          if (UPD) x = __vadd2(x, sm.getd(k - k0, tid));
+          ext[c4_word(k, 0)] = x;
         }
         beta_fast(b, c);
         if ((k & PM) == 0) renorm(b);
       }
     }
+    a[0] = cka.x; a[1] = cka.y; a[2] = cka.z; a[3] = cka.w; a[4] = ckb.x; a[5] = ckb.y; a[6] = ckb.z; a[7] = ckb.w;
   }
 
   // ---- beta re-run over the last 5 steps, ext for the last 6 ------------------------------
@@ -520,8 +571,12 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     ckpt_get(ck + sa * 32, a);
     for (int k = sa * S; k < W; ++k) {
       if ((k & PM) == 0 && k != sa * S) renorm(a);
-      const FC c = fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
-      if (k >= kk0) { sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c); }
+      const u32 sv = __ldg(sys + c4_word(k, 0));
+      const FC c = fconst(sv, __ldg(par + c4_word(k, 0)));
+      if (k >= kk0) {
+        sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c);
+        if (UPD) sm.putd(k - kk0, tid, __vsub2(__ldg(s0 + c4_word(k, 0)), sv));
+      }
       if (k + 1 < W) alpha_fast(a, c);
     }
     if (kk0 <= RERUN_STEPS) {
@@ -536,7 +591,9 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     for (int k = W - 1; k >= kk0; --k) {
       const FC c = sm.getc(k - kk0, tid);
       sm.get(k - kk0, tid, a);
-      ext[c4_word(k, 0)] = ext_fast(a, b, c);
+      u32 x = ext_fast(a, b, c);
+      if (UPD) x = __vadd2(x, sm.getd(k - kk0, tid));
+      ext[c4_word(k, 0)] = x;
       if (k >= W - RERUN_STEPS) {
         beta_fast(b, c);
         if ((k & PM) == 0) renorm(b);
@@ -586,10 +643,18 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
   const int16_t* Tv = p.state[blk].T[p.term];
 
   unsigned char* smem = reinterpret_cast<unsigned char*>(abuf);
-  if (P >= 16)     map_pass_fast<S, 15>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
-  else if (P >= 4) map_pass_fast<S, 3>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
-  else if (P >= 1) map_pass_fast<S, 0>(sys, par, ext, ck, W, t, gmask, Tv, smem, tid);
-  else             map_pass<SatArith, S>(sys, par, ext, ck, W, t, gmask, Tv, abuf, tid);
+  const u32* s0 = reinterpret_cast<const u32*>(slot + (long)ARR_S0 * p.A) + t * 4;
+  if (p.upd) {
+    if (P >= 16)     map_pass_fast<S, 15, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else if (P >= 4) map_pass_fast<S, 3, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else if (P >= 1) map_pass_fast<S, 0, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else             map_pass<SatArith, S>(sys, par, s0, true, ext, ck, W, t, gmask, Tv, abuf, tid);
+  } else {
+    if (P >= 16)     map_pass_fast<S, 15, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else if (P >= 4) map_pass_fast<S, 3, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else if (P >= 1) map_pass_fast<S, 0, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
+    else             map_pass<SatArith, S>(sys, par, s0, false, ext, ck, W, t, gmask, Tv, abuf, tid);
+  }
 }
 
 }  // namespace oai

@@ -5,7 +5,7 @@
 //   k_demux16 : y (s,p1,p2 triples + 12 tail LLRs) -> S0/P1/P2 in C4 lane layout, tail
 //               metrics for the beta start of lane 7, max|y|
 //               (reference: 3gpplte_turbo_decoder_sse_16bit.c:1055-1189, 474-520)
-//   k_x1_16   : [ext = (ext (-) s1) (+) s0 ;] s2 = ext o pi            (:1354-1375, 1209-1231)
+//   k_x1_16   : s2 = ext o pi                                          (:1209-1231)
 //   k_x2_16   : s1 = (ext2 o pi^-1 (-) ext) (+) s0 ; hard decision, CRC, early exit
 //               (:1241-1351)
 // (+)/(-) are int16 saturating, always computed exactly here (SatArith) -- only the MAP
@@ -24,7 +24,8 @@ struct XchgArgs {
   long slot_hw;
   int A;                        // halfwords per array (multiple of 32)
   int nblk;
-  const uint16_t* pi_pool;      // QPP tables, pi[i] = (f1*i + f2*i*i) mod K
+  const uint16_t* pi_pool;      // per K: H[j] (K entries) = C4 halfword index of natural position j
+  const uint16_t* t_pool;       // per K: T[h] (A entries, layout order) = H[pi(pos(h))]; padding maps to itself
   const u32* crc_xp;            // [4][768]: x^(8m+w) mod P, per CRC type
   const int16_t* in_base;       // batch input (device)
   uint8_t* out_base;            // batch output (device)
@@ -64,22 +65,20 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (!(m.flags & 1)) { if (threadIdx.x == 0) st->status = 0xFE; return; }
-  const int K = m.K, W = m.W, A = p.A;
-  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  const int K = m.K, A = p.A;
   const int16_t* y = p.in_base + (((long)m.in_off_hi << 32) | m.in_off_lo);
   int16_t* s0 = sm, *p1 = sm + A, *p2 = sm + 2 * A;
   for (int i = threadIdx.x; i < 3 * A / 2; i += XCHG_THREADS) reinterpret_cast<u32*>(sm)[i] = 0;
   __syncthreads();
   int mx = 0;
-  for (int i = threadIdx.x; i < 3 * K + 12; i += XCHG_THREADS) {
-    int v = y[i];
-    mx = max(mx, abs(v));
-    if (i < 3 * K) {
-      int pos = i / 3, c = i - 3 * pos;
-      int h = pos_hw(pos, W, magic);
-      (c == 0 ? s0 : (c == 1 ? p1 : p2))[h] = (int16_t)v;
-    }
+  const uint16_t* H = p.pi_pool + m.pi_off;
+  for (int pos = threadIdx.x; pos < K; pos += XCHG_THREADS) {
+    const int h = H[pos];
+    const int v0 = y[3 * pos], v1 = y[3 * pos + 1], v2 = y[3 * pos + 2];
+    s0[h] = (int16_t)v0; p1[h] = (int16_t)v1; p2[h] = (int16_t)v2;
+    mx = max(max(mx, abs(v0)), max(abs(v1), abs(v2)));
   }
+  if (threadIdx.x < 12) mx = max(mx, abs((int)y[3 * K + threadIdx.x]));
   __syncthreads();
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
   for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
@@ -131,36 +130,30 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;
-  const int K = m.K, W = m.W, A = p.A;
-  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  const int A = p.A;
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
-  uint4* gext = reinterpret_cast<uint4*>(slot + (long)ARR_EXT * A);
+  const uint4* gext = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT * A);
   uint4* gsys = reinterpret_cast<uint4*>(slot + (long)ARR_SYS * A);
-  const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)ARR_S0 * A);
-  int16_t* in = sm, *out = sm + A;
-  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
-    uint4 e = gext[i];
-    if (p.iter > 1) {           // ext = (ext (-) s1) (+) s0, reference :1354-1375
-      uint4 s1 = gsys[i], s0 = gs0[i];
-      e.x = __vaddss2(__vsubss2(e.x, s1.x), s0.x);
-      e.y = __vaddss2(__vsubss2(e.y, s1.y), s0.y);
-      e.z = __vaddss2(__vsubss2(e.z, s1.z), s0.z);
-      e.w = __vaddss2(__vsubss2(e.w, s1.w), s0.w);
-      gext[i] = e;
-    }
-    reinterpret_cast<uint4*>(in)[i] = e;
-    reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
-  }
+  const int n8 = c4_words(m.W) >> 2;           // uint4 groups actually used by this K
+  int16_t* in = sm;
+  // (the feedback ext = (ext (-) s1) (+) s0 of reference :1354-1375 is applied by the MAP kernel
+  // that produced ext, see MapArgs::upd)
+  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) reinterpret_cast<uint4*>(in)[i] = gext[i];
   __syncthreads();
-  const uint16_t* pi = p.pi_pool + m.pi_off;
+  const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
   int mx = 0;
-  for (int i = threadIdx.x; i < K; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
-    int v = in[pos_hw(pi[i], W, magic)];
-    out[pos_hw(i, W, magic)] = (int16_t)v;
-    mx = max(mx, abs(v));
+  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
+    const uint4 tt = __ldg(T4 + i);
+    const u32 tw[4] = {tt.x, tt.y, tt.z, tt.w};
+    u32 o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const u32 lo = (uint16_t)in[tw[q] & 0xffffu], hi = (uint16_t)in[tw[q] >> 16];
+      o[q] = lo | (hi << 16);
+      mx = max(mx, absmax2(o[q]));
+    }
+    gsys[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) gsys[i] = reinterpret_cast<uint4*>(out)[i];
   mx = blk_max_reduce(mx, red);
   if (threadIdx.x == 0) st->max_sys = mx;
 }
@@ -182,31 +175,33 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int red[XCHG_THREADS / 32];
   __shared__ u32 xred[XCHG_THREADS / 32];
-  __shared__ uint8_t sbytes[768 + 8];
+  __shared__ __align__(16) uint8_t sbytes[768 + 32];
   const int blk = blockIdx.x;
   if (blk >= p.nblk) return;
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;
-  const int K = m.K, W = m.W, A = p.A;
-  const u32 magic = 0xffffffffu / (u32)W + 1u;
+  const int K = m.K, A = p.A;
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
   const uint4* gext2 = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT2 * A);
   const uint4* gext = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT * A);
   const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)ARR_S0 * A);
   uint4* gsys = reinterpret_cast<uint4*>(slot + (long)ARR_SYS * A);
-  int16_t* in = sm, *nat = sm + A;
-  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
-    reinterpret_cast<uint4*>(in)[i] = gext2[i];
-    reinterpret_cast<uint4*>(nat)[i] = make_uint4(0, 0, 0, 0);
+  const int n8 = c4_words(m.W) >> 2;
+  int16_t* nat = sm;
+  const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
+  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // ext2 back to natural order (scatter)
+    const uint4 v = gext2[i], tt = __ldg(T4 + i);
+    const u32 vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      nat[tw[q] & 0xffffu] = (int16_t)(vw[q] & 0xffffu);
+      nat[tw[q] >> 16] = (int16_t)(vw[q] >> 16);
+    }
   }
   __syncthreads();
-  const uint16_t* pi = p.pi_pool + m.pi_off;
-  for (int i = threadIdx.x; i < K; i += XCHG_THREADS)        // ext2 back to natural order
-    nat[pos_hw(pi[i], W, magic)] = in[pos_hw(i, W, magic)];
-  __syncthreads();
   int mx = 0;
-  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {   // s1 = (ext2 (-) ext) (+) s0, :1241-1265
+  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 (-) ext) (+) s0, :1241-1265
     uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i], r;
     r.x = __vaddss2(__vsubss2(d.x, e.x), s0.x);
     r.y = __vaddss2(__vsubss2(d.y, e.y), s0.y);
@@ -222,14 +217,17 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   if (p.iter > 1) {                                            // :1267-1351
     const int nb = K >> 3;
     uint8_t* outp = p.out_base + m.out_off;
-    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) {     // bit = ext2 > 0, MSB first
-      u32 v = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v = (v << 1) | (nat[pos_hw(8 * b + q, W, magic)] > 0 ? 1u : 0u);
-      sbytes[b] = (uint8_t)v;
-      outp[b] = (uint8_t)v;
+    const uint16_t* H = p.pi_pool + m.pi_off;
+    // bit = ext2 > 0 at natural position j, MSB first: one ballot per 32 positions
+    for (int j0 = (threadIdx.x & ~31); j0 < K; j0 += XCHG_THREADS) {
+      const int j = j0 + (threadIdx.x & 31);
+      const bool bit = (j < K) && (nat[H[j]] > 0);
+      const u32 mask = __ballot_sync(0xffffffffu, bit);
+      if ((threadIdx.x & 31) == 0)
+        *reinterpret_cast<u32*>(&sbytes[j0 >> 3]) = __byte_perm(__brev(mask), 0, 0x0123);
     }
     __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) outp[b] = sbytes[b];
     // CRC over `bits` bits starting at byte f0 (CRC24A skips the F filler bits, :1312-1313)
     const int ct = m.crc_type;
     const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);

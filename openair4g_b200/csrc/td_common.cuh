@@ -25,7 +25,8 @@ struct CbMeta {
   uint8_t  crc_type;
   uint8_t  F;
   uint8_t  flags;      // bit0: decode enabled
-  uint32_t pi_off;     // offset of this K's QPP table in the uint16 table pool
+  uint32_t pi_off;     // offset of this K's H table (natural position -> C4 halfword index)
+  uint32_t t_off;      // offset of this K's T table (layout order -> C4 index of the QPP image)
   uint32_t in_off_lo;  // input offset (int16 units) from the batch input base
   uint32_t in_off_hi;
   uint32_t out_off;    // output offset (bytes) from the batch output base
