@@ -103,16 +103,24 @@ static int ctx_get(int dev, DevCtx** out) {
     CU(cudaMemcpy(c.pi_pool, pool.data(), pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.t_pool, tpool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.t_pool, tpool.data(), tpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    // x^(8m+w) mod P for the four CRCs (polynomials: crc_byte.c:53-57)
-    std::vector<u32> xp(4 * 768);
+    // per-byte CRC remainders for the four CRCs (polynomials: crc_byte.c:53-57): entry
+    // [t][m][n] = n(x) * x^(8m + w + 4) mod P for the high nibble n (0..15) and
+    // [t][m][16+n] = n(x) * x^(8m + w) mod P for the low nibble of the byte m bytes before the end
+    std::vector<u32> xp(4 * 768 * 32);
     const u32 polys[4] = {0x864cfbu, 0x800063u, 0x1021u, 0x9Bu};
     const int ws[4] = {24, 24, 16, 8};
     for (int t = 0; t < 4; ++t) {
       u32 r = 1;
       for (int i = 0; i < ws[t]; ++i) r = gf_xtimes(r, polys[t], ws[t]);    // x^w
       for (int m = 0; m < 768; ++m) {
-        xp[t * 768 + m] = r;
-        for (int i = 0; i < 8; ++i) r = gf_xtimes(r, polys[t], ws[t]);
+        u32 pw[8];                                                            // x^(8m+w+i), i = 0..7
+        for (int i = 0; i < 8; ++i) { pw[i] = r; r = gf_xtimes(r, polys[t], ws[t]); }
+        for (int n = 0; n < 16; ++n) {
+          u32 lo = 0, hi = 0;
+          for (int i = 0; i < 4; ++i) if (n & (1 << i)) { lo ^= pw[i]; hi ^= pw[4 + i]; }
+          xp[(t * 768 + m) * 32 + n] = hi;
+          xp[(t * 768 + m) * 32 + 16 + n] = lo;
+        }
       }
     }
     CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
@@ -204,7 +212,7 @@ struct Batch {
     XchgArgs x;
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
-    x.status_out = status_dev; x.iter = 0;
+    x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B;
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B;
@@ -544,7 +552,7 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   XchgArgs x;
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
   x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
-  x.status_out = nullptr; x.iter = 0;
+  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B;
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
   MapArgs mp;
   mp.meta = b.d_meta; mp.state = b.d_state; mp.ws = b.d_ws; mp.slot_hw = b.slot_hw; mp.A = b.A;

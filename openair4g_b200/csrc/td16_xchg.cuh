@@ -26,11 +26,13 @@ struct XchgArgs {
   int nblk;
   const uint16_t* pi_pool;      // per K: H[j] (K entries) = C4 halfword index of natural position j
   const uint16_t* t_pool;       // per K: T[h] (A entries, layout order) = H[pi(pos(h))]; padding maps to itself
-  const u32* crc_xp;            // [4][768]: x^(8m+w) mod P, per CRC type
+  const u32* crc_xp;            // [4][768][32]: remainder of a high nibble v (entries 0..15) / low nibble (16..31)
+                                // of the byte m bytes before the end of the message: v(x) * x^(8m+w[+4]) mod P
   const int16_t* in_base;       // batch input (device)
   uint8_t* out_base;            // batch output (device)
   uint8_t* status_out;          // batch status bytes (device), written when a block finishes
   int iter;                     // iteration_cnt of the reference loop (1..max)
+  int guard_b;                  // MAP fast-path guard (same value as MapArgs::guard_b)
 };
 
 __device__ __forceinline__ int blk_max_reduce(int v, int* red) {
@@ -48,7 +50,23 @@ __device__ __forceinline__ int blk_max_reduce(int v, int* red) {
   return red[0];
 }
 
+__device__ __forceinline__ void warp_max_to(int v, int* dst) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(dst, v);
+}
+
 __device__ __forceinline__ int absmax2(u32 x) { return max(abs(lo16(x)), abs(hi16(x))); }
+
+// running per-halfword max and min (2 instructions per word); |.|max is taken once at the end
+struct MinMax2 {
+  u32 mx = 0x80008000u, mn = 0x7fff7fffu;
+  __device__ __forceinline__ void add(u32 w) { mx = __vmaxs2(mx, w); mn = __vmins2(mn, w); }
+  __device__ __forceinline__ void add(const uint4& v) { add(v.x); add(v.y); add(v.z); add(v.w); }
+  __device__ __forceinline__ int absmax() const {
+    return max(max(lo16(mx), hi16(mx)), max(-lo16(mn), -hi16(mn)));      // >= 0 once a value was added
+  }
+};
 
 // position p -> halfword index in the C4 layout; magic = floor(2^32/W)+1
 __device__ __forceinline__ int pos_hw(int p, int W, u32 magic) {
@@ -124,12 +142,13 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
-  __shared__ int red[XCHG_THREADS / 32];
+  __shared__ int smax;
   const int blk = blockIdx.x;
   if (blk >= p.nblk) return;
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;
+  if (threadIdx.x == 0) smax = 0;
   const int A = p.A;
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
   const uint4* gext = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT * A);
@@ -138,10 +157,14 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   int16_t* in = sm;
   // (the feedback ext = (ext (-) s1) (+) s0 of reference :1354-1375 is applied by the MAP kernel
   // that produced ext, see MapArgs::upd)
-  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) reinterpret_cast<uint4*>(in)[i] = gext[i];
+  MinMax2 mm;
+  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {
+    const uint4 e = gext[i];
+    mm.add(e);
+    reinterpret_cast<uint4*>(in)[i] = e;
+  }
   __syncthreads();
   const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
-  int mx = 0;
   for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
     const uint4 tt = __ldg(T4 + i);
     const u32 tw[4] = {tt.x, tt.y, tt.z, tt.w};
@@ -150,30 +173,19 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
     for (int q = 0; q < 4; ++q) {
       const u32 lo = (uint16_t)in[tw[q] & 0xffffu], hi = (uint16_t)in[tw[q] >> 16];
       o[q] = lo | (hi << 16);
-      mx = max(mx, absmax2(o[q]));
     }
     gsys[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  mx = blk_max_reduce(mx, red);
-  if (threadIdx.x == 0) st->max_sys = mx;
+  // s2 is a permutation of ext: same maximum
+  warp_max_to(mm.absmax(), &smax);
+  __syncthreads();
+  if (threadIdx.x == 0) { st->max_sys = smax; st->max_ext = smax; }
 }
 
 // ------------------------------------------------------------------------------------
-// GF(2) helpers for the parallel CRC: registers are right-aligned w-bit values.
-__device__ __forceinline__ u32 crc_byte_times(u32 byte, u32 xp, u32 poly, u32 topbit, u32 mask) {
-  // byte(x) * xp mod P, Horner over the 8 bits (MSB first)
-  u32 r = 0;
-#pragma unroll
-  for (int j = 7; j >= 0; --j) {
-    r = ((r << 1) & mask) ^ ((r & topbit) ? poly : 0u);
-    if ((byte >> j) & 1u) r ^= xp;
-  }
-  return r;
-}
-
 __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
-  __shared__ int red[XCHG_THREADS / 32];
+  __shared__ int smax;
   __shared__ u32 xred[XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
   const int blk = blockIdx.x;
@@ -181,6 +193,9 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;
+  if (threadIdx.x == 0) smax = 0;
+  // max_sys still describes the second decoder's input (written by k_x1_16 of this iteration)
+  const int guardB = max(st->max_sys, st->max_in) + st->max_in;
   const int K = m.K, A = p.A;
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
   const uint4* gext2 = reinterpret_cast<const uint4*>(slot + (long)ARR_EXT2 * A);
@@ -200,24 +215,51 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
     }
   }
   __syncthreads();
-  int mx = 0;
-  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 (-) ext) (+) s0, :1241-1265
-    uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i], r;
-    r.x = __vaddss2(__vsubss2(d.x, e.x), s0.x);
-    r.y = __vaddss2(__vsubss2(d.y, e.y), s0.y);
-    r.z = __vaddss2(__vsubss2(d.z, e.z), s0.z);
-    r.w = __vaddss2(__vsubss2(d.w, e.w), s0.w);
-    gsys[i] = r;
-    mx = max(max(mx, absmax2(r.x)), max(max(absmax2(r.y), absmax2(r.z)), absmax2(r.w)));
+  // When this block satisfies the MAP fast-path guard (B <= guard) its a-posteriori
+  // LLRs obey |ext2| <= 12(B+1)+276, so |ext2| + |ext| + |s0| stays inside int16 and the two
+  // saturating operations below are plain adds: 4 instead of 14 instructions per word.
+  const bool nosat = (guardB <= p.guard_b) && (12 * (guardB + 1) + 276 + st->max_ext + st->max_in <= 32767);
+  MinMax2 mm;
+  if (nosat) {
+    for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 - ext) + s0, :1241-1265
+      const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
+      uint4 r;
+      r.x = __vadd2(d.x, __vsub2(s0.x, e.x));
+      r.y = __vadd2(d.y, __vsub2(s0.y, e.y));
+      r.z = __vadd2(d.z, __vsub2(s0.z, e.z));
+      r.w = __vadd2(d.w, __vsub2(s0.w, e.w));
+      gsys[i] = r;
+      mm.add(r);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 (-) ext) (+) s0
+      const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
+      uint4 r;
+      r.x = __vaddss2(__vsubss2(d.x, e.x), s0.x);
+      r.y = __vaddss2(__vsubss2(d.y, e.y), s0.y);
+      r.z = __vaddss2(__vsubss2(d.z, e.z), s0.z);
+      r.w = __vaddss2(__vsubss2(d.w, e.w), s0.w);
+      gsys[i] = r;
+      mm.add(r);
+    }
   }
-  mx = blk_max_reduce(mx, red);
-  if (threadIdx.x == 0) st->max_sys = mx;
+  warp_max_to(mm.absmax(), &smax);
 
   bool pass = false;
   if (p.iter > 1) {                                            // :1267-1351
     const int nb = K >> 3;
     uint8_t* outp = p.out_base + m.out_off;
     const uint16_t* H = p.pi_pool + m.pi_off;
+    // CRC parameters.  The reference walks `bits` bits starting at byte f0 (CRC24A skips the F
+    // filler bits, :1312-1313) and compares with the trailing crc bytes of the block.  A CRC
+    // (zero start value, no final xor) is linear over GF(2): the remainder of the message is the
+    // XOR of the remainders of its bytes, each shifted by its distance from the message end.
+    const int ct = m.crc_type;
+    const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
+    const int j_lo = (ct == 0) ? ((m.F >> 3) << 3) : 0;
+    const int j_hi = j_lo + K - w - ((ct == 0) ? m.F : 0);     // message = bits [j_lo, j_hi)
+    const int f0 = j_lo >> 3, full = (j_hi - j_lo) >> 3, resbit = (j_hi - j_lo) & 7;
+    const u32* RB = p.crc_xp + ct * (768 * 32);
     // bit = ext2 > 0 at natural position j, MSB first: one ballot per 32 positions
     for (int j0 = (threadIdx.x & ~31); j0 < K; j0 += XCHG_THREADS) {
       const int j = j0 + (threadIdx.x & 31);
@@ -227,42 +269,42 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
         *reinterpret_cast<u32*>(&sbytes[j0 >> 3]) = __byte_perm(__brev(mask), 0, 0x0123);
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) outp[b] = sbytes[b];
-    // CRC over `bits` bits starting at byte f0 (CRC24A skips the F filler bits, :1312-1313)
-    const int ct = m.crc_type;
-    const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
-    const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
-    const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
-    const int f0 = (ct == 0) ? (m.F >> 3) : 0;
-    const int bits = K - w - ((ct == 0) ? m.F : 0);
-    const int full = bits >> 3, resbit = bits & 7;
-    const u32* xp = p.crc_xp + ct * 768;
+    // CRC of the `full` whole bytes: XOR of per-byte remainders (two nibble look-ups each)
     u32 acc = 0;
-    for (int b = threadIdx.x; b < full; b += XCHG_THREADS)
-      acc ^= crc_byte_times(sbytes[f0 + b], xp[full - 1 - b], poly, topbit, mask);
+    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) {
+      const u32 v = sbytes[b];
+      outp[b] = (uint8_t)v;
+      const int mdist = f0 + full - 1 - b;                     // bytes between this one and the message end
+      if (b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) xred[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
+      const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
+      const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
       u32 crc = 0;
       for (int i = 0; i < XCHG_THREADS / 32; ++i) crc ^= xred[i];
-      for (int j = 0; j < resbit; ++j) {                       // residual bits, crc_byte.c:130-131
-        u32 bit = (sbytes[f0 + full] >> (7 - j)) & 1u;
-        u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
+      for (int jb = 0; jb < resbit; ++jb) {                    // residual bits, crc_byte.c:130-131
+        const u32 bit = (sbytes[f0 + full] >> (7 - jb)) & 1u;
+        const u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
         crc = (crc << 1) & mask;
         if (top) crc ^= poly;
       }
-      u32 old;
-      if (w == 24) old = ((u32)sbytes[nb - 3] << 16) | ((u32)sbytes[nb - 2] << 8) | sbytes[nb - 1];
-      else if (w == 16) old = ((u32)sbytes[nb - 1] << 8) | sbytes[nb - 2];   // no byte swap, :1329-1333
-      else old = sbytes[nb - 1];
-      red[0] = (crc == old && crc != 0) ? 1 : 0;               // :1348
+      // received CRC as the reference assembles it: big-endian for the 24-bit CRCs (after its
+      // byte swap, :1314-1326), a little-endian 16-bit load for CRC16 (:1329-1333)
+      u32 rx;
+      if (w == 24) rx = ((u32)sbytes[nb - 3] << 16) | ((u32)sbytes[nb - 2] << 8) | sbytes[nb - 1];
+      else if (w == 16) rx = ((u32)sbytes[nb - 1] << 8) | sbytes[nb - 2];
+      else rx = sbytes[nb - 1];
+      pass = (crc == rx && crc != 0);                          // :1348
     }
+  } else {
     __syncthreads();
-    pass = red[0] != 0;
   }
   if (threadIdx.x == 0) {
+    st->max_sys = smax;
     int s = 0;
     if (pass) s = p.iter;
     else if (p.iter >= m.max_iter) s = m.max_iter + 1;

@@ -38,7 +38,7 @@ struct CbState {
   int32_t  max_in;     // max |y| over the 3K+12 inputs
   int32_t  max_sys;    // max |systematic input| of the next MAP pass
   int32_t  status;     // 0 = active, otherwise the decoder's return value
-  int32_t  pad;
+  int32_t  max_ext;    // max |ext| (first decoder's a-posteriori LLRs after feedback)
 };
 
 // workspace arrays of one block slot, each `A` halfwords long
