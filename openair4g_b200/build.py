@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "liboai_turbo_b200.so")
+LIB = os.environ.get("OAI_TURBO_LIB") or os.path.join(LIBDIR, "liboai_turbo_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -28,14 +28,16 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (tools/ use it for tuning sweeps)."""
+    target = out or LIB
+    if not force and out is None and not is_stale():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(os.path.dirname(target), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + sources()
     subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

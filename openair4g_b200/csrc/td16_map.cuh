@@ -372,7 +372,13 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
                               u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv,
                               unsigned char* smem, int tid) {
   static_assert(S == 16, "segment = 4 chunks of 4 steps");
-  constexpr int PF = 3;                                        // L2 prefetch distance in segments
+#ifndef MAP_PF_SEGS
+#define MAP_PF_SEGS 3
+#endif
+#ifndef MAP_FWD_DIST2
+#define MAP_FWD_DIST2 0
+#endif
+  constexpr int PF = MAP_PF_SEGS;                              // L2 prefetch distance in segments
   const FastSmem<S> sm(smem);
   const int nseg = (W + S - 1) / S, nchunk = (W + 3) >> 2;
   const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
@@ -389,8 +395,14 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   for (int j = 0; j < 4; ++j)
     if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = __ldg(par4 + j * 4); }
   const int nfull = W / S;                                     // segments with all 16 steps
+#if MAP_FWD_DIST2
+  uint4 sc[4], pc[4];                                          // segment seg+1 (registers are free in this phase)
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (4 + j < nchunk) { sc[j] = __ldg(sys4 + (4 + j) * 4); pc[j] = __ldg(par4 + (4 + j) * 4); }
+#endif
   for (int seg = 0; seg < nfull; ++seg) {
-    {                                                          // thread t warms L2 with chunk t of segment seg+PF
+    if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
       const int cp = (seg + PF) * 4 + t;
       if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t); }
     }
@@ -402,8 +414,14 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
         alpha_fast(a, fconst(pick4(sb[j], q), pick4(pb[j], q)));
       }
+#if MAP_FWD_DIST2
+      sb[j] = sc[j]; pb[j] = pc[j];
+      const int cn = (seg + 2) * 4 + j;
+      if (cn < nchunk) { sc[j] = __ldg(sys4 + cn * 4); pc[j] = __ldg(par4 + cn * 4); }
+#else
       const int cn = (seg + 1) * 4 + j;
       if (cn < nchunk) { sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4); }
+#endif
     }
     renorm(a);                                                 // checkpoints are stored normalised
   }
@@ -461,7 +479,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
     const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
-    if (seg >= PF) {                              // warm L2 for segment seg-PF (inputs + checkpoint)
+    if (PF > 0 && seg >= PF) {                    // warm L2 for segment seg-PF (inputs + checkpoint)
       const int cp = (seg - PF) * 4 + t;
       l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t);
       if (UPD) l2_prefetch(s04 + cp * 4 - t);
