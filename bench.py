@@ -262,10 +262,14 @@ def run_b200(args):
     if not same:
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
 
+    # final result gather (outside every timed region): per-rank block / bit / status counts
+    from openair4g_b200 import sharding
+    recs = sharding.gather_results(st_dev, B * K, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    per_rank = [{"blocks": int(r[0]), "info_bits": int(r[1]), "status_7": int(r[2 + MAX_ITER + 1])} for r in recs]
 
     # ---- roofline of the dominant kernel (k_map16: one MAP pass over all blocks per launch) ----
     peak, peak_src = measured_peaks()
@@ -310,7 +314,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "blocks_per_gpu_per_step": B, "e2e_blocks_per_gpu_per_step": Be,
                        "l2": "inputs larger than L2 (%.0f MB of LLRs per GPU per step, workspace %.0f MB)"
                              % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6),
-                       "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks"},
+                       "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
+                       "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,

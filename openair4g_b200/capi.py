@@ -104,8 +104,31 @@ def phy_threegpplte_turbo_decoder8(y, n, f1=0, f2=0, max_iterations=4, crc_type=
     return _decode_one(lib.phy_threegpplte_turbo_decoder8, y, n, f1, f2, max_iterations, crc_type, F, decoded_bytes)
 
 
+def generate_dummy_w(D, w, F):
+    """Marks the NULL positions in the uint8 array w (3*Kpi entries, modified in place); returns RTC."""
+    assert w.dtype == np.uint8 and w.flags["C_CONTIGUOUS"]
+    return int(lib.generate_dummy_w(D, w.ctypes.data, F))
+
+
+def lte_rate_matching_turbo_rx(RTC, G, w, dummy_w, soft_input, C_, Nsoft, Mdlharq, Kmimo, rvidx, clear, Qm, Nl, r):
+    """Reference call shape; w (int16, in place).  Returns (rc, E)."""
+    assert w.dtype == np.int16 and dummy_w.dtype == np.uint8 and soft_input.dtype == np.int16
+    E = C.c_uint32(0)
+    rc = lib.lte_rate_matching_turbo_rx(RTC, G, w.ctypes.data, dummy_w.ctypes.data, soft_input.ctypes.data, C_, Nsoft,
+                                        Mdlharq, Kmimo, rvidx, clear, Qm, Nl, r, C.byref(E))
+    return int(rc), int(E.value)
+
+
+def sub_block_deinterleaving_turbo(D, d_buf, d_offset, w):
+    """Writes into d_buf (int16) around element d_offset exactly what the reference writes around its `d`."""
+    assert d_buf.dtype == np.int16 and w.dtype == np.int16
+    lib.sub_block_deinterleaving_turbo(D, d_buf.ctypes.data + 2 * d_offset, w.ctypes.data)
+
+
 def decode_batch(blocks, flags=0, gpu=-1):
     """blocks: list of dicts {y, K, max_iterations, crc_type, F=0, tb_id=0, llr8=0, decode_enable=1}.
+    With "dematch": {G, C, r, rvidx, clear, Qm, Nl=1, Mdlharq=8, Kmimo=1, Nsoft=1827072, w=int16 array or None}
+    `y` is the block's slice of rate-matched soft bits e and the front end runs on the GPU first.
     One submit + wait; returns (list of uint8 arrays, list of status ints)."""
     n = len(blocks)
     descs = (CbDesc * n)()
@@ -127,6 +150,16 @@ def decode_batch(blocks, flags=0, gpu=-1):
         d.llr8 = b.get("llr8", 0)
         d.decode_enable = b.get("decode_enable", 1)
         d.tb_id = b.get("tb_id", 0)
+        dm = b.get("dematch")
+        if dm:
+            d.dematch_enable = 1
+            w = dm.get("w")
+            if w is not None:
+                assert w.dtype == np.int16 and w.flags["C_CONTIGUOUS"]
+                keep.append(w)
+                d.w = w.ctypes.data
+            d.G, d.C, d.r, d.rvidx, d.clear, d.Qm = dm["G"], dm["C"], dm["r"], dm["rvidx"], dm["clear"], dm["Qm"]
+            d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = dm.get("Nl", 1), dm.get("Mdlharq", 8), dm.get("Kmimo", 1), dm.get("Nsoft", 1827072)
     h = C.c_void_p()
     rc = lib.oai_turbo_submit_batch(descs, n, flags, gpu, C.byref(h))
     if rc != 0:

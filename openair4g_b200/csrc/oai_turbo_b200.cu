@@ -15,6 +15,7 @@
 #include "td_common.cuh"
 #include "td16_map.cuh"
 #include "td16_xchg.cuh"
+#include "rm_kernels.cuh"
 
 namespace oai {
 
@@ -263,6 +264,45 @@ static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long
 }
 
 
+
+// ---- rate-matching parameters (lte_rate_matching.c:719-735) ---------------------------------
+struct RmParams { uint32_t RTC, Kpi, ND, Ncb, k0, E; };
+static int rm_params(uint32_t K, uint32_t G, uint8_t C, uint32_t Nsoft, uint8_t Mdlharq, uint8_t Kmimo, uint8_t rvidx,
+                     uint8_t Qm, uint8_t Nl, uint8_t r, uint32_t RTC_in, RmParams* o) {
+  if (Kmimo == 0 || Mdlharq == 0 || C == 0 || Qm == 0 || Nl == 0) return -1;       // :713-717
+  const uint32_t D = K + 4;
+  o->RTC = RTC_in ? RTC_in : (D >> 5) + ((D & 31) ? 1 : 0);
+  o->Kpi = o->RTC << 5;
+  o->ND = o->Kpi - D;
+  const uint32_t Nir = Nsoft / Kmimo / (Mdlharq < 8 ? Mdlharq : 8);
+  o->Ncb = std::min<uint32_t>(Nir / C, 3 * o->Kpi);
+  const uint32_t Gp = G / Nl / Qm, GpmodC = Gp % C;
+  o->E = (r < (uint32_t)(C - GpmodC)) ? Nl * Qm * (Gp / C) : Nl * Qm * ((GpmodC == 0 ? 0 : 1) + (Gp / C));
+  const uint32_t Ncbmod = o->Ncb % (o->RTC << 3);
+  o->k0 = o->RTC * (2 + (rvidx * (((Ncbmod == 0) ? 0 : 1) + (o->Ncb / (o->RTC << 3))) * 2));
+  return 0;
+}
+
+// per-thread scratch for the single-call reference entry points of the front end
+struct Scratch {
+  cudaStream_t st = nullptr;
+  void* h = nullptr; void* d = nullptr; size_t cap = 0;
+  int ensure(size_t bytes) {
+    DevCtx* c;
+    int rc = ctx_get(-1, &c);
+    if (rc) return rc;
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (bytes > cap) {
+      if (h) { cudaFreeHost(h); cudaFree(d); }
+      cap = bytes + (bytes >> 2) + 4096;
+      CU(cudaMallocHost(&h, cap));
+      CU(cudaMalloc(&d, cap));
+    }
+    return 0;
+  }
+};
+static thread_local Scratch t_scratch;
+
 // ---- host-buffer batches: pinned staging + one stream per batch object ---------------
 struct HostBatch {
   Batch b;
@@ -273,6 +313,13 @@ struct HostBatch {
   int16_t* h_in = nullptr;  int16_t* d_in = nullptr;
   uint8_t* h_out = nullptr; uint8_t* d_out = nullptr;
   uint8_t* h_status = nullptr; uint8_t* d_status = nullptr;
+  // fused front end (dematch + deinterleave): soft-bit pool, HARQ w pool, per-block parameters
+  size_t cap_e = 0, cap_w = 0; int cap_rm = 0;
+  int16_t* h_e = nullptr; int16_t* d_e = nullptr;
+  int16_t* h_w = nullptr; int16_t* d_w = nullptr;
+  RmBlock* d_rm = nullptr;
+  std::vector<RmBlock> rm;
+  std::vector<int> rm_desc;        // descriptor index of each RmBlock
   // bookkeeping of the submitted batch
   std::vector<oai_cb_desc_t> descs;
   std::vector<int> order;          // GPU block i <-> descriptor order[i]
@@ -310,8 +357,32 @@ struct HostBatch {
     }
     return 0;
   }
+  int ensure_rm(size_t e_hw, size_t w_hw, int nrm) {
+    if (e_hw > cap_e) {
+      if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); }
+      cap_e = e_hw;
+      CU(cudaMallocHost(&h_e, cap_e * sizeof(int16_t)));
+      CU(cudaMalloc(&d_e, cap_e * sizeof(int16_t)));
+    }
+    if (w_hw > cap_w) {
+      if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); }
+      cap_w = w_hw;
+      CU(cudaMallocHost(&h_w, cap_w * sizeof(int16_t)));
+      CU(cudaMalloc(&d_w, cap_w * sizeof(int16_t)));
+    }
+    if (nrm > cap_rm) {
+      if (d_rm) cudaFree(d_rm);
+      cap_rm = nrm;
+      CU(cudaMalloc(&d_rm, sizeof(RmBlock) * cap_rm));
+    }
+    return 0;
+  }
   void release() {
     b.release();
+    if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); h_e = nullptr; d_e = nullptr; }
+    if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); h_w = nullptr; d_w = nullptr; }
+    if (d_rm) { cudaFree(d_rm); d_rm = nullptr; }
+    cap_e = cap_w = 0; cap_rm = 0;
     if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); h_in = nullptr; d_in = nullptr; }
     if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); h_out = nullptr; d_out = nullptr; }
     if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
@@ -328,8 +399,9 @@ struct HostBatch {
       const oai_cb_desc_t& d = descs[i];
       if (d.crc_type > 3 || qpp_index(d.K) < 0) { if (d.status) *d.status = 255; continue; }   // TD16:1003-1018
       if (d.llr8) return fail(-3, "8-bit decoder not built yet");
-      if (d.dematch_enable) return fail(-3, "fused dematch front end not built yet");
-      if (!d.decode_enable) { if (d.status) *d.status = 0xFE; continue; }
+      // without the front end a block that is not decoded needs no GPU work at all; with it the
+      // HARQ buffer is still combined (dlsch_decoding.c:333-385 runs before the err_flag test)
+      if (!d.decode_enable && !d.dematch_enable) { if (d.status) *d.status = 0xFE; continue; }
       order.push_back(i);
       Kmax = std::max<int>(Kmax, d.K);
     }
@@ -348,17 +420,53 @@ struct HostBatch {
     int rc = ensure(gpu, n, Kmax, in_hw, out_b);
     if (rc) return rc;
     std::vector<CbMeta> meta(n);
+    rm.clear(); rm_desc.clear();
+    size_t e_hw = 0, w_hw = 0;
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
-      make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, 1, (long)in_off[i], (long)out_off[i], &meta[i]);
+      make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i]);
+      if (d.dematch_enable) {
+        RmParams q;
+        if (rm_params(d.K, d.G, d.C, d.Nsoft, d.Mdlharq, d.Kmimo, d.rvidx, d.Qm, d.Nl, d.r, 0, &q))
+          return fail(-4, "invalid rate-matching parameters for block %d (lte_rate_matching_turbo_rx returns -1)", order[i]);
+        RmBlock rb;
+        memset(&rb, 0, sizeof(rb));
+        rb.K = d.K; rb.F = d.F; rb.RTC = q.RTC; rb.Kpi = q.Kpi; rb.ND = q.ND; rb.Ncb = q.Ncb; rb.k0 = q.k0; rb.E = q.E;
+        rb.clear = d.clear; rb.w_off = (uint32_t)w_hw;
+        rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
+        rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
+        rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
+        e_hw += ((size_t)q.E + 7) & ~(size_t)7;
+        w_hw += (size_t)3 * q.Kpi;
+        rm.push_back(rb); rm_desc.push_back(order[i]);
+      }
+    }
+    if (!rm.empty()) {
+      rc = ensure_rm(e_hw, w_hw, (int)rm.size());
+      if (rc) return rc;
+      for (size_t j = 0; j < rm.size(); ++j) {
+        const oai_cb_desc_t& d = descs[rm_desc[j]];
+        const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
+        memcpy(h_e + eo, d.in, sizeof(int16_t) * rm[j].E);
+        if (d.w) memcpy(h_w + rm[j].w_off, d.w, sizeof(int16_t) * 3 * rm[j].Kpi);
+        else memset(h_w + rm[j].w_off, 0, sizeof(int16_t) * 3 * rm[j].Kpi);
+      }
+      CU(cudaMemcpyAsync(d_e, h_e, e_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
+      k_rm_rx<<<(int)rm.size(), RM_THREADS, 0, st>>>(d_rm, (int)rm.size(), d_w, d_e, nullptr);
+      k_deint<<<(int)rm.size(), RM_THREADS, 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t), st>>>(d_rm, (int)rm.size(), d_w, d_in, 0);
+      g_launches += 2;
+      CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     }
     // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
     // page-locked caller memory is copied from directly, pageable memory through the pinned stage
     for (int i = 0; i < n;) {
+      if (descs[order[i]].dematch_enable) { ++i; continue; }     // y is produced on the device by k_deint
       const int16_t* base = descs[order[i]].in;
       size_t len = (size_t)3 * descs[order[i]].K + 12;
       int j = i + 1;
-      while (j < n && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
+      while (j < n && !descs[order[j]].dematch_enable && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
       cudaPointerAttributes at;
       bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
       cudaGetLastError();
@@ -382,9 +490,14 @@ struct HostBatch {
     if (n) CU(cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
+      if (!d.decode_enable) { if (d.status) *d.status = 0xFE; continue; }
       // the reference leaves decoded_bytes untouched when max_iterations < 2 (no hard decision, TD16:1267)
       if (d.decoded_bytes && d.max_iterations >= 2) memcpy(d.decoded_bytes, h_out + out_off[i], d.K >> 3);
       if (d.status) *d.status = h_status[i];
+    }
+    for (size_t j = 0; j < rm.size(); ++j) {                     // HARQ buffers back to their owners
+      const oai_cb_desc_t& d = descs[rm_desc[j]];
+      if (d.w) memcpy(d.w, h_w + rm[j].w_off, sizeof(int16_t) * rm[j].Ncb);
     }
     if (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) {
       // dlsch_decoding.c:400,417,448-451: after the first failing block of a transport block the
@@ -525,12 +638,77 @@ unsigned char phy_threegpplte_turbo_decoder8(short*, unsigned char*, unsigned sh
   return 255;
 }
 
-uint32_t generate_dummy_w(uint32_t, uint8_t*, uint8_t) { fail(-3, "generate_dummy_w: not built yet"); return 0; }
-int lte_rate_matching_turbo_rx(uint32_t, uint32_t, int16_t*, uint8_t*, int16_t*, uint8_t, uint32_t, uint8_t, uint8_t,
-                               uint8_t, uint8_t, uint8_t, uint8_t, uint8_t, uint32_t*) {
-  return fail(-3, "lte_rate_matching_turbo_rx: not built yet");
+uint32_t generate_dummy_w(uint32_t D, uint8_t* w, uint8_t F) {
+  const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
+  Scratch& sc = t_scratch;
+  if (sc.ensure(3 * (size_t)Kpi)) { fprintf(stderr, "[oai_turbo_b200] generate_dummy_w: GPU path failed (%s)\n", g_err); return RTC; }
+  memcpy(sc.h, w, 3 * (size_t)Kpi);
+  cudaMemcpyAsync(sc.d, sc.h, 3 * (size_t)Kpi, cudaMemcpyHostToDevice, sc.st);
+  k_dummy_w<<<(3 * Kpi + 255) / 256, 256, 0, sc.st>>>((uint8_t*)sc.d, RTC, Kpi, ND, F);
+  ++g_launches;
+  cudaMemcpyAsync(sc.h, sc.d, 3 * (size_t)Kpi, cudaMemcpyDeviceToHost, sc.st);
+  if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "generate_dummy_w: CUDA failure"); return RTC; }
+  memcpy(w, sc.h, 3 * (size_t)Kpi);
+  return RTC;
 }
-void sub_block_deinterleaving_turbo(uint32_t, int16_t*, int16_t*) { fail(-3, "sub_block_deinterleaving_turbo: not built yet"); }
+
+int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* dummy_w, int16_t* soft_input, uint8_t C,
+                               uint32_t Nsoft, uint8_t Mdlharq, uint8_t Kmimo, uint8_t rvidx, uint8_t clear, uint8_t Qm,
+                               uint8_t Nl, uint8_t r, uint32_t* E_out) {
+  RmParams q;
+  if (Kmimo == 0 || Mdlharq == 0 || C == 0 || Qm == 0 || Nl == 0) {
+    printf("lte_rate_matching.c: invalid parameters (Kmimo %d, Mdlharq %d, C %d, Qm %d, Nl %d\n", Kmimo, Mdlharq, C, Qm, Nl);
+    return -1;
+  }
+  // K is not an argument of the reference call; everything it needs follows from RTC
+  rm_params(32 * RTC - 4, G, C, Nsoft, Mdlharq, Kmimo, rvidx, Qm, Nl, r, RTC, &q);
+  Scratch& sc = t_scratch;
+  // layout of the scratch buffer: [RmBlock][w: Ncb int16][dummy: Ncb bytes][e: E int16]
+  const size_t o_w = 256, o_dm = o_w + (((size_t)q.Ncb * 2 + 255) & ~(size_t)255), o_e = o_dm + (((size_t)q.Ncb + 255) & ~(size_t)255);
+  const size_t total = o_e + (size_t)q.E * 2 + 256;
+  if (sc.ensure(total)) return fail(-100, "lte_rate_matching_turbo_rx: GPU path failed (%s)", g_err);
+  RmBlock b;
+  memset(&b, 0, sizeof(b));
+  b.K = 32 * RTC - 4; b.F = 0; b.RTC = RTC; b.Kpi = q.Kpi; b.ND = 0; b.Ncb = q.Ncb; b.k0 = q.k0; b.E = q.E; b.clear = clear;
+  b.w_off = 0; b.e_off_lo = 0; b.e_off_hi = 0; b.dummy_off = 0;
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  memcpy(h, &b, sizeof(b));
+  if (clear != 1) memcpy(h + o_w, w, (size_t)q.Ncb * 2);
+  memcpy(h + o_dm, dummy_w, q.Ncb);
+  memcpy(h + o_e, soft_input, (size_t)q.E * 2);
+  CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, sc.st));
+  k_rm_rx<<<1, RM_THREADS, 0, sc.st>>>((const RmBlock*)d, 1, (int16_t*)(d + o_w), (const int16_t*)(d + o_e), (const uint8_t*)(d + o_dm));
+  ++g_launches;
+  CU(cudaMemcpyAsync(h + o_w, d + o_w, (size_t)q.Ncb * 2, cudaMemcpyDeviceToHost, sc.st));
+  CU(cudaStreamSynchronize(sc.st));
+  memcpy(w, h + o_w, (size_t)q.Ncb * 2);
+  *E_out = q.E;
+  return 0;
+}
+
+void sub_block_deinterleaving_turbo(uint32_t D, int16_t* dd, int16_t* w) {
+  const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
+  Scratch& sc = t_scratch;
+  const size_t o_w = 256, o_y = o_w + (((size_t)3 * Kpi * 2 + 255) & ~(size_t)255), total = o_y + ((size_t)3 * Kpi + 3) * 2 + 256;
+  if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] sub_block_deinterleaving_turbo: GPU path failed (%s)\n", g_err); return; }
+  RmBlock b;
+  memset(&b, 0, sizeof(b));
+  b.K = D - 4; b.RTC = RTC; b.Kpi = Kpi; b.ND = ND; b.w_off = 0; b.y_off_lo = 0; b.y_off_hi = 0;
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  memcpy(h, &b, sizeof(b));
+  memcpy(h + o_w, w, (size_t)3 * Kpi * 2);
+  cudaMemcpyAsync(d, h, o_y, cudaMemcpyHostToDevice, sc.st);
+  k_deint<<<1, RM_THREADS, 3 * Kpi * sizeof(int16_t), sc.st>>>((const RmBlock*)d, 1, (const int16_t*)(d + o_w), (int16_t*)(d + o_y), 1);
+  ++g_launches;
+  cudaMemcpyAsync(h + o_y, d + o_y, ((size_t)3 * Kpi + 3) * 2, cudaMemcpyDeviceToHost, sc.st);
+  if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "sub_block_deinterleaving_turbo: CUDA failure"); return; }
+  // the reference writes d1[q], d1 = d - 3*ND, for q in [0, 3*Kpi+3) except q = 2, 3*Kpi, 3*Kpi+1 (:216-231)
+  const int16_t* y = (const int16_t*)(h + o_y);
+  int16_t* d1 = dd - 3 * (long)ND;
+  d1[0] = y[0]; d1[1] = y[1];
+  memcpy(d1 + 3, y + 3, ((size_t)3 * Kpi - 3) * 2);
+  d1[3 * Kpi + 2] = y[3 * Kpi + 2];
+}
 
 // Kernel-level test hook: one MAP pass (demux + k_map16) on a single block; the systematic
 // input is the channel systematic stream, the parity stream is p1 (term=0) or p2 (term=1).

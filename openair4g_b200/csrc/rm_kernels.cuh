@@ -1,0 +1,124 @@
+// Receive-side rate dematching, NULL map and sub-block deinterleaving on the GPU.
+//
+//   k_dummy_w   : generate_dummy_w                (reference: lte_rate_matching.c:293-382)
+//   k_rm_rx     : lte_rate_matching_turbo_rx      (reference: lte_rate_matching.c:688-831)
+//   k_deint     : sub_block_deinterleaving_turbo  (reference: lte_rate_matching.c:193-243)
+//
+// One CTA per code block.  The reference's dematching loop is serial: it walks the circular
+// buffer from k0, skips NULL slots and adds soft bit k to the k-th non-NULL slot it meets,
+// wrapping around until E bits are consumed.  Parallel form: with N non-NULL slots in
+// [0,Ncb) and rank(ind) = number of non-NULL slots met before ind on that walk, slot ind
+// receives e[rank], e[rank+N], e[rank+2N], ... (< E).  int16 accumulation WRAPS in the
+// reference (plain `+=`, :749,765), so the sum is order-independent mod 2^16 and exact.
+#pragma once
+#include "td_common.cuh"
+
+namespace oai {
+
+constexpr int RM_THREADS = 256;
+
+struct RmBlock {
+  uint32_t K, F;            // block size, filler bits (F only used when dummy == nullptr)
+  uint32_t RTC, Kpi, ND;    // rows, 32*RTC, Kpi - (K+4)
+  uint32_t Ncb, k0, E;      // circular buffer length, start, soft bits of this block
+  uint32_t clear;
+  uint32_t w_off;           // int16 offset of this block's w in the w pool (3*Kpi entries)
+  uint32_t e_off_lo, e_off_hi;   // int16 offset of this block's soft bits in the input pool
+  uint32_t dummy_off;       // byte offset of a caller-provided NULL map, or 0xffffffff: derive from (K,F)
+  uint32_t y_off_lo, y_off_hi;   // int16 offset of the decoder input y (3K+12) written by k_deint
+};
+
+__device__ __forceinline__ uint32_t brev5(uint32_t c) { return __brev(c) >> 27; }
+
+// NULL predicate of generate_dummy_w for circular-buffer index `ind` (reference :329-370).
+// Only rows 0..2 are ever marked for streams 0/1 and row 0 for stream 2 -- restated as is.
+__device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F) {
+  if (ind < Kpi) {                                   // stream 0: w[k], k = col*RTC + row
+    const uint32_t col = ind / RTC, row = ind - col * RTC;
+    return row <= 2 && brev5(col) + 32 * row < ND + F;
+  }
+  const uint32_t j = ind - Kpi, k = j >> 1;
+  const uint32_t col = k / RTC, row = k - col * RTC;
+  if ((j & 1) == 0) return row <= 2 && brev5(col) + 32 * row < ND + F;       // stream 1: w[Kpi+2k]
+  if (ND > 0 && ind == 3 * Kpi - 1) return true;                               // :369-370
+  return row == 0 && brev5(col) + 1 < ND;                                      // stream 2: w[Kpi+2k+1]
+}
+
+// generate_dummy_w on a device copy of the caller's buffer: only SETS LTE_NULL (=2)
+__global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * Kpi; i += gridDim.x * blockDim.x)
+    if (dummy_is_null(i, RTC, Kpi, ND, F)) w[i] = 2;
+}
+
+__global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
+                                                      const int16_t* e_pool, const uint8_t* dummy_pool) {
+  __shared__ uint32_t s_cnt[RM_THREADS + 1];
+  const int blk = blockIdx.x;
+  if (blk >= nblk) return;
+  const RmBlock b = blocks[blk];
+  int16_t* w = w_pool + b.w_off;
+  const int16_t* e = e_pool + (((long)b.e_off_hi << 32) | b.e_off_lo);
+  const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
+  auto is_null = [&](uint32_t ind) -> bool {
+    return dm ? (dm[ind] == 2) : dummy_is_null(ind, b.RTC, b.Kpi, b.ND, b.F);
+  };
+  // each thread owns a contiguous run of the circular buffer
+  const uint32_t per = (b.Ncb + RM_THREADS - 1) / RM_THREADS;
+  const uint32_t lo = min(b.Ncb, threadIdx.x * per), hi = min(b.Ncb, lo + per);
+  uint32_t cnt = 0;
+  for (uint32_t i = lo; i < hi; ++i) cnt += is_null(i) ? 0u : 1u;
+  s_cnt[threadIdx.x + 1] = cnt;
+  if (threadIdx.x == 0) s_cnt[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0)                                // 256 values: a serial scan is negligible here
+    for (int i = 1; i <= RM_THREADS; ++i) s_cnt[i] += s_cnt[i - 1];
+  __syncthreads();
+  const uint32_t N = s_cnt[RM_THREADS];                 // non-NULL slots in [0,Ncb)
+  if (N == 0) return;                                   // (the reference would loop forever)
+  // non-NULL slots before `start`; the first reference loop runs only when k0 < Ncb (:747)
+  const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
+  const uint32_t st_t = min((uint32_t)RM_THREADS - 1, start / per);
+  uint32_t before_start = s_cnt[st_t];
+  for (uint32_t i = st_t * per; i < start; ++i) before_start += is_null(i) ? 0u : 1u;
+  uint32_t c = s_cnt[threadIdx.x];
+  for (uint32_t i = lo; i < hi; ++i) {
+    const bool nul = is_null(i);
+    int acc = (b.clear == 1) ? 0 : (int)w[i];          // memset(w,0,Ncb) when clear==1 (:741-742)
+    if (!nul) {
+      const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
+      for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+      ++c;
+    }
+    w[i] = (int16_t)acc;                               // wraps like the reference's int16 +=
+  }
+}
+
+// w (three sub-blocks) -> d triples.  Output element q of d1 = d - 3*ND (reference :216-231):
+//   q = 3*idx   <- w[k], q = 3*idx+1 <- w[Kpi+2k], q = 3*idx+5 <- w[Kpi+2k+1],  k = brev5(idx&31)*RTC + (idx>>5)
+// Elements q = 2, 3*Kpi, 3*Kpi+1 are never written by the reference.  out[q - q_lo] for q in [q_lo,q_hi).
+__global__ void __launch_bounds__(RM_THREADS) k_deint(const RmBlock* blocks, int nblk, const int16_t* w_pool,
+                                                      int16_t* y_pool, int api_mode) {
+  extern __shared__ int16_t sw[];
+  const int blk = blockIdx.x;
+  if (blk >= nblk) return;
+  const RmBlock b = blocks[blk];
+  const int16_t* w = w_pool + b.w_off;
+  for (uint32_t i = threadIdx.x; i < 3 * b.Kpi / 2; i += RM_THREADS)
+    reinterpret_cast<uint32_t*>(sw)[i] = reinterpret_cast<const uint32_t*>(w)[i];
+  __syncthreads();
+  int16_t* y = y_pool + (((long)b.y_off_hi << 32) | b.y_off_lo);
+  // api_mode: the whole range the reference touches, q in [0, 3*Kpi+3) (y points at d1[0]);
+  // batch mode: the decoder input only, q in [3*ND, 3*ND + 3K+12) (y points at d[0])
+  const uint32_t q_lo = api_mode ? 0 : 3 * b.ND;
+  const uint32_t q_hi = api_mode ? 3 * b.Kpi + 3 : 3 * b.ND + 3 * b.K + 12;
+  for (uint32_t q = q_lo + threadIdx.x; q < q_hi; q += RM_THREADS) {
+    const uint32_t r = q % 3;
+    if (q == 2 || q == 3 * b.Kpi || q == 3 * b.Kpi + 1) continue;
+    const uint32_t idx = (r == 2) ? (q - 5) / 3 : q / 3;
+    const uint32_t k = brev5(idx & 31) * b.RTC + (idx >> 5);
+    const int16_t v = (r == 0) ? sw[k] : (r == 1 ? sw[b.Kpi + 2 * k] : sw[b.Kpi + 2 * k + 1]);
+    y[q - q_lo] = v;
+  }
+}
+
+}  // namespace oai
