@@ -190,14 +190,16 @@ def run_b200(args):
     from openair4g_b200 import capi
     capi.init_td16()
 
-    B, K = args.blocks, K_BITS
+    B, K = args.blocks, (args.K if args.llr8 else K_BITS)
+    if args.llr8:
+        return run_llr8(args, capi, B, K, rank, world, dist)
     row = 3 * K + 12
     g = torch.Generator(device="cuda")
     g.manual_seed(1000 + rank)
     y_dev = torch.randint(-16, 17, (B, row), dtype=torch.int16, device="cuda", generator=g)
     out_dev = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
     st_dev = torch.zeros(B, dtype=torch.uint8, device="cuda")
-    plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE)
+    plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE, llr8=1 if args.llr8 else 0)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
@@ -326,6 +328,34 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_llr8(args, capi, B, K, rank, world, dist):
+    """Side measurement (BASELINE configs[4]): 8-bit decoder throughput, device-resident, same timing rules."""
+    import torch
+    row = 3 * K + 12 + 4
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1000 + rank)
+    y_dev = torch.randint(-16, 17, (B, row), dtype=torch.int16, device="cuda", generator=g)
+    out_dev = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
+    st_dev = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE, llr8=1)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(args.warmup):
+        plan.decode(y_dev.data_ptr(), row, out_dev.data_ptr(), K // 8, st_dev.data_ptr(), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.decode(y_dev.data_ptr(), row, out_dev.data_ptr(), K // 8, st_dev.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"metric": "turbo_decoded_info_mbit_per_s_8bit_decoder", "value": B * K * args.steps / (ms * 1e-3) / 1e6,
+                      "unit": "Mbit/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                      "dtype": "int8", "data": "synthetic",
+                      "config": {"workload": "8-bit decoder, K=%d, max_iterations=6, noise regime" % K, "blocks": B},
+                      "status_hist": torch.bincount(st_dev.long()).nonzero().flatten().tolist()}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +368,8 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=4096, help="code blocks per GPU per step (host-buffer API)")
     ap.add_argument("--cpu-blocks", type=int, default=8192, help="bounded CPU-baseline sample (blocks)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
+    ap.add_argument("--K", type=int, default=K_BITS, help="block size for --llr8 / side measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

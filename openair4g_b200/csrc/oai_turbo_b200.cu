@@ -16,6 +16,7 @@
 #include "td16_map.cuh"
 #include "td16_xchg.cuh"
 #include "rm_kernels.cuh"
+#include "td8_kernels.cuh"
 
 namespace oai {
 
@@ -62,6 +63,8 @@ struct DevCtx {
   uint16_t* pi_pool = nullptr;        // H tables of all 188 K (natural position -> C4 halfword index)
   uint16_t* t_pool = nullptr;         // T tables (layout order -> C4 index of the QPP image)
   uint32_t pi_off[188], t_off[188];
+  uint16_t* qpp_pool = nullptr;       // plain QPP tables pi[i] (8-bit decoder kernels)
+  uint32_t qpp_off[188];
   u32* crc_xp = nullptr;              // [4][768]
   bool ok = false;
 };
@@ -83,11 +86,12 @@ static int ctx_get(int dev, DevCtx** out) {
     int prev = 0;
     CU(cudaGetDevice(&prev));
     CU(cudaSetDevice(dev));
-    std::vector<uint16_t> pool, tpool;
+    std::vector<uint16_t> pool, tpool, qpool;
     for (int i = 0; i < 188; ++i) {
       const int K = qpp_K(i), W = K / 8, A = c4_words(W) * 2;
       c.pi_off[i] = (uint32_t)pool.size();
       c.t_off[i] = (uint32_t)tpool.size();
+      c.qpp_off[i] = (uint32_t)qpool.size();
       const uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
       std::vector<uint16_t> H(K), T(A);
       for (int j = 0; j < K; ++j) H[j] = (uint16_t)c4_hw(j % W, j / W);
@@ -95,6 +99,7 @@ static int ctx_get(int dev, DevCtx** out) {
       for (uint64_t j = 0; j < (uint64_t)K; ++j) {
         const uint64_t pj = (f1 * j + f2 * j * j) % (uint64_t)K;           // pi(j), 36.212 5.1.3.2.3
         T[H[j]] = H[pj];
+        qpool.push_back((uint16_t)pj);
       }
       pool.insert(pool.end(), H.begin(), H.end());
       while (pool.size() & 7) pool.push_back(0);
@@ -102,6 +107,8 @@ static int ctx_get(int dev, DevCtx** out) {
     }
     CU(cudaMalloc(&c.pi_pool, pool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.pi_pool, pool.data(), pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.qpp_pool, qpool.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(c.qpp_pool, qpool.data(), qpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.t_pool, tpool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.t_pool, tpool.data(), tpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     // per-byte CRC remainders for the four CRCs (polynomials: crc_byte.c:53-57): entry
@@ -250,12 +257,81 @@ struct Batch {
   }
 };
 
-static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long in_off, long out_off, CbMeta* m) {
+
+// ---- 8-bit decoder batch (TD8): int8 per-position arrays + full alpha/beta arrays in HBM ----
+struct Batch8 {
+  DevCtx* ctx = nullptr;
+  int cap = 0, n = 0, A = 0, max_iter = 0;
+  long slot_b = 0, ab_b = 0;
+  CbMeta* d_meta = nullptr;
+  CbState* d_state = nullptr;
+  int8_t* d_ws = nullptr;
+  int8_t* d_ab = nullptr;
+  std::vector<CbMeta> h_meta;
+  int alloc(DevCtx* c, int ncb, int Kmax) {
+    ctx = c; cap = ncb;
+    A = (Kmax + 15) & ~15;
+    slot_b = (long)A8_COUNT * A;
+    ab_b = 2L * 128 * (Kmax / 16 + 1);
+    CU(cudaMalloc(&d_meta, sizeof(CbMeta) * ncb));
+    CU(cudaMalloc(&d_state, sizeof(CbState) * ncb));
+    CU(cudaMalloc(&d_ws, slot_b * ncb));
+    CU(cudaMalloc(&d_ab, ab_b * ncb));
+    CU(cudaMemset(d_ws, 0, slot_b * ncb));
+    CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
+    return 0;
+  }
+  void release() {
+    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ab);
+    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ab = nullptr; cap = 0;
+  }
+  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
+    h_meta = m;
+    n = (int)m.size();
+    max_iter = 0;
+    for (auto& x : m) if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter);
+    CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  int decode8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
+    int launches = 0;
+    Td8Args a;
+    a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ab = d_ab; a.ab_b = ab_b;
+    a.nblk = n; a.qpp = ctx->qpp_pool; a.crc_xp = ctx->crc_xp; a.in_base = in_dev; a.out_base = out_dev;
+    a.status_out = status_dev; a.iter = 0; a.sys_arr = a.par_arr = a.out_arr = 0;
+    const int map_grid = (n * 16 + MAP8_THREADS - 1) / MAP8_THREADS;
+    auto map = [&](int sys_arr, int par_arr, int out_arr, int iter) {
+      a.sys_arr = sys_arr; a.par_arr = par_arr; a.out_arr = out_arr; a.iter = iter;
+      k_map8<<<map_grid, MAP8_THREADS, 0, st>>>(a);
+      ++launches;
+    };
+    k_demux8<<<n, XCHG_THREADS, 3 * A, st>>>(a);
+    ++launches;
+    map(A8_S0, A8_P1, A8_EXT, 1);                                // TD8:1325
+    for (int it = 1; it <= max_iter; ++it) {                    // TD8:1327
+      a.iter = it;
+      k_x1_8<<<n, XCHG_THREADS, A, st>>>(a);
+      map(A8_SYS, A8_P2, A8_EXT2, it);                           // TD8:1386
+      k_x2_8<<<n, XCHG_THREADS, 2 * A, st>>>(a);
+      launches += 2;
+      if (it < max_iter) map(A8_SYS, A8_P1, A8_EXT, it + 1);     // TD8:1634
+    }
+    g_launches += launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-101, "kernel launch failed: %s", cudaGetErrorString(e));
+    return launches;
+  }
+};
+
+static bool td8_domain(int K) { return K >= 256 && (K & 15) == 0; }
+
+static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long in_off, long out_off, CbMeta* m,
+                     bool llr8 = false) {
   int idx = qpp_index(K);
   if (idx < 0) return -1;
   m->K = (uint16_t)K; m->W = (uint16_t)(K >> 3);
   m->max_iter = (uint8_t)max_it; m->crc_type = (uint8_t)crc; m->F = (uint8_t)F; m->flags = dec ? 1 : 0;
-  m->pi_off = c->pi_off[idx];
+  m->pi_off = llr8 ? c->qpp_off[idx] : c->pi_off[idx];
   m->t_off = c->t_off[idx];
   m->in_off_lo = (uint32_t)((unsigned long long)in_off & 0xffffffffu);
   m->in_off_hi = (uint32_t)((unsigned long long)in_off >> 32);
@@ -306,13 +382,15 @@ static thread_local Scratch t_scratch;
 // ---- host-buffer batches: pinned staging + one stream per batch object ---------------
 struct HostBatch {
   Batch b;
+  Batch8 b8;                       // 8-bit decoder blocks of the same submit (placed after the 16-bit ones)
+  int cap8_blocks = 0, cap8_K = 0, n16 = 0;
   cudaStream_t st = nullptr;
   int dev = -1;
   int cap_blocks = 0, cap_K = 0;
   size_t cap_in = 0, cap_out = 0;
   int16_t* h_in = nullptr;  int16_t* d_in = nullptr;
   uint8_t* h_out = nullptr; uint8_t* d_out = nullptr;
-  uint8_t* h_status = nullptr; uint8_t* d_status = nullptr;
+  uint8_t* h_status = nullptr; uint8_t* d_status = nullptr; int cap_status = 0;
   // fused front end (dematch + deinterleave): soft-bit pool, HARQ w pool, per-block parameters
   size_t cap_e = 0, cap_w = 0; int cap_rm = 0;
   int16_t* h_e = nullptr; int16_t* d_e = nullptr;
@@ -326,7 +404,7 @@ struct HostBatch {
   std::vector<uint32_t> out_off;
   unsigned flags = 0;
 
-  int ensure(int gpu, int nblk, int Kmax, size_t in_hw, size_t out_bytes) {
+  int ensure(int gpu, int nblk, int Kmax, size_t in_hw, size_t out_bytes, int nblk8 = 0, int Kmax8 = 0) {
     DevCtx* c;
     int rc = ctx_get(gpu, &c);
     if (rc) return rc;
@@ -338,11 +416,20 @@ struct HostBatch {
       cap_blocks = std::max(nblk, cap_blocks); cap_K = std::max(Kmax, cap_K);
       rc = b.alloc(c, cap_blocks, cap_K);
       if (rc) return rc;
-      if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); }
-      CU(cudaMallocHost(&h_status, cap_blocks));
-      CU(cudaMalloc(&d_status, cap_blocks));
     }
-    b.ctx = c;
+    if (nblk8 > cap8_blocks || (nblk8 > 0 && Kmax8 > cap8_K)) {
+      b8.release();
+      cap8_blocks = std::max(nblk8, cap8_blocks); cap8_K = std::max(Kmax8, cap8_K);
+      rc = b8.alloc(c, cap8_blocks, cap8_K);
+      if (rc) return rc;
+    }
+    if (nblk + nblk8 > cap_status) {
+      if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); }
+      cap_status = nblk + nblk8;
+      CU(cudaMallocHost(&h_status, cap_status));
+      CU(cudaMalloc(&d_status, cap_status));
+    }
+    b.ctx = c; b8.ctx = c;
     if (in_hw > cap_in) {
       if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); }
       cap_in = in_hw;
@@ -379,6 +466,7 @@ struct HostBatch {
   }
   void release() {
     b.release();
+    b8.release(); cap8_blocks = cap8_K = 0; cap_status = 0;
     if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); h_e = nullptr; d_e = nullptr; }
     if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); h_w = nullptr; d_w = nullptr; }
     if (d_rm) { cudaFree(d_rm); d_rm = nullptr; }
@@ -398,17 +486,27 @@ struct HostBatch {
     for (int i = 0; i < ncb; ++i) {
       const oai_cb_desc_t& d = descs[i];
       if (d.crc_type > 3 || qpp_index(d.K) < 0) { if (d.status) *d.status = 255; continue; }   // TD16:1003-1018
-      if (d.llr8) return fail(-3, "8-bit decoder not built yet");
+      if (d.llr8 && !td8_domain(d.K)) { if (d.status) *d.status = 255; continue; }    // outside TD8's parity domain
       // without the front end a block that is not decoded needs no GPU work at all; with it the
       // HARQ buffer is still combined (dlsch_decoding.c:333-385 runs before the err_flag test)
       if (!d.decode_enable && !d.dematch_enable) { if (d.status) *d.status = 0xFE; continue; }
       order.push_back(i);
       Kmax = std::max<int>(Kmax, d.K);
     }
-    // equal-K blocks next to each other: a warp of the MAP kernel carries 8 blocks
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return descs[a].K < descs[c].K; });
+    // 16-bit blocks first, then 8-bit ones; equal-K blocks next to each other (a warp of the MAP
+    // kernel carries 8 blocks)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+      if ((descs[a].llr8 != 0) != (descs[c].llr8 != 0)) return descs[a].llr8 == 0;
+      return descs[a].K < descs[c].K;
+    });
     const int n = (int)order.size();
     if (n == 0) return 0;
+    n16 = 0;
+    int Kmax8 = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!descs[order[i]].llr8) ++n16;
+      else Kmax8 = std::max<int>(Kmax8, descs[order[i]].K);
+    }
     size_t in_hw = 0, out_b = 0;
     std::vector<size_t> in_off(n);
     out_off.resize(n);
@@ -417,14 +515,15 @@ struct HostBatch {
       in_off[i] = in_hw;  in_hw += (size_t)3 * d.K + 12;
       out_off[i] = (uint32_t)out_b; out_b += ((size_t)(d.K >> 3) + 15) & ~(size_t)15;
     }
-    int rc = ensure(gpu, n, Kmax, in_hw, out_b);
+    int rc = ensure(gpu, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
     if (rc) return rc;
     std::vector<CbMeta> meta(n);
     rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
-      make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i]);
+      make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i],
+                d.llr8 != 0);
       if (d.dematch_enable) {
         RmParams q;
         if (rm_params(d.K, d.G, d.C, d.Nsoft, d.Mdlharq, d.Kmimo, d.rvidx, d.Qm, d.Nl, d.r, 0, &q))
@@ -475,11 +574,19 @@ struct HostBatch {
       CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
       i = j;
     }
-    rc = b.set_meta(meta, st);
-    if (rc) return rc;
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
-    rc = b.decode16(d_in, d_out, d_status, st);
-    if (rc < 0) return rc;
+    if (n16 > 0) {
+      rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
+      if (rc) return rc;
+      rc = b.decode16(d_in, d_out, d_status, st);
+      if (rc < 0) return rc;
+    }
+    if (n > n16) {
+      rc = b8.set_meta(std::vector<CbMeta>(meta.begin() + n16, meta.end()), st);
+      if (rc) return rc;
+      rc = b8.decode8(d_in, d_out, d_status + n16, st);
+      if (rc < 0) return rc;
+    }
     CU(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
     return 0;
@@ -525,6 +632,7 @@ using namespace oai;
 // ======================================================================================
 struct oai_turbo_dev_plan {
   Batch b;
+  Batch8 b8;
   int ncb; uint16_t K; uint8_t max_it, crc, llr8;
   long y_stride = -1, out_stride = -1;
 };
@@ -538,15 +646,15 @@ unsigned long long oai_turbo_b200_launch_count(void) { return g_launches.load();
 int oai_turbo_dev_plan_create(int ncb, uint16_t K, uint8_t max_iterations, uint8_t crc_type, uint8_t llr8,
                               oai_turbo_dev_plan_t** plan) {
   if (!plan || ncb <= 0) return fail(-1, "bad arguments");
-  if (llr8) return fail(-3, "8-bit decoder not built yet");
   if (qpp_index(K) < 0 || crc_type > 3) return fail(-1, "illegal K=%d or crc_type=%d", (int)K, (int)crc_type);
+  if (llr8 && !td8_domain(K)) return fail(-1, "K=%d is outside the 8-bit decoder's domain (K >= 256, K %% 16 == 0)", (int)K);
   DevCtx* c;
   int rc = ctx_get(-1, &c);
   if (rc) return rc;
   oai_turbo_dev_plan* p = new oai_turbo_dev_plan();
   p->ncb = ncb; p->K = K; p->max_it = max_iterations; p->crc = crc_type; p->llr8 = llr8;
-  rc = p->b.alloc(c, ncb, K);
-  if (rc) { p->b.release(); delete p; return rc; }
+  rc = llr8 ? p->b8.alloc(c, ncb, K) : p->b.alloc(c, ncb, K);
+  if (rc) { p->b.release(); p->b8.release(); delete p; return rc; }
   *plan = p;
   return 0;
 }
@@ -557,14 +665,15 @@ int oai_turbo_dev_decode(oai_turbo_dev_plan_t* p, const int16_t* y_dev, long y_s
   cudaStream_t st = (cudaStream_t)stream;
   if (p->y_stride != y_stride || p->out_stride != out_stride) {
     std::vector<CbMeta> m(p->ncb);
+    DevCtx* c = p->llr8 ? p->b8.ctx : p->b.ctx;
     for (int i = 0; i < p->ncb; ++i)
-      make_meta(p->b.ctx, p->K, p->max_it, p->crc, 0, 1, (long)i * y_stride, (long)i * out_stride, &m[i]);
-    int rc = p->b.set_meta(m, st);
+      make_meta(c, p->K, p->max_it, p->crc, 0, 1, (long)i * y_stride, (long)i * out_stride, &m[i], p->llr8 != 0);
+    int rc = p->llr8 ? p->b8.set_meta(m, st) : p->b.set_meta(m, st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));      // h_meta is pageable; done once per plan
     p->y_stride = y_stride; p->out_stride = out_stride;
   }
-  return p->b.decode16(y_dev, out_dev, status_dev, st);
+  return p->llr8 ? p->b8.decode8(y_dev, out_dev, status_dev, st) : p->b.decode16(y_dev, out_dev, status_dev, st);
 }
 
 
@@ -631,11 +740,33 @@ unsigned char phy_threegpplte_turbo_decoder16(short* y, unsigned char* decoded_b
   return status;
 }
 
-unsigned char phy_threegpplte_turbo_decoder8(short*, unsigned char*, unsigned short, unsigned short, unsigned short,
-    unsigned char, unsigned char, unsigned char, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*,
-    oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*) {
-  fail(-3, "phy_threegpplte_turbo_decoder8: 8-bit decoder not built yet");
-  return 255;
+static unsigned char decode_one(short* y, unsigned char* decoded_bytes, unsigned short n, unsigned char max_iterations,
+                                unsigned char crc_type, unsigned char F, int llr8, const char* who) {
+  if (!t_single) t_single = new HostBatch();
+  oai_cb_desc_t d;
+  memset(&d, 0, sizeof(d));
+  uint8_t status = 255;
+  d.in = y; d.decoded_bytes = decoded_bytes; d.status = &status; d.K = n; d.max_iterations = max_iterations;
+  d.crc_type = crc_type; d.F = F; d.decode_enable = 1; d.llr8 = (uint8_t)llr8;
+  if (t_single->submit(&d, 1, 0, -1) || t_single->wait()) {
+    fprintf(stderr, "[oai_turbo_b200] %s: GPU path failed (%s); there is no CPU fallback\n", who, g_err);
+    return 255;
+  }
+  return status;
+}
+
+unsigned char phy_threegpplte_turbo_decoder8(short* y, unsigned char* decoded_bytes, unsigned short n, unsigned short f1,
+    unsigned short f2, unsigned char max_iterations, unsigned char crc_type, unsigned char F, oai_time_stats_t*,
+    oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*, oai_time_stats_t*) {
+  (void)f1; (void)f2;
+  if (crc_type > 3) { fprintf(stderr, "Illegal crc length!\n"); return 255; }          // TD8:954-957
+  if (qpp_index(n) < 0) { fprintf(stderr, "Illegal frame length!\n"); return 255; }    // TD8:969-972
+  if (!td8_domain(n)) {
+    fprintf(stderr, "[oai_turbo_b200] phy_threegpplte_turbo_decoder8: n=%d is outside the supported domain "
+                    "(n >= 256, n %% 16 == 0; the reference overruns its buffers there)\n", (int)n);
+    return 255;
+  }
+  return decode_one(y, decoded_bytes, n, max_iterations, crc_type, F, 1, "phy_threegpplte_turbo_decoder8");
 }
 
 uint32_t generate_dummy_w(uint32_t D, uint8_t* w, uint8_t F) {
@@ -770,6 +901,7 @@ int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4,
 void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t* p) {
   if (!p) return;
   p->b.release();
+  p->b8.release();
   delete p;
 }
 

@@ -183,6 +183,57 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
 }
 
 // ------------------------------------------------------------------------------------
+// CRC early-termination test of one block (all threads of the CTA call it after the decoded
+// bytes are in shared memory and a barrier; the result is valid in thread 0).  Also copies the
+// bytes to the output.  The reference walks `bits` bits starting at byte f0 (CRC24A skips the F
+// filler bits, TD16:1312-1313) and compares with the trailing crc bytes of the block.  A CRC
+// (zero start value, no final xor) is linear over GF(2): the remainder of the message is the
+// XOR of the remainders of its bytes, each shifted by its distance from the message end.
+__device__ __forceinline__ bool block_crc_check(const uint8_t* sbytes, uint8_t* outp, const CbMeta& m,
+                                                const u32* crc_tab, u32* xred) {
+  const int K = m.K, nb = K >> 3;
+  const int ct = m.crc_type;
+  const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
+  const int j_lo = (ct == 0) ? ((m.F >> 3) << 3) : 0;
+  const int j_hi = j_lo + K - w - ((ct == 0) ? m.F : 0);       // message = bits [j_lo, j_hi)
+  const int f0 = j_lo >> 3, full = (j_hi - j_lo) >> 3, resbit = (j_hi - j_lo) & 7;
+  const u32* RB = crc_tab + ct * (768 * 32);
+  // CRC of the `full` whole bytes: XOR of per-byte remainders (two nibble look-ups each)
+  u32 acc = 0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const u32 v = sbytes[b];
+    outp[b] = (uint8_t)v;
+    const int mdist = f0 + full - 1 - b;                       // bytes between this one and the message end
+    if (b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) xred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  bool pass = false;
+  if (threadIdx.x == 0) {
+    const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
+    const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
+    u32 crc = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) crc ^= xred[i];
+    for (int jb = 0; jb < resbit; ++jb) {                      // residual bits, crc_byte.c:130-131
+      const u32 bit = (sbytes[f0 + full] >> (7 - jb)) & 1u;
+      const u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
+      crc = (crc << 1) & mask;
+      if (top) crc ^= poly;
+    }
+    // received CRC as the reference assembles it: big-endian for the 24-bit CRCs (after its
+    // byte swap, TD16:1314-1326), a little-endian 16-bit load for CRC16 (:1329-1333)
+    u32 rx;
+    if (w == 24) rx = ((u32)sbytes[nb - 3] << 16) | ((u32)sbytes[nb - 2] << 8) | sbytes[nb - 1];
+    else if (w == 16) rx = ((u32)sbytes[nb - 1] << 8) | sbytes[nb - 2];
+    else rx = sbytes[nb - 1];
+    pass = (crc == rx && crc != 0);                            // TD16:1348
+  }
+  return pass;
+}
+
+// ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
@@ -247,19 +298,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
 
   bool pass = false;
   if (p.iter > 1) {                                            // :1267-1351
-    const int nb = K >> 3;
     uint8_t* outp = p.out_base + m.out_off;
     const uint16_t* H = p.pi_pool + m.pi_off;
-    // CRC parameters.  The reference walks `bits` bits starting at byte f0 (CRC24A skips the F
-    // filler bits, :1312-1313) and compares with the trailing crc bytes of the block.  A CRC
-    // (zero start value, no final xor) is linear over GF(2): the remainder of the message is the
-    // XOR of the remainders of its bytes, each shifted by its distance from the message end.
-    const int ct = m.crc_type;
-    const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
-    const int j_lo = (ct == 0) ? ((m.F >> 3) << 3) : 0;
-    const int j_hi = j_lo + K - w - ((ct == 0) ? m.F : 0);     // message = bits [j_lo, j_hi)
-    const int f0 = j_lo >> 3, full = (j_hi - j_lo) >> 3, resbit = (j_hi - j_lo) & 7;
-    const u32* RB = p.crc_xp + ct * (768 * 32);
     // bit = ext2 > 0 at natural position j, MSB first: one ballot per 32 positions
     for (int j0 = (threadIdx.x & ~31); j0 < K; j0 += XCHG_THREADS) {
       const int j = j0 + (threadIdx.x & 31);
@@ -269,37 +309,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
         *reinterpret_cast<u32*>(&sbytes[j0 >> 3]) = __byte_perm(__brev(mask), 0, 0x0123);
     }
     __syncthreads();
-    // CRC of the `full` whole bytes: XOR of per-byte remainders (two nibble look-ups each)
-    u32 acc = 0;
-    for (int b = threadIdx.x; b < nb; b += XCHG_THREADS) {
-      const u32 v = sbytes[b];
-      outp[b] = (uint8_t)v;
-      const int mdist = f0 + full - 1 - b;                     // bytes between this one and the message end
-      if (b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) xred[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
-      const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
-      u32 crc = 0;
-      for (int i = 0; i < XCHG_THREADS / 32; ++i) crc ^= xred[i];
-      for (int jb = 0; jb < resbit; ++jb) {                    // residual bits, crc_byte.c:130-131
-        const u32 bit = (sbytes[f0 + full] >> (7 - jb)) & 1u;
-        const u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
-        crc = (crc << 1) & mask;
-        if (top) crc ^= poly;
-      }
-      // received CRC as the reference assembles it: big-endian for the 24-bit CRCs (after its
-      // byte swap, :1314-1326), a little-endian 16-bit load for CRC16 (:1329-1333)
-      u32 rx;
-      if (w == 24) rx = ((u32)sbytes[nb - 3] << 16) | ((u32)sbytes[nb - 2] << 8) | sbytes[nb - 1];
-      else if (w == 16) rx = ((u32)sbytes[nb - 1] << 8) | sbytes[nb - 2];
-      else rx = sbytes[nb - 1];
-      pass = (crc == rx && crc != 0);                          // :1348
-    }
+    pass = block_crc_check(sbytes, outp, m, p.crc_xp, xred);
   } else {
     __syncthreads();
   }

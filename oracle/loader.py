@@ -184,3 +184,12 @@ def ref_decode_batch(y_blocks, n, max_it, crc_type, total=None, threads=1, which
                    max(total or nd, nd), n, max_it, crc_type, which, threads)
     dt = time.perf_counter() - t0
     return out[:, :n // 8].copy(), ret, dt
+
+
+def port_decode8(y, n, max_it, crc_type, F=0):
+    L = port()
+    yy = np.zeros(3 * n + 12 + 64, dtype=np.int16)
+    yy[:3 * n + 12] = y[:3 * n + 12]
+    out = np.zeros(n // 8 + 4, dtype=np.uint8)
+    r = L.orc_turbo_decoder8(yy, out, n, max_it, crc_type, F)
+    return out[:n // 8].copy(), int(r)

@@ -49,6 +49,22 @@ def main():
     print("td16:", len(meta), "blocks; ret histogram",
           {int(k): int(v) for k, v in zip(*np.unique(np.array(meta)[:, 4], return_counts=True))})
 
+    # 8-bit decoder (parity domain K >= 256, K % 16 == 0); amplitudes cover every input-scaling bracket
+    ys, outs, meta = [], [], []
+    blk = 2000
+    for K in (256, 512, 1024, 2048, 5824, 6144):
+        for regime, A in (("clean", 8), ("waterfall", 8), ("noise", 8), ("full", 8), ("waterfall", 40),
+                          ("waterfall", 100), ("clean", 300), ("waterfall", 2000)):
+            crc = blk & 1
+            y, _ = vectors.llr_block(K, blk, regime, A=A, crc_type=crc)
+            b, r = loader.ref_decode16(y, K, 6, crc, 0, which=8)
+            ys.append(y); outs.append(b); meta.append((K, 6, crc, 0, r))
+            blk += 1
+    np.savez_compressed(os.path.join(HERE, "td8_golden.npz"), y=np.concatenate(ys), out=np.concatenate(outs),
+                        meta=np.array(meta, dtype=np.int32))
+    print("td8:", len(meta), "blocks; ret histogram",
+          {int(k): int(v) for k, v in zip(*np.unique(np.array(meta)[:, 4], return_counts=True))})
+
     # rate dematching + sub-block deinterleaving chain (dlsim / ulsim shapes + HARQ rounds)
     rng = np.random.default_rng(0xD15)
     rm = {}

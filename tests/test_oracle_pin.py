@@ -211,3 +211,25 @@ def test_log_map16_internals_match_reference(port, ref):
                 assert np.array_equal(e1[:n], e2[:n])
                 assert np.array_equal(a1[:64 * (W + 1)], a2[:64 * (W + 1)])
                 assert np.array_equal(b1[:64 * (W + 1)], b2[:64 * (W + 1)])
+
+
+def test_td8_all_sizes_of_its_domain(ref):
+    """8-bit decoder: every K >= 256 with K % 16 == 0 (145 sizes), all input-scaling brackets
+    (amplitudes 8..2000 and full-range int16), both hard-decision rules (K % 128 == 0 or not)."""
+    hist = {}
+    n = 0
+    for i, K in enumerate(k for k in ALL_K if k >= 256 and k % 16 == 0):
+        for regime, A in (("clean", 8), ("waterfall", 8), ("noise", 8), ("full", 8), ("waterfall", 40),
+                          ("waterfall", 100), ("clean", 300), ("waterfall", 2000)):
+            y, info = vectors.llr_block(K, 3000 + i, regime, A=A, crc_type=i & 1)
+            b1, r1 = loader.ref_decode16(y, K, 6, i & 1, which=8)
+            b2, r2 = loader.port_decode8(y, K, 6, i & 1)
+            assert r1 == r2 and np.array_equal(b1, b2), (K, regime, A)
+            hist[r1] = hist.get(r1, 0) + 1
+            n += 1
+    assert n == 145 * 8 and set(hist) >= {2, 3, 4, 7}
+    for max_it, crc in ((1, 1), (2, 0), (3, 2), (4, 3)):
+        y, _ = vectors.llr_block(512, 9, "clean", crc_type=min(crc, 1))
+        assert loader.ref_decode16(y, 512, max_it, crc, which=8)[1] == loader.port_decode8(y, 512, max_it, crc)[1]
+    y = np.zeros(3 * 40 + 12 + 64, dtype=np.int16)
+    assert loader.port_decode8(y, 40, 4, 1)[1] == 254            # outside the parity domain (reference overruns)
