@@ -185,6 +185,7 @@ struct Batch {
   CbState* d_state = nullptr;
   int16_t* d_ws = nullptr;
   u32* d_ckpt = nullptr;
+  int* d_batch_max = nullptr;
   std::vector<CbMeta> h_meta;
 
   int alloc(DevCtx* c, int ncb, int Kmax) {
@@ -198,13 +199,14 @@ struct Batch {
     CU(cudaMalloc(&d_state, sizeof(CbState) * ncb));
     CU(cudaMalloc(&d_ws, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
+    CU(cudaMalloc(&d_batch_max, sizeof(int)));
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     return 0;
   }
   void release() {
-    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt);
-    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr;
+    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt); cudaFree(d_batch_max);
+    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr; d_batch_max = nullptr;
   }
   int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
     h_meta = m;
@@ -220,10 +222,11 @@ struct Batch {
     XchgArgs x;
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
-    x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B;
+    x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
+    cudaMemsetAsync(d_batch_max, 0, sizeof(int), st);
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
-    mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B;
+    mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
     const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
     const size_t map_smem = MAP_SMEM_BYTES;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
@@ -861,11 +864,12 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   XchgArgs x;
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
   x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
-  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B;
+  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max;
+  cudaMemsetAsync(b.d_batch_max, 0, sizeof(int), hb.st);
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
   MapArgs mp;
   mp.meta = b.d_meta; mp.state = b.d_state; mp.ws = b.d_ws; mp.slot_hw = b.slot_hw; mp.A = b.A;
-  mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1;
+  mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1; mp.batch_max = (policy == 3) ? b.d_batch_max : nullptr;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
   mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1; mp.upd = 0;
   k_map16<CKPT_S><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
@@ -873,6 +877,16 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   std::vector<int16_t> tmp(b.A);
   CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));
   CU(cudaStreamSynchronize(hb.st));
+  if (getenv("OAI_TURBO_DEBUG_B8")) {
+    std::vector<int16_t> p1(b.A), b8(b.A);
+    cudaMemcpy(p1.data(), b.d_ws + (long)ARR_P1 * b.A, b.A * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(b8.data(), b.d_ws + (long)ARR_B8A * b.A, b.A * 2, cudaMemcpyDeviceToHost);
+    const int8_t* q = (const int8_t*)b8.data();
+    int bad = 0, bm = -1;
+    cudaMemcpy(&bm, b.d_batch_max, 4, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < b.A; ++i) if ((int)q[i] != (int)p1[i]) { if (bad < 5) fprintf(stderr, "b8 mismatch at %d: %d vs %d\n", i, q[i], p1[i]); ++bad; }
+    fprintf(stderr, "B8A check: A=%d bad=%d batch_max=%d\n", b.A, bad, bm);
+  }
   if (getenv("OAI_TURBO_DEBUG_T")) {
     CbState stt;
     cudaMemcpy(&stt, b.d_state, sizeof(stt), cudaMemcpyDeviceToHost);

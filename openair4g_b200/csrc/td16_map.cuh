@@ -31,7 +31,10 @@
 namespace oai {
 
 constexpr int MAP_THREADS = 64;      // 16 code blocks per CTA
-constexpr int MAP_SEG = 16;          // checkpoint distance S (steps)
+#ifndef MAP_SEG_STEPS
+#define MAP_SEG_STEPS 16
+#endif
+constexpr int MAP_SEG = MAP_SEG_STEPS;   // checkpoint distance S (steps): 16 or 8
 // dynamic shared memory per CTA: per segment step and thread 32 B of alpha, 8 B of branch constants
 // and 4 B for the feedback term s0 - sys
 constexpr int MAP_SMEM_BYTES = MAP_SEG * MAP_THREADS * 44;
@@ -51,6 +54,7 @@ struct MapArgs {
   int term;              // 0: first constituent decoder, 1: second
   int iter;              // blocks with max_iter < iter are finished (skipped)
   int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
+  const int* batch_max;  // max |y| over the batch: <= 127 selects the int8 parity / s0 copies
   int upd;               // 1: write ext = (ext (-) sys) (+) s0 (the feedback step, reference :1354-1375)
 };
 
@@ -271,6 +275,39 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
 // =====================================================================================
 struct FC { u32 X, Y, Z; };
 
+#ifndef MAP_CACHE_HINTS
+#define MAP_CACHE_HINTS 0
+#endif
+// L2 policy hints: the forward sweep's LAST reads are the backward sweep's FIRST reads, so the
+// tail of the forward stream is kept (evict_last) and everything that is not reused soon streams
+// through (evict_first): the backward sweep's reads and the ext output.
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_hint(const uint4* p, unsigned long long pol) {
+#if MAP_CACHE_HINTS
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void stg_hint(uint4* p, const uint4& v, unsigned long long pol) {
+#if MAP_CACHE_HINTS
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol));
+#else
+  *p = v;
+#endif
+}
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ u32 vaddmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
@@ -356,6 +393,13 @@ struct FastSmem {
   }
 };
 
+// prmt with the sign-replication selector bit (__byte_perm only honours 3 bits per nibble)
+__device__ __forceinline__ u32 prmt_sx(u32 a, u32 sel) {
+  u32 d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+
 __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
 
 // Fast MAP pass.  PM = P-1 with P the renormalisation period (1, 4 or 16 steps; compile time so
@@ -367,11 +411,13 @@ __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.
 //             constants), then beta / ext from the segment end to its start.
 // The register that held chunk j is refilled with chunk j of the NEXT segment as soon as it has
 // been consumed, so global loads run a whole segment ahead of their use.
-template <int S, int PM, bool UPD>
+// P8: parity (and s0) are read from the int8 copies: chunk c of this thread = 8 bytes at par8[c*4]
+template <int S, int PM, bool UPD, bool P8>
 __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0,
                               u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv,
                               unsigned char* smem, int tid) {
-  static_assert(S == 16, "segment = 4 chunks of 4 steps");
+  static_assert(S == 16 || S == 8, "segment = NCH chunks of 4 steps");
+  constexpr int NCH = S / 4;
 #ifndef MAP_PF_SEGS
 #define MAP_PF_SEGS 3
 #endif
@@ -384,43 +430,67 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
   const uint4* par4 = reinterpret_cast<const uint4*>(par);
   const uint4* s04 = reinterpret_cast<const uint4*>(s0);
+  const uint2* par8 = reinterpret_cast<const uint2*>(par);     // P8: `par`/`s0` point at the int8 copies
+  const uint2* s08 = reinterpret_cast<const uint2*>(s0);
+  // chunk loaders: in P8 mode only .x/.y of the uint4 are used (8 bytes = 4 steps x 2 lanes)
+  auto ldp = [&](int c) -> uint4 { if (P8) { uint2 v = __ldg(par8 + c * 4); return make_uint4(v.x, v.y, 0, 0); } return __ldg(par4 + c * 4); };
+  auto ldz = [&](int c) -> uint4 { if (P8) { uint2 v = __ldg(s08 + c * 4); return make_uint4(v.x, v.y, 0, 0); } return __ldg(s04 + c * 4); };
+  // value of step q inside a chunk register (sign-extending the two int8 to a packed int16 pair)
+  auto pk = [&](const uint4& v, int q) -> u32 {
+    if (P8) return prmt_sx(q < 2 ? v.x : v.y, (q & 1) ? 0xB3A2u : 0x9180u);
+    return pick4(v, q);
+  };
+  // single-step loaders for the short boundary loops
+  auto ldp1 = [&](int k) -> u32 {
+    if (P8) { u32 w = reinterpret_cast<const uint16_t*>(par)[c4_word(k, 0)]; return prmt_sx(w, 0x9180u); }
+    return __ldg(par + c4_word(k, 0));
+  };
+  auto ldz1 = [&](int k) -> u32 {
+    if (P8) { u32 w = reinterpret_cast<const uint16_t*>(s0)[c4_word(k, 0)]; return prmt_sx(w, 0x9180u); }
+    return __ldg(s0 + c4_word(k, 0));
+  };
   u32 a[8];
-  uint4 sb[4], pb[4], zb[4];
+  uint4 sb[NCH], pb[NCH], zb[NCH];
 
   // ---- forward sweep ------------------------------------------------------------------
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = pack2(NEG_INIT, NEG_INIT);
   if (t == 0) a[0] = pack2(0, NEG_INIT);
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = __ldg(par4 + j * 4); }
+  for (int j = 0; j < NCH; ++j)
+    if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = ldp(j); }
   const int nfull = W / S;                                     // segments with all 16 steps
+  const int keep_from = nchunk - (nchunk * 2) / 5;             // forward reads of the last 40% stay in L2
+  const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
 #if MAP_FWD_DIST2
-  uint4 sc[4], pc[4];                                          // segment seg+1 (registers are free in this phase)
+  uint4 sc[NCH], pc[NCH];                                          // segment seg+1 (registers are free in this phase)
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (4 + j < nchunk) { sc[j] = __ldg(sys4 + (4 + j) * 4); pc[j] = __ldg(par4 + (4 + j) * 4); }
+  for (int j = 0; j < NCH; ++j)
+    if (NCH + j < nchunk) { sc[j] = __ldg(sys4 + (NCH + j) * 4); pc[j] = ldp(NCH + j); }
 #endif
   for (int seg = 0; seg < nfull; ++seg) {
     if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
-      const int cp = (seg + PF) * 4 + t;
-      if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t); }
+      const int cp = (seg + PF) * NCH + (t % NCH);
+      if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t); }
     }
     ckpt_put(ck + seg * 32, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NCH; ++j) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
-        alpha_fast(a, fconst(pick4(sb[j], q), pick4(pb[j], q)));
+        alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
 #if MAP_FWD_DIST2
       sb[j] = sc[j]; pb[j] = pc[j];
-      const int cn = (seg + 2) * 4 + j;
-      if (cn < nchunk) { sc[j] = __ldg(sys4 + cn * 4); pc[j] = __ldg(par4 + cn * 4); }
+      const int cn = (seg + 2) * NCH + j;
+      if (cn < nchunk) { sc[j] = __ldg(sys4 + cn * 4); pc[j] = ldp(cn); }
 #else
-      const int cn = (seg + 1) * 4 + j;
-      if (cn < nchunk) { sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4); }
+      const int cn = (seg + 1) * NCH + j;
+      if (cn < nchunk) {
+        if (cn >= keep_from) { sb[j] = ldg_hint(sys4 + cn * 4, pol_keep); pb[j] = ldp(cn); }
+        else { sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn); }
+      }
 #endif
     }
     renorm(a);                                                 // checkpoints are stored normalised
@@ -428,13 +498,13 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   if (nfull < nseg) {                                          // partial last segment
     ckpt_put(ck + nfull * 32, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NCH; ++j) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int e = j * 4 + q;
         if (nfull * S + e < W) {
           if ((e & PM) == 0 && e != 0) renorm(a);
-          alpha_fast(a, fconst(pick4(sb[j], q), pick4(pb[j], q)));
+          alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
         }
       }
     }
@@ -454,7 +524,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     for (int s = 0; s < 8; ++s) a[s] = seed[s];
     for (int k = 0; k < W; ++k) {
       if ((k & PM) == 0) renorm(a);
-      alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+      alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), ldp1(k)));
     }
   }
 
@@ -468,11 +538,11 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 
   // ---- backward sweep, pass 1 -----------------------------------------------------------
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = (nseg - 1) * 4 + j;
+  for (int j = 0; j < NCH; ++j) {
+    const int c = (nseg - 1) * NCH + j;
     if (c < nchunk) {
-      sb[j] = __ldg(sys4 + c * 4); pb[j] = __ldg(par4 + c * 4);
-      if (UPD) zb[j] = __ldg(s04 + c * 4);
+      sb[j] = __ldg(sys4 + c * 4); pb[j] = ldp(c);
+      if (UPD) zb[j] = ldz(c);
     }
   }
   ckpt_get(ck + (nseg - 1) * 32, a);
@@ -480,52 +550,53 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     const int k0 = seg * S, k1 = min(W, k0 + S);
     const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
     if (PF > 0 && seg >= PF) {                    // warm L2 for segment seg-PF (inputs + checkpoint)
-      const int cp = (seg - PF) * 4 + t;
-      l2_prefetch(sys4 + cp * 4 - t); l2_prefetch(par4 + cp * 4 - t);
-      if (UPD) l2_prefetch(s04 + cp * 4 - t);
+      const int cp = (seg - PF) * NCH + (t % NCH);
+      l2_prefetch(sys4 + cp * 4 - t);
+      if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t);
+      if (UPD) { if (P8) l2_prefetch(s08 + cp * 4 - t); else l2_prefetch(s04 + cp * 4 - t); }
       if (t == 0) l2_prefetch(ck + (seg - PF) * 32);
     }
     // a holds the checkpoint of this segment (fetched during the previous segment's beta phase)
     if (steady) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NCH; ++j) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = j * 4 + q;
           if ((e & PM) == 0 && e != 0) renorm(a);
           const u32 sv = pick4(sb[j], q);
-          const FC c = fconst(sv, pick4(pb[j], q));
+          const FC c = fconst(sv, pk(pb[j], q));
           sm.put(e, tid, a);
           sm.putc(e, tid, c);
-          if (UPD) sm.putd(e, tid, __vsub2(pick4(zb[j], q), sv));
+          if (UPD) sm.putd(e, tid, __vsub2(pk(zb[j], q), sv));
           if (e != S - 1) alpha_fast(a, c);
         }
         if (seg > 0) {
-          const int cn = (seg - 1) * 4 + j;
-          sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4);
-          if (UPD) zb[j] = __ldg(s04 + cn * 4);
+          const int cn = (seg - 1) * NCH + j;
+          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
+          if (UPD) zb[j] = ldz(cn);
         }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NCH; ++j) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = j * 4 + q;
           if (k0 + e < k1) {
             if ((e & PM) == 0 && e != 0) renorm(a);
             const u32 sv = pick4(sb[j], q);
-            const FC c = fconst(sv, pick4(pb[j], q));
+            const FC c = fconst(sv, pk(pb[j], q));
             sm.put(e, tid, a);
             sm.putc(e, tid, c);
-            if (UPD) sm.putd(e, tid, __vsub2(pick4(zb[j], q), sv));
+            if (UPD) sm.putd(e, tid, __vsub2(pk(zb[j], q), sv));
             alpha_fast(a, c);
           }
         }
         if (seg > 0) {
-          const int cn = (seg - 1) * 4 + j;
-          sb[j] = __ldg(sys4 + cn * 4); pb[j] = __ldg(par4 + cn * 4);
-          if (UPD) zb[j] = __ldg(s04 + cn * 4);
+          const int cn = (seg - 1) * NCH + j;
+          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
+          if (UPD) zb[j] = ldz(cn);
         }
       }
     }
@@ -545,20 +616,32 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       ckb = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[1];
     }
     if (steady) {
+      // software pipeline: the shared-memory loads of step e-1 are issued before the arithmetic of step e
+      u32 an[8];
+      FC cn = sm.getc(S - 1, tid);
+      u32 dn = UPD ? sm.getd(S - 1, tid) : 0u;
+      sm.get(S - 1, tid, an);
 #pragma unroll
-      for (int j = 3; j >= 0; --j) {
+      for (int j = NCH - 1; j >= 0; --j) {
         u32 e4[4];
 #pragma unroll
         for (int q = 3; q >= 0; --q) {
           const int e = j * 4 + q;
-          const FC c = sm.getc(e, tid);
-          sm.get(e, tid, a);
+          const FC c = cn;
+          const u32 dcur = dn;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) a[s] = an[s];
+          if (e > 0) {
+            cn = sm.getc(e - 1, tid);
+            if (UPD) dn = sm.getd(e - 1, tid);
+            sm.get(e - 1, tid, an);
+          }
           e4[q] = ext_fast(a, b, c);
-          if (UPD) e4[q] = __vadd2(e4[q], sm.getd(e, tid));
+          if (UPD) e4[q] = __vadd2(e4[q], dcur);
           beta_fast(b, c);
           if ((e & PM) == 0) renorm(b);
         }
-        *reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+        stg_hint(reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16), make_uint4(e4[0], e4[1], e4[2], e4[3]), pol_stream);
       }
     } else {
       for (int k = k1 - 1; k >= k0; --k) {
@@ -590,10 +673,10 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     for (int k = sa * S; k < W; ++k) {
       if ((k & PM) == 0 && k != sa * S) renorm(a);
       const u32 sv = __ldg(sys + c4_word(k, 0));
-      const FC c = fconst(sv, __ldg(par + c4_word(k, 0)));
+      const FC c = fconst(sv, ldp1(k));
       if (k >= kk0) {
         sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c);
-        if (UPD) sm.putd(k - kk0, tid, __vsub2(__ldg(s0 + c4_word(k, 0)), sv));
+        if (UPD) sm.putd(k - kk0, tid, __vsub2(ldz1(k), sv));
       }
       if (k + 1 < W) alpha_fast(a, c);
     }
@@ -603,7 +686,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       for (int k = 0; k <= RERUN_STEPS && k < W; ++k) {
         if ((k & PM) == 0) renorm(a);
         if (k >= kk0) sm.put(k - kk0, tid, a);
-        if (k < RERUN_STEPS) alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+        if (k < RERUN_STEPS) alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), ldp1(k)));
       }
     }
     for (int k = W - 1; k >= kk0; --k) {
@@ -662,17 +745,29 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
 
   unsigned char* smem = reinterpret_cast<unsigned char*>(abuf);
   const u32* s0 = reinterpret_cast<const u32*>(slot + (long)ARR_S0 * p.A) + t * 4;
-  if (p.upd) {
-    if (P >= 16)     map_pass_fast<S, 15, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else if (P >= 4) map_pass_fast<S, 3, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else if (P >= 1) map_pass_fast<S, 0, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else             map_pass<SatArith, S>(sys, par, s0, true, ext, ck, W, t, gmask, Tv, abuf, tid);
-  } else {
-    if (P >= 16)     map_pass_fast<S, 15, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else if (P >= 4) map_pass_fast<S, 3, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else if (P >= 1) map_pass_fast<S, 0, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);
-    else             map_pass<SatArith, S>(sys, par, s0, false, ext, ck, W, t, gmask, Tv, abuf, tid);
+  if (P == 0) {                                 // exact saturating policy, int16 arrays
+    map_pass<SatArith, S>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
+    return;
   }
+  // int8 copies of parity / s0 when the whole batch has |y| <= 127 (warp-uniform: one flag per batch)
+  const bool p8 = p.batch_max && (*p.batch_max <= 127);
+  if (p8) {
+    const int8_t* b8a = reinterpret_cast<const int8_t*>(slot + (long)ARR_B8A * p.A);
+    const int8_t* b8b = reinterpret_cast<const int8_t*>(slot + (long)ARR_B8B * p.A);
+    par = reinterpret_cast<const u32*>(b8a + (p.par_arr == ARR_P2 ? p.A : 0) + t * 8);
+    s0 = reinterpret_cast<const u32*>(b8b + t * 8);
+  }
+#define MAP_DISPATCH(PMV)                                                                                   \
+  do {                                                                                                      \
+    if (p.upd) { if (p8) map_pass_fast<S, PMV, true, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);   \
+                 else    map_pass_fast<S, PMV, true, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid); } \
+    else       { if (p8) map_pass_fast<S, PMV, false, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid);  \
+                 else    map_pass_fast<S, PMV, false, false>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid); } \
+  } while (0)
+  if (P >= 16)     MAP_DISPATCH(15);
+  else if (P >= 4) MAP_DISPATCH(3);
+  else             MAP_DISPATCH(0);
+#undef MAP_DISPATCH
 }
 
 }  // namespace oai

@@ -33,6 +33,7 @@ struct XchgArgs {
   uint8_t* status_out;          // batch status bytes (device), written when a block finishes
   int iter;                     // iteration_cnt of the reference loop (1..max)
   int guard_b;                  // MAP fast-path guard (same value as MapArgs::guard_b)
+  int* batch_max;               // max |y| over the whole batch (atomicMax by k_demux16)
 };
 
 __device__ __forceinline__ int blk_max_reduce(int v, int* red) {
@@ -103,8 +104,16 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
     reinterpret_cast<uint4*>(slot + (long)ARR_S0 * A)[i] = reinterpret_cast<uint4*>(s0)[i];
     reinterpret_cast<uint4*>(slot + (long)ARR_P1 * A)[i] = reinterpret_cast<uint4*>(p1)[i];
     reinterpret_cast<uint4*>(slot + (long)ARR_P2 * A)[i] = reinterpret_cast<uint4*>(p2)[i];
+    // int8 copies (low bytes; meaningful only when |y| <= 127, which the batch flag certifies)
+    const uint4 a = reinterpret_cast<uint4*>(p1)[i], b = reinterpret_cast<uint4*>(p2)[i], c = reinterpret_cast<uint4*>(s0)[i];
+    int8_t* b8a = reinterpret_cast<int8_t*>(slot + (long)ARR_B8A * A);
+    int8_t* b8b = reinterpret_cast<int8_t*>(slot + (long)ARR_B8B * A);
+    reinterpret_cast<uint2*>(b8a)[i] = make_uint2(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420));
+    reinterpret_cast<uint2*>(b8a + A)[i] = make_uint2(__byte_perm(b.x, b.y, 0x6420), __byte_perm(b.z, b.w, 0x6420));
+    reinterpret_cast<uint2*>(b8b)[i] = make_uint2(__byte_perm(c.x, c.y, 0x6420), __byte_perm(c.z, c.w, 0x6420));
   }
   mx = blk_max_reduce(mx, red);
+  if (threadIdx.x == 0 && p.batch_max) atomicMax(p.batch_max, mx);
   if (threadIdx.x < 2) {
     // tail-bit beta start metrics in WRAPPING int16 (reference :474-520); the gamma of
     // the tail uses the saturating add/sub + >>1 of compute_gamma16 (:160-161)

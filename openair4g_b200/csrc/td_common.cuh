@@ -42,7 +42,9 @@ struct CbState {
 };
 
 // workspace arrays of one block slot, each `A` halfwords long
-enum { ARR_S0 = 0, ARR_P1 = 1, ARR_P2 = 2, ARR_SYS = 3, ARR_EXT = 4, ARR_EXT2 = 5, ARR_COUNT = 6 };
+// ARR_B8A / ARR_B8B hold int8 copies (A bytes each, same C4 index in bytes): [P1 | P2] and [S0 | unused];
+// the MAP kernel reads them instead of the int16 arrays when every |y| of the batch is <= 127.
+enum { ARR_S0 = 0, ARR_P1 = 1, ARR_P2 = 2, ARR_SYS = 3, ARR_EXT = 4, ARR_EXT2 = 5, ARR_B8A = 6, ARR_B8B = 7, ARR_COUNT = 8 };
 
 __host__ __device__ inline int c4_words(int W) { return ((W + 3) >> 2) << 4; }      // uint32 words per array
 __host__ __device__ inline int c4_word(int k, int t) { return ((k >> 2) << 4) + (t << 2) + (k & 3); }
