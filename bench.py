@@ -246,6 +246,8 @@ def run_b200(args):
     Be = args.e2e_blocks
     y_pin = torch.empty((Be, row), dtype=torch.int16).pin_memory()
     y_pin.copy_(y_dev[:Be].cpu())
+    # one submit + wait per step.  (Keeping two batches in flight was measured and is NOT used: on this
+    # box kernels run ~2.5x slower while a host->device copy of another batch is in flight, see DESIGN.md.)
     call = capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE)
     for _ in range(2):
         call.run()
@@ -321,7 +323,7 @@ def run_b200(args):
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
-                    "api": "oai_turbo_submit_batch + oai_turbo_wait, pinned host input, host output"},
+                    "api": "oai_turbo_submit_batch + oai_turbo_wait per step, pinned host input, host output"},
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -365,8 +367,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=23680,
                     help="code blocks per GPU per step (device-resident); 23680 = 2 full waves of the MAP kernel "
                          "(148 SMs x 5 resident CTAs x 16 blocks)")
-    ap.add_argument("--e2e-blocks", type=int, default=4096, help="code blocks per GPU per step (host-buffer API)")
-    ap.add_argument("--cpu-blocks", type=int, default=8192, help="bounded CPU-baseline sample (blocks)")
+    ap.add_argument("--e2e-blocks", type=int, default=23680, help="code blocks per GPU per step (host-buffer API)")
+    ap.add_argument("--cpu-blocks", type=int, default=32768, help="bounded CPU-baseline sample (blocks), ~12-25 s of CPU work")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
     ap.add_argument("--K", type=int, default=K_BITS, help="block size for --llr8 / side measurements")

@@ -204,15 +204,23 @@ class HostBatchCall:
         self.h2d_bytes = n * row
         self.d2h_bytes = n * (K // 8 + 1)
 
-    def run(self):
+    def submit(self):
+        """oai_turbo_submit_batch: returns the in-flight handle (copies + kernels are enqueued)."""
         h = C.c_void_p()
         rc = lib.oai_turbo_submit_batch(self.descs, self.n, self.flags, self.gpu, C.byref(h))
         if rc != 0:
             raise RuntimeError("oai_turbo_submit_batch failed (%d): %s" % (rc, last_error()))
+        return h
+
+    def wait(self, h):
+        """oai_turbo_wait: blocks until the batch is done; results are in self.out / self.status."""
         rc = lib.oai_turbo_wait(h)
         if rc != 0:
             raise RuntimeError("oai_turbo_wait failed (%d): %s" % (rc, last_error()))
         return self.out, self.status
+
+    def run(self):
+        return self.wait(self.submit())
 
 
 class DevPlan:

@@ -401,6 +401,7 @@ struct HostBatch {
   RmBlock* d_rm = nullptr;
   std::vector<RmBlock> rm;
   std::vector<int> rm_desc;        // descriptor index of each RmBlock
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // OAI_TURBO_TRACE: submit, H2D done, kernels done, D2H done
   // bookkeeping of the submitted batch
   std::vector<oai_cb_desc_t> descs;
   std::vector<int> order;          // GPU block i <-> descriptor order[i]
@@ -484,6 +485,7 @@ struct HostBatch {
   int submit(const oai_cb_desc_t* cbs, int ncb, unsigned fl, int gpu) {
     descs.assign(cbs, cbs + ncb);
     flags = fl;
+    static const bool trace = getenv("OAI_TURBO_TRACE") != nullptr;
     order.clear();
     int Kmax = 40;
     for (int i = 0; i < ncb; ++i) {
@@ -520,6 +522,7 @@ struct HostBatch {
     }
     int rc = ensure(gpu, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
     if (rc) return rc;
+    if (trace) { for (auto& e : ev) if (!e) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
     std::vector<CbMeta> meta(n);
     rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
@@ -577,6 +580,7 @@ struct HostBatch {
       CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
       i = j;
     }
+    if (trace) cudaEventRecord(ev[1], st);
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
     if (n16 > 0) {
       rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
@@ -590,14 +594,23 @@ struct HostBatch {
       rc = b8.decode8(d_in, d_out, d_status + n16, st);
       if (rc < 0) return rc;
     }
+    if (trace) cudaEventRecord(ev[2], st);
     CU(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
+    if (trace) cudaEventRecord(ev[3], st);
     return 0;
   }
 
   int wait() {
     const int n = (int)order.size();
     if (n) CU(cudaStreamSynchronize(st));
+    if (ev[0] && getenv("OAI_TURBO_TRACE")) {
+      static cudaEvent_t origin = nullptr;
+      if (!origin) origin = ev[0];
+      float t[4];
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], origin, ev[i]);
+      fprintf(stderr, "[trace %p] submit %.2f  h2d_done %.2f  kernels_done %.2f  d2h_done %.2f ms\n", (void*)this, t[0], t[1], t[2], t[3]);
+    }
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
       if (!d.decode_enable) { if (d.status) *d.status = 0xFE; continue; }

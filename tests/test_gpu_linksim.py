@@ -1,0 +1,101 @@
+"""ulsim/dlsim-equivalent harness on the GPU decoder: BASELINE configs[0] and [1] shapes.  Every
+block the harness decodes is re-decoded by the oracle chain from the same soft bits and must
+agree bit for bit; the BLER curve must fall with SNR."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import loader  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    assert torch.cuda.is_available()
+    from openair4g_b200 import capi as c
+    c.init_td16()
+    return c
+
+
+class Recorder:
+    """wraps capi.decode_batch to keep the submitted blocks and results for the oracle cross-check"""
+    def __init__(self, capi):
+        self.capi, self.calls = capi, []
+        self.BATCH_DL_STOP_AFTER_FAILURE = capi.BATCH_DL_STOP_AFTER_FAILURE
+
+    def decode_batch(self, blocks, flags=0):
+        w_before = [b["dematch"]["w"].copy() for b in blocks]
+        outs, status = self.capi.decode_batch(blocks, flags=flags)
+        w_after = [b["dematch"]["w"].copy() for b in blocks]
+        self.calls.append((blocks, w_before, w_after, outs, status, flags))
+        return outs, status
+
+
+def oracle_check(rec, llr8=0):
+    P = loader.port()
+    n = 0
+    for blocks, w_before, w_after, outs, status, flags in rec.calls:
+        failed_tb = set()
+        for b, w0, w1, ob, st in zip(blocks, w_before, w_after, outs, status):
+            dm, K, F = b["dematch"], b["K"], b["F"]
+            D = K + 4
+            RTC = (D + 31) // 32
+            dw = np.zeros(3 * 32 * RTC, dtype=np.uint8)
+            P.orc_generate_dummy_w(D, dw, F)
+            E = C.c_uint32(0)
+            w = w0.copy()
+            assert P.orc_lte_rate_matching_turbo_rx(RTC, dm["G"], w, dw, b["y"], dm["C"], 1827072, dm["Mdlharq"], dm["Kmimo"],
+                                                    dm["rvidx"], dm["clear"], dm["Qm"], dm["Nl"], dm["r"], C.byref(E)) == 0
+            assert np.array_equal(w, w1), "HARQ buffer differs from the oracle"
+            if flags and b["tb_id"] in failed_tb:
+                assert st == 0xFE and not ob.any()
+                continue
+            d = np.zeros(96 + 3 * D + 16, dtype=np.int16)
+            P.orc_sub_block_deinterleaving_turbo(D, d.ctypes.data + 96 * 2, w)
+            dec = loader.port_decode8 if llr8 else loader.port_decode16
+            wb, wr = dec(d[96:], K, b["max_iterations"], b["crc_type"], F)
+            assert st == wr and np.array_equal(ob, wb), (K, dm["r"], st, wr)
+            if wr > b["max_iterations"]:
+                failed_tb.add(b["tb_id"])
+            n += 1
+    return n
+
+
+def test_ulsim_25prb_mcs16_sweep(capi):
+    from openair4g_b200.sim import linksim
+    rec = Recorder(capi)
+    sim = linksim.LinkSim(linksim.ULSIM_25PRB_MCS16, max_iterations=4, seed=7)
+    assert (sim.C, sim.K, sim.F) == (2, 3904, 0)
+    bler = []
+    for snr in (5.5, 6.5, 7.5, 9.0):
+        r = sim.run(snr, 24, max_rounds=2, capi=rec)
+        bler.append(r["bler_round0"])
+        assert r["mismatch_vs_tx"] == 0
+        assert r["residual_bler"] <= r["bler_round0"]
+    assert bler[0] > 0.5 and bler[-1] == 0.0 and all(a >= b for a, b in zip(bler, bler[1:])), bler
+    assert oracle_check(rec) > 300
+
+
+def test_dlsim_100prb_mcs28_subframes(capi):
+    from openair4g_b200.sim import linksim
+    rec = Recorder(capi)
+    sim = linksim.LinkSim(linksim.DLSIM_100PRB_MCS28, max_iterations=4, seed=3)
+    assert (sim.C, sim.K, sim.F) == (13, 5824, 0)
+    hi = sim.run(25.0, 6, capi=rec)
+    lo = sim.run(17.0, 6, capi=rec)
+    assert hi["bler_round0"] == 0.0 and hi["mismatch_vs_tx"] == 0 and hi["avg_iterations"] <= 3.0
+    assert lo["bler_round0"] == 1.0
+    assert oracle_check(rec) >= 13 * 6
+
+
+def test_ulsim_8bit_decoder_switch(capi):
+    from openair4g_b200.sim import linksim
+    rec = Recorder(capi)
+    sim = linksim.LinkSim(linksim.UL_100PRB_MCS16, max_iterations=4, llr8=1, seed=5)
+    assert (sim.C, sim.K) == (5, 6144)
+    r = sim.run(8.0, 6, capi=rec)
+    assert r["mismatch_vs_tx"] == 0
+    assert oracle_check(rec, llr8=1) >= 5
