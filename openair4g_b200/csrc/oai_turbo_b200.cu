@@ -145,6 +145,8 @@ static int ctx_get(int dev, DevCtx** out) {
 // ---- a batch of code blocks resident on one GPU ---------------------------------------
 constexpr int CKPT_S = MAP_SEG;
 constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
+constexpr int MAX_PARTS = 8;      // pipeline stages of one host batch (copy of part i+1 overlaps the decode of part i)
+constexpr int MIN_PART_BLOCKS = 2960;
 
 // optional per-launch CUDA-event timing (bench.py's roofline leg): class 0 demux, 1 map, 2 x1, 3 x2
 struct Profiler {
@@ -199,7 +201,7 @@ struct Batch {
     CU(cudaMalloc(&d_state, sizeof(CbState) * ncb));
     CU(cudaMalloc(&d_ws, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
-    CU(cudaMalloc(&d_batch_max, sizeof(int)));
+    CU(cudaMalloc(&d_batch_max, sizeof(int) * MAX_PARTS));
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     return 0;
@@ -216,9 +218,19 @@ struct Batch {
     CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
-  // enqueue the whole 16-bit decode; returns #kernels launched or <0
-  int decode16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
+  // enqueue the whole 16-bit decode of blocks [lo, lo+cnt) (cnt < 0: all); returns #kernels launched or <0.
+  // `part` selects the batch-maximum cell, so that parts of one batch can run as independent pipeline stages.
+  int decode16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st, int lo = 0, int cnt = -1,
+               int part = 0) {
     int launches = 0;
+    const int n = (cnt < 0) ? this->n : cnt;
+    if (n <= 0) return 0;
+    CbMeta* d_meta = this->d_meta + lo;
+    CbState* d_state = this->d_state + lo;
+    int16_t* d_ws = this->d_ws + (long)lo * slot_hw;
+    u32* d_ckpt = this->d_ckpt + (long)lo * ckpt_words;
+    int* d_batch_max = this->d_batch_max + part;
+    if (status_dev) status_dev += lo;
     XchgArgs x;
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
@@ -388,6 +400,9 @@ struct HostBatch {
   Batch8 b8;                       // 8-bit decoder blocks of the same submit (placed after the 16-bit ones)
   int cap8_blocks = 0, cap8_K = 0, n16 = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st_copy = nullptr;                        // input copies of the pipelined form
+  cudaEvent_t ev_part[MAX_PARTS] = {};
+  bool direct_out = false;
   int dev = -1;
   int cap_blocks = 0, cap_K = 0;
   size_t cap_in = 0, cap_out = 0;
@@ -479,6 +494,7 @@ struct HostBatch {
     if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); h_out = nullptr; d_out = nullptr; }
     if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
+    if (st_copy) { cudaStreamDestroy(st_copy); st_copy = nullptr; for (auto& e : ev_part) { cudaEventDestroy(e); e = nullptr; } }
     cap_blocks = cap_K = 0; cap_in = cap_out = 0;
   }
 
@@ -564,27 +580,47 @@ struct HostBatch {
       g_launches += 2;
       CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     }
-    // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
-    // page-locked caller memory is copied from directly, pageable memory through the pinned stage
-    for (int i = 0; i < n;) {
-      if (descs[order[i]].dematch_enable) { ++i; continue; }     // y is produced on the device by k_deint
-      const int16_t* base = descs[order[i]].in;
-      size_t len = (size_t)3 * descs[order[i]].K + 12;
-      int j = i + 1;
-      while (j < n && !descs[order[j]].dematch_enable && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
-      cudaPointerAttributes at;
-      bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
-      cudaGetLastError();
-      const int16_t* src = base;
-      if (!pinned) { memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i]; }
-      CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-      i = j;
+    // Pipelined form (plain 16-bit batches that are large enough): the batch is cut into `parts` ranges of
+    // blocks; the input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).
+    int parts = 1;
+    if (rm.empty() && n == n16 && !getenv("OAI_TURBO_NO_PIPELINE")) parts = std::max(1, std::min(MAX_PARTS, n16 / MIN_PART_BLOCKS));
+    if (parts > 1 && !st_copy) {
+      CU(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+      for (auto& e : ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    if (trace) cudaEventRecord(ev[1], st);
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
     if (n16 > 0) {
       rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
       if (rc) return rc;
+    }
+    // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
+    // page-locked caller memory is copied from directly, pageable memory through the pinned stage
+    for (int part = 0; part < parts; ++part) {
+      const int lo = (int)((long)n * part / parts), hi = (int)((long)n * (part + 1) / parts);
+      cudaStream_t cs = (parts > 1) ? st_copy : st;
+      for (int i = lo; i < hi;) {
+        if (descs[order[i]].dematch_enable) { ++i; continue; }     // y is produced on the device by k_deint
+        const int16_t* base = descs[order[i]].in;
+        size_t len = (size_t)3 * descs[order[i]].K + 12;
+        int j = i + 1;
+        while (j < hi && !descs[order[j]].dematch_enable && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
+        cudaPointerAttributes at;
+        bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const int16_t* src = base;
+        if (!pinned) { memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i]; }
+        CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+        i = j;
+      }
+      if (parts > 1) {
+        CU(cudaEventRecord(ev_part[part], st_copy));
+        CU(cudaStreamWaitEvent(st, ev_part[part], 0));
+        rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
+        if (rc < 0) return rc;
+      }
+    }
+    if (trace) cudaEventRecord(ev[1], st);
+    if (n16 > 0 && parts == 1) {
       rc = b.decode16(d_in, d_out, d_status, st);
       if (rc < 0) return rc;
     }
@@ -595,7 +631,25 @@ struct HostBatch {
       if (rc < 0) return rc;
     }
     if (trace) cudaEventRecord(ev[2], st);
-    CU(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+    // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
+    // every block decoded) in page-locked memory, the result is copied straight into them
+    direct_out = false;
+    {
+      uint8_t* base = descs[order[0]].decoded_bytes;
+      bool ok = base != nullptr;
+      for (int i = 0; ok && i < n; ++i) {
+        const oai_cb_desc_t& d = descs[order[i]];
+        ok = d.decode_enable && d.max_iterations >= 2 && d.decoded_bytes == base + out_off[i];
+      }
+      if (ok) {
+        cudaPointerAttributes at;
+        ok = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+      }
+      direct_out = ok;
+    }
+    const size_t out_used = (size_t)out_off[n - 1] + (descs[order[n - 1]].K >> 3);
+    CU(cudaMemcpyAsync(direct_out ? descs[order[0]].decoded_bytes : h_out, d_out, direct_out ? out_used : out_b, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
     if (trace) cudaEventRecord(ev[3], st);
     return 0;
@@ -615,7 +669,7 @@ struct HostBatch {
       const oai_cb_desc_t& d = descs[order[i]];
       if (!d.decode_enable) { if (d.status) *d.status = 0xFE; continue; }
       // the reference leaves decoded_bytes untouched when max_iterations < 2 (no hard decision, TD16:1267)
-      if (d.decoded_bytes && d.max_iterations >= 2) memcpy(d.decoded_bytes, h_out + out_off[i], d.K >> 3);
+      if (!direct_out && d.decoded_bytes && d.max_iterations >= 2) memcpy(d.decoded_bytes, h_out + out_off[i], d.K >> 3);
       if (d.status) *d.status = h_status[i];
     }
     for (size_t j = 0; j < rm.size(); ++j) {                     // HARQ buffers back to their owners

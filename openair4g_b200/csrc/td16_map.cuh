@@ -309,6 +309,13 @@ __device__ __forceinline__ void stg_hint(uint4* p, const uint4& v, unsigned long
 #endif
 }
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction warms L2 with `bytes` contiguous bytes (multiple of 16, 16-byte aligned address)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
+#ifndef MAP_PF_MODE
+#define MAP_PF_MODE 0     // 0: one prefetch.global.L2 per 64-byte chunk; 1: + the second 32-byte sector; 2: bulk per segment
+#endif
 
 __device__ __forceinline__ u32 vaddmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
 
@@ -470,8 +477,21 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #endif
   for (int seg = 0; seg < nfull; ++seg) {
     if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
+#if MAP_PF_MODE == 2
+      const int c0 = (seg + PF) * NCH, nc = min(NCH, nchunk - c0);     // thread 0: systematic, thread 1: parity
+      if (nc > 0 && t < 2) {
+        if (t == 0) l2_prefetch_bulk(sys4 + c0 * 4, nc * 64);
+        else if (P8) l2_prefetch_bulk(par8 + c0 * 4 - t, nc * 32); else l2_prefetch_bulk(par4 + c0 * 4 - t, nc * 64);
+      }
+#else
       const int cp = (seg + PF) * NCH + (t % NCH);
-      if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t); }
+      if (cp < nchunk) {
+        l2_prefetch(sys4 + cp * 4 - t); if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t);
+#if MAP_PF_MODE == 1
+        l2_prefetch(sys4 + cp * 4 - t + 2); if (!P8) l2_prefetch(par4 + cp * 4 - t + 2);
+#endif
+      }
+#endif
     }
     ckpt_put(ck + seg * 32, a);
 #pragma unroll
@@ -550,11 +570,25 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     const int k0 = seg * S, k1 = min(W, k0 + S);
     const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
     if (PF > 0 && seg >= PF) {                    // warm L2 for segment seg-PF (inputs + checkpoint)
+#if MAP_PF_MODE == 2
+      const int c0 = (seg - PF) * NCH;                         // a full segment: thread 0 sys, 1 parity, 2 s0, 3 checkpoint
+      if (t == 0) l2_prefetch_bulk(sys4 + c0 * 4, NCH * 64);
+      else if (t == 1) { if (P8) l2_prefetch_bulk(par8 + c0 * 4 - t, NCH * 32); else l2_prefetch_bulk(par4 + c0 * 4 - t, NCH * 64); }
+      else if (t == 2) { if (UPD) { if (P8) l2_prefetch_bulk(s08 + c0 * 4 - t, NCH * 32); else l2_prefetch_bulk(s04 + c0 * 4 - t, NCH * 64); } }
+      else l2_prefetch_bulk(ck - t * 8 + (seg - PF) * 32, 128);
+#else
       const int cp = (seg - PF) * NCH + (t % NCH);
       l2_prefetch(sys4 + cp * 4 - t);
       if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t);
       if (UPD) { if (P8) l2_prefetch(s08 + cp * 4 - t); else l2_prefetch(s04 + cp * 4 - t); }
+#if MAP_PF_MODE == 1
+      l2_prefetch(sys4 + cp * 4 - t + 2);
+      if (!P8) { l2_prefetch(par4 + cp * 4 - t + 2); if (UPD) l2_prefetch(s04 + cp * 4 - t + 2); }
+      l2_prefetch(ck - t * 8 + (seg - PF) * 32 + t * 8);
+#else
       if (t == 0) l2_prefetch(ck + (seg - PF) * 32);
+#endif
+#endif
     }
     // a holds the checkpoint of this segment (fetched during the previous segment's beta phase)
     if (steady) {

@@ -192,28 +192,65 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
 }
 
 // ------------------------------------------------------------------------------------
-// CRC early-termination test of one block (all threads of the CTA call it after the decoded
-// bytes are in shared memory and a barrier; the result is valid in thread 0).  Also copies the
-// bytes to the output.  The reference walks `bits` bits starting at byte f0 (CRC24A skips the F
-// filler bits, TD16:1312-1313) and compares with the trailing crc bytes of the block.  A CRC
-// (zero start value, no final xor) is linear over GF(2): the remainder of the message is the
-// XOR of the remainders of its bytes, each shifted by its distance from the message end.
-__device__ __forceinline__ bool block_crc_check(const uint8_t* sbytes, uint8_t* outp, const CbMeta& m,
+// Hard decision of 32 consecutive natural positions j0..j0+31 (clipped to K) from the natural-order
+// C4 array in shared memory: bit = (sat8(x) > 0) = (x > 0), first position in bit 31
+// (reference TD16:1267-1302: MSB-first packing).
+__device__ __forceinline__ u32 hd_word32(const int16_t* nat, int j0, int K, int W) {
+  int lane = j0 / W, k = j0 - lane * W;
+  u32 bits = 0;
+  if ((W & 3) == 0) {
+    // K is a multiple of 32: all 32 positions exist and every group of 4 steps of one lane sits in
+    // one 16-byte chunk of the C4 layout (4 words, the lane's halfword selected by its parity)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 v = *reinterpret_cast<const uint4*>(nat + 2 * (((k >> 2) << 4) + ((lane >> 1) << 2)));
+      const int sh = (lane & 1) ? 0 : 16;
+      bits = (bits << 4) | ((int)(v.x << sh) >= 0x10000 ? 8u : 0u) | ((int)(v.y << sh) >= 0x10000 ? 4u : 0u) |
+             ((int)(v.z << sh) >= 0x10000 ? 2u : 0u) | ((int)(v.w << sh) >= 0x10000 ? 1u : 0u);
+      k += 4;
+      if (k >= W) { k = 0; ++lane; }
+    }
+  } else {
+    for (int q = 0; q < 32; ++q) {
+      const bool bit = (j0 + q < K) && (nat[c4_hw(k, lane)] > 0);
+      bits = (bits << 1) | (bit ? 1u : 0u);
+      if (++k >= W) { k = 0; ++lane; }
+    }
+  }
+  return bits;
+}
+
+// CRC early-termination test of one block.  Thread w < ceil(K/32) owns decoded bytes 4w..4w+3
+// (`word`, first byte in the low 8 bits); all threads of the CTA call this; the result is valid in
+// thread 0.  Also writes the bytes to the output.  The reference walks `bits` bits starting at byte
+// f0 (CRC24A skips the F filler bits, TD16:1312-1313) and compares with the trailing crc bytes of
+// the block.  A CRC (zero start value, no final xor) is linear over GF(2): the remainder of the
+// message is the XOR of the remainders of its bytes, each shifted by its distance from the message
+// end (two nibble look-ups per byte).
+__device__ __forceinline__ bool block_crc_check(u32 word, uint8_t* sbytes, uint8_t* outp, const CbMeta& m,
                                                 const u32* crc_tab, u32* xred) {
-  const int K = m.K, nb = K >> 3;
+  const int K = m.K, nb = K >> 3, nw = (nb + 3) >> 2;
   const int ct = m.crc_type;
   const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
   const int j_lo = (ct == 0) ? ((m.F >> 3) << 3) : 0;
   const int j_hi = j_lo + K - w - ((ct == 0) ? m.F : 0);       // message = bits [j_lo, j_hi)
   const int f0 = j_lo >> 3, full = (j_hi - j_lo) >> 3, resbit = (j_hi - j_lo) & 7;
   const u32* RB = crc_tab + ct * (768 * 32);
-  // CRC of the `full` whole bytes: XOR of per-byte remainders (two nibble look-ups each)
   u32 acc = 0;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    const u32 v = sbytes[b];
-    outp[b] = (uint8_t)v;
-    const int mdist = f0 + full - 1 - b;                       // bytes between this one and the message end
-    if (b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
+  const int wi = threadIdx.x;
+  if (wi < nw) {
+    reinterpret_cast<u32*>(sbytes)[wi] = word;
+    const int b0 = wi << 2;
+    if (b0 + 3 < nb && ((reinterpret_cast<uintptr_t>(outp) & 3) == 0)) reinterpret_cast<u32*>(outp)[wi] = word;
+    else
+      for (int q = 0; q < 4 && b0 + q < nb; ++q) outp[b0 + q] = (uint8_t)(word >> (8 * q));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = b0 + q;
+      const u32 v = (word >> (8 * q)) & 0xffu;
+      const int mdist = f0 + full - 1 - b;                       // bytes between this one and the message end
+      if (b < nb && b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
@@ -309,16 +346,11 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   if (p.iter > 1) {                                            // :1267-1351
     uint8_t* outp = p.out_base + m.out_off;
     const uint16_t* H = p.pi_pool + m.pi_off;
-    // bit = ext2 > 0 at natural position j, MSB first: one ballot per 32 positions
-    for (int j0 = (threadIdx.x & ~31); j0 < K; j0 += XCHG_THREADS) {
-      const int j = j0 + (threadIdx.x & 31);
-      const bool bit = (j < K) && (nat[H[j]] > 0);
-      const u32 mask = __ballot_sync(0xffffffffu, bit);
-      if ((threadIdx.x & 31) == 0)
-        *reinterpret_cast<u32*>(&sbytes[j0 >> 3]) = __byte_perm(__brev(mask), 0, 0x0123);
-    }
-    __syncthreads();
-    pass = block_crc_check(sbytes, outp, m, p.crc_xp, xred);
+    // bit = ext2 > 0 at natural position j, MSB first: thread w packs positions 32w..32w+31
+    u32 word = 0;
+    if ((int)threadIdx.x < ((K >> 3) + 3) >> 2)
+      word = __byte_perm(hd_word32(nat, threadIdx.x << 5, K, m.W), 0, 0x0123);
+    pass = block_crc_check(word, sbytes, outp, m, p.crc_xp, xred);
   } else {
     __syncthreads();
   }

@@ -289,15 +289,14 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += XCHG_THREADS) natdec[pi[i]] = dec[((i % W) << 4) + i / W];
     __syncthreads();
-    for (int j0 = (threadIdx.x & ~31); j0 < n; j0 += XCHG_THREADS) {
-      const int j = j0 + (threadIdx.x & 31);
-      const bool bit = (j < n) && (natdec[j] > 0);
-      const u32 mask = __ballot_sync(0xffffffffu, bit);
-      if ((threadIdx.x & 31) == 0)
-        *reinterpret_cast<u32*>(&sbytes[j0 >> 3]) = __byte_perm(__brev(mask), 0, 0x0123);
+    u32 word = 0;                              // thread w packs natural positions 32w..32w+31, MSB first
+    if ((int)threadIdx.x < ((n >> 3) + 3) >> 2) {
+      const int j0 = threadIdx.x << 5;
+      u32 bits = 0;
+      for (int q = 0; q < 32; ++q) bits = (bits << 1) | ((j0 + q < n && natdec[j0 + q] > 0) ? 1u : 0u);
+      word = __byte_perm(bits, 0, 0x0123);
     }
-    __syncthreads();
-    pass = block_crc_check(sbytes, p.out_base + m.out_off, m, p.crc_xp, xred);
+    pass = block_crc_check(word, sbytes, p.out_base + m.out_off, m, p.crc_xp, xred);
   }
   if (threadIdx.x == 0) {
     int s = 0;
