@@ -143,7 +143,7 @@ static int ctx_get(int dev, DevCtx** out) {
 }
 
 // ---- a batch of code blocks resident on one GPU ---------------------------------------
-constexpr int CKPT_S = MAP_SEG;
+constexpr int CKPT_S = MAP_CKPT_STEPS;
 constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
 constexpr int MAX_PARTS = 8;      // pipeline stages of one host batch (copy of part i+1 overlaps the decode of part i)
 constexpr int MIN_PART_BLOCKS = 2960;
@@ -244,7 +244,7 @@ struct Batch {
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter; mp.upd = upd;
       prof.begin(1, st);
-      k_map16<CKPT_S><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
+      k_map16<MAP_SEG><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
       prof.end(st);
       ++launches;
     };
@@ -939,7 +939,7 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1; mp.batch_max = (policy == 3) ? b.d_batch_max : nullptr;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
   mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1; mp.upd = 0;
-  k_map16<CKPT_S><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
+  k_map16<MAP_SEG><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
   g_launches += 2;
   std::vector<int16_t> tmp(b.A);
   CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));

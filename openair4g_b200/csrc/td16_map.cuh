@@ -34,10 +34,12 @@ constexpr int MAP_THREADS = 64;      // 16 code blocks per CTA
 #ifndef MAP_SEG_STEPS
 #define MAP_SEG_STEPS 16
 #endif
-constexpr int MAP_SEG = MAP_SEG_STEPS;   // checkpoint distance S (steps): 16 or 8
-// dynamic shared memory per CTA: per segment step and thread 32 B of alpha, 8 B of branch constants
-// and 4 B for the feedback term s0 - sys
-constexpr int MAP_SMEM_BYTES = MAP_SEG * MAP_THREADS * 44;
+constexpr int MAP_SEG = MAP_SEG_STEPS;   // checkpoint distance S of the fast path (steps)
+constexpr int MAP_ABUF_ENTRIES = 8;      // alpha entries per thread in shared memory (fast path: the even steps of a segment;
+                                         // exact path: all steps of its 8-step segments)
+constexpr int MAP_CKPT_STEPS = 8;        // the checkpoint pool is sized for the smaller of the two distances
+// dynamic shared memory per CTA: 32 B of alpha per entry and thread
+constexpr int MAP_SMEM_BYTES = MAP_ABUF_ENTRIES * MAP_THREADS * 32;
 constexpr int RERUN_STEPS = 5;       // L>>3, reference :171,189
 constexpr int NEG_INIT = -128;       // -MAX/2, reference :79,201
 
@@ -373,17 +375,14 @@ __device__ __forceinline__ void renorm(u32 (&a)[8]) {
   for (int s = 1; s < 8; ++s) a[s] = __vadd2(a[s], n);
 }
 
-template <int S>
+// shared-memory alpha buffer of the fast path: NE entries of 8 packed states per thread
+// (two conflict-free 128-bit rows per entry)
 struct FastSmem {
-  uint4* a0; uint4* a1; uint2* cc; u32* dd;
+  uint4* a0; uint4* a1;
   __device__ __forceinline__ FastSmem(unsigned char* base) {
     a0 = reinterpret_cast<uint4*>(base);
-    a1 = a0 + S * MAP_THREADS;
-    cc = reinterpret_cast<uint2*>(a1 + S * MAP_THREADS);
-    dd = reinterpret_cast<u32*>(cc + S * MAP_THREADS);
+    a1 = a0 + MAP_ABUF_ENTRIES * MAP_THREADS;
   }
-  __device__ __forceinline__ void putd(int e, int tid, u32 d) const { dd[e * MAP_THREADS + tid] = d; }
-  __device__ __forceinline__ u32 getd(int e, int tid) const { return dd[e * MAP_THREADS + tid]; }
   __device__ __forceinline__ void put(int e, int tid, const u32 (&a)[8]) const {
     a0[e * MAP_THREADS + tid] = make_uint4(a[0], a[1], a[2], a[3]);
     a1[e * MAP_THREADS + tid] = make_uint4(a[4], a[5], a[6], a[7]);
@@ -391,12 +390,6 @@ struct FastSmem {
   __device__ __forceinline__ void get(int e, int tid, u32 (&a)[8]) const {
     uint4 x = a0[e * MAP_THREADS + tid], y = a1[e * MAP_THREADS + tid];
     a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
-  }
-  __device__ __forceinline__ void putc(int e, int tid, const FC& c) const { cc[e * MAP_THREADS + tid] = make_uint2(c.Y, c.Z); }
-  __device__ __forceinline__ FC getc(int e, int tid) const {
-    uint2 v = cc[e * MAP_THREADS + tid];
-    FC c; c.Y = v.x; c.Z = v.y; c.X = __vadd2(v.x, v.y);
-    return c;
   }
 };
 
@@ -412,27 +405,30 @@ __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.
 // Fast MAP pass.  PM = P-1 with P the renormalisation period (1, 4 or 16 steps; compile time so
 // that the unrolled steady-state code has no data-dependent branches).
 //
-// Structure per 16-step segment (4 chunks of 4 steps, one LDG.128 per chunk and stream):
-//   forward : alpha in registers, checkpoint at the segment start
-//   backward: reload checkpoint, recompute alpha -> shared memory (+ the step's branch
-//             constants), then beta / ext from the segment end to its start.
-// The register that held chunk j is refilled with chunk j of the NEXT segment as soon as it has
-// been consumed, so global loads run a whole segment ahead of their use.
+// The kernel is bound by the SM's shared-memory/L1 data pipe (one 128-byte wavefront per cycle),
+// so the steady state keeps shared-memory traffic to the minimum:
+//   forward : alpha in registers, checkpoint (HBM) at every segment start (16 steps)
+//   backward: per segment, the inputs of its 16 steps stay in registers (4 chunks of 4 steps, one
+//             LDG.128 per chunk and stream); alpha is recomputed from the checkpoint and only the
+//             EVEN steps are written to shared memory; the beta / ext sweep reloads an even alpha
+//             and recomputes the following odd one from it (one extra alpha step per two trellis
+//             steps instead of 32 B stored + 32 B loaded); branch constants are recomputed from
+//             the input registers instead of going through shared memory.
+//   The registers of chunk j are refilled with chunk j of the NEXT segment as soon as the beta sweep
+//   has consumed them (chunk 0, which is needed first and freed last, goes through a spare set).
 // P8: parity (and s0) are read from the int8 copies: chunk c of this thread = 8 bytes at par8[c*4]
 template <int S, int PM, bool UPD, bool P8>
 __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0,
                               u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv,
                               unsigned char* smem, int tid) {
-  static_assert(S == 16 || S == 8, "segment = NCH chunks of 4 steps");
+  static_assert(S == 16, "steady-state segment = 4 chunks of 4 steps");
   constexpr int NCH = S / 4;
+  constexpr int HS = MAP_ABUF_ENTRIES;                         // boundary code works on sub-segments of HS steps
 #ifndef MAP_PF_SEGS
 #define MAP_PF_SEGS 3
 #endif
-#ifndef MAP_FWD_DIST2
-#define MAP_FWD_DIST2 0
-#endif
   constexpr int PF = MAP_PF_SEGS;                              // L2 prefetch distance in segments
-  const FastSmem<S> sm(smem);
+  const FastSmem sm(smem);
   const int nseg = (W + S - 1) / S, nchunk = (W + 3) >> 2;
   const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c of this thread at sys4[c*4]
   const uint4* par4 = reinterpret_cast<const uint4*>(par);
@@ -447,7 +443,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     if (P8) return prmt_sx(q < 2 ? v.x : v.y, (q & 1) ? 0xB3A2u : 0x9180u);
     return pick4(v, q);
   };
-  // single-step loaders for the short boundary loops
+  // single-step loaders for the boundary code
   auto ldp1 = [&](int k) -> u32 {
     if (P8) { u32 w = reinterpret_cast<const uint16_t*>(par)[c4_word(k, 0)]; return prmt_sx(w, 0x9180u); }
     return __ldg(par + c4_word(k, 0));
@@ -456,6 +452,8 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     if (P8) { u32 w = reinterpret_cast<const uint16_t*>(s0)[c4_word(k, 0)]; return prmt_sx(w, 0x9180u); }
     return __ldg(s0 + c4_word(k, 0));
   };
+  auto c1 = [&](int k) -> FC { return fconst(__ldg(sys + c4_word(k, 0)), ldp1(k)); };
+  auto d1 = [&](int k) -> u32 { return UPD ? __vsub2(ldz1(k), __ldg(sys + c4_word(k, 0))) : 0u; };   // s0 - sys
   u32 a[8];
   uint4 sb[NCH], pb[NCH], zb[NCH];
 
@@ -467,31 +465,11 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   for (int j = 0; j < NCH; ++j)
     if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = ldp(j); }
   const int nfull = W / S;                                     // segments with all 16 steps
-  const int keep_from = nchunk - (nchunk * 2) / 5;             // forward reads of the last 40% stay in L2
-  const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
-#if MAP_FWD_DIST2
-  uint4 sc[NCH], pc[NCH];                                          // segment seg+1 (registers are free in this phase)
-#pragma unroll
-  for (int j = 0; j < NCH; ++j)
-    if (NCH + j < nchunk) { sc[j] = __ldg(sys4 + (NCH + j) * 4); pc[j] = ldp(NCH + j); }
-#endif
+  const unsigned long long pol_stream = l2_policy_stream();
   for (int seg = 0; seg < nfull; ++seg) {
     if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
-#if MAP_PF_MODE == 2
-      const int c0 = (seg + PF) * NCH, nc = min(NCH, nchunk - c0);     // thread 0: systematic, thread 1: parity
-      if (nc > 0 && t < 2) {
-        if (t == 0) l2_prefetch_bulk(sys4 + c0 * 4, nc * 64);
-        else if (P8) l2_prefetch_bulk(par8 + c0 * 4 - t, nc * 32); else l2_prefetch_bulk(par4 + c0 * 4 - t, nc * 64);
-      }
-#else
       const int cp = (seg + PF) * NCH + (t % NCH);
-      if (cp < nchunk) {
-        l2_prefetch(sys4 + cp * 4 - t); if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t);
-#if MAP_PF_MODE == 1
-        l2_prefetch(sys4 + cp * 4 - t + 2); if (!P8) l2_prefetch(par4 + cp * 4 - t + 2);
-#endif
-      }
-#endif
+      if (cp < nchunk) { l2_prefetch(sys4 + cp * 4 - t); if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t); }
     }
     ckpt_put(ck + seg * 32, a);
 #pragma unroll
@@ -501,17 +479,8 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
         alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
-#if MAP_FWD_DIST2
-      sb[j] = sc[j]; pb[j] = pc[j];
-      const int cn = (seg + 2) * NCH + j;
-      if (cn < nchunk) { sc[j] = __ldg(sys4 + cn * 4); pc[j] = ldp(cn); }
-#else
       const int cn = (seg + 1) * NCH + j;
-      if (cn < nchunk) {
-        if (cn >= keep_from) { sb[j] = ldg_hint(sys4 + cn * 4, pol_keep); pb[j] = ldp(cn); }
-        else { sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn); }
-      }
-#endif
+      if (cn < nchunk) { sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn); }
     }
     renorm(a);                                                 // checkpoints are stored normalised
   }
@@ -530,21 +499,23 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     }
   }
 
-  // ---- alpha re-run seed ------------------------------------------------------------
-  u32 seed[8];
+  // ---- alpha re-run seed (kept in the checkpoint pool, slot nseg) -----------------------
+  {
+    u32 seed[8];
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    u32 prev = __shfl_sync(gmask, a[s], (t + 3) & 3, 4);
-    if (t == 0) prev = pack2(0, (s == 0) ? 0 : NEG_INIT);
-    seed[s] = __byte_perm(prev, a[s], 0x5432);
-  }
-  ckpt_put(ck + nseg * 32, seed);
-  if (W <= RERUN_STEPS) {
+    for (int s = 0; s < 8; ++s) {
+      u32 prev = __shfl_sync(gmask, a[s], (t + 3) & 3, 4);
+      if (t == 0) prev = pack2(0, (s == 0) ? 0 : NEG_INIT);
+      seed[s] = __byte_perm(prev, a[s], 0x5432);
+    }
+    ckpt_put(ck + nseg * 32, seed);
+    if (W <= RERUN_STEPS) {
 #pragma unroll
-    for (int s = 0; s < 8; ++s) a[s] = seed[s];
-    for (int k = 0; k < W; ++k) {
-      if ((k & PM) == 0) renorm(a);
-      alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), ldp1(k)));
+      for (int s = 0; s < 8; ++s) a[s] = seed[s];
+      for (int k = 0; k < W; ++k) {
+        if ((k & PM) == 0) renorm(a);
+        alpha_fast(a, c1(k));
+      }
     }
   }
 
@@ -557,139 +528,135 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   }
 
   // ---- backward sweep, pass 1 -----------------------------------------------------------
+  // loads the inputs of a whole segment into the chunk registers and its checkpoint into a[]
+  auto load_segment = [&](int seg) {
 #pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int c = (nseg - 1) * NCH + j;
-    if (c < nchunk) {
-      sb[j] = __ldg(sys4 + c * 4); pb[j] = ldp(c);
-      if (UPD) zb[j] = ldz(c);
+    for (int j = 0; j < NCH; ++j) {
+      const int c = seg * NCH + j;
+      if (c < nchunk) {
+        sb[j] = __ldg(sys4 + c * 4); pb[j] = ldp(c);
+        if (UPD) zb[j] = ldz(c);
+      }
     }
-  }
-  ckpt_get(ck + (nseg - 1) * 32, a);
+    ckpt_get(ck + seg * 32, a);
+  };
+  bool loaded = false;                             // sb/pb/zb/a hold segment `seg`
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
     const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
     if (PF > 0 && seg >= PF) {                    // warm L2 for segment seg-PF (inputs + checkpoint)
-#if MAP_PF_MODE == 2
-      const int c0 = (seg - PF) * NCH;                         // a full segment: thread 0 sys, 1 parity, 2 s0, 3 checkpoint
-      if (t == 0) l2_prefetch_bulk(sys4 + c0 * 4, NCH * 64);
-      else if (t == 1) { if (P8) l2_prefetch_bulk(par8 + c0 * 4 - t, NCH * 32); else l2_prefetch_bulk(par4 + c0 * 4 - t, NCH * 64); }
-      else if (t == 2) { if (UPD) { if (P8) l2_prefetch_bulk(s08 + c0 * 4 - t, NCH * 32); else l2_prefetch_bulk(s04 + c0 * 4 - t, NCH * 64); } }
-      else l2_prefetch_bulk(ck - t * 8 + (seg - PF) * 32, 128);
-#else
       const int cp = (seg - PF) * NCH + (t % NCH);
       l2_prefetch(sys4 + cp * 4 - t);
       if (P8) l2_prefetch(par8 + cp * 4 - t); else l2_prefetch(par4 + cp * 4 - t);
       if (UPD) { if (P8) l2_prefetch(s08 + cp * 4 - t); else l2_prefetch(s04 + cp * 4 - t); }
-#if MAP_PF_MODE == 1
-      l2_prefetch(sys4 + cp * 4 - t + 2);
-      if (!P8) { l2_prefetch(par4 + cp * 4 - t + 2); if (UPD) l2_prefetch(s04 + cp * 4 - t + 2); }
-      l2_prefetch(ck - t * 8 + (seg - PF) * 32 + t * 8);
-#else
       if (t == 0) l2_prefetch(ck + (seg - PF) * 32);
-#endif
-#endif
     }
-    // a holds the checkpoint of this segment (fetched during the previous segment's beta phase)
-    if (steady) {
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int e = j * 4 + q;
-          if ((e & PM) == 0 && e != 0) renorm(a);
-          const u32 sv = pick4(sb[j], q);
-          const FC c = fconst(sv, pk(pb[j], q));
-          sm.put(e, tid, a);
-          sm.putc(e, tid, c);
-          if (UPD) sm.putd(e, tid, __vsub2(pk(zb[j], q), sv));
-          if (e != S - 1) alpha_fast(a, c);
+    if (!steady) {
+      // boundary segment (the last one; every segment of a short block): two sub-segments of HS steps,
+      // alpha of every step in shared memory, inputs re-read step by step
+      for (int half = (S / HS) - 1; half >= 0; --half) {
+        const int ka = k0 + half * HS, kb = min(k1, ka + HS);
+        if (ka >= kb) continue;
+        ckpt_get(ck + seg * 32, a);
+        for (int k = k0; k < ka; ++k) {
+          if (((k - k0) & PM) == 0 && k != k0) renorm(a);
+          alpha_fast(a, c1(k));
         }
-        if (seg > 0) {
-          const int cn = (seg - 1) * NCH + j;
-          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
-          if (UPD) zb[j] = ldz(cn);
+        for (int k = ka; k < kb; ++k) {
+          if (((k - k0) & PM) == 0 && k != k0) renorm(a);
+          sm.put(k - ka, tid, a);
+          alpha_fast(a, c1(k));
         }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int e = j * 4 + q;
-          if (k0 + e < k1) {
-            if ((e & PM) == 0 && e != 0) renorm(a);
-            const u32 sv = pick4(sb[j], q);
-            const FC c = fconst(sv, pk(pb[j], q));
-            sm.put(e, tid, a);
-            sm.putc(e, tid, c);
-            if (UPD) sm.putd(e, tid, __vsub2(pk(zb[j], q), sv));
-            alpha_fast(a, c);
+        if (seg == 0 && half == 0) {               // alpha[0..5] come from the re-run chain
+          ckpt_get(ck + nseg * 32, a);
+          for (int k = 0; k <= RERUN_STEPS && k < kb; ++k) {
+            if ((k & PM) == 0) renorm(a);
+            sm.put(k, tid, a);
+            if (k < RERUN_STEPS) alpha_fast(a, c1(k));
           }
         }
-        if (seg > 0) {
-          const int cn = (seg - 1) * NCH + j;
-          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
-          if (UPD) zb[j] = ldz(cn);
+        for (int k = kb - 1; k >= ka; --k) {
+          const FC c = c1(k);
+          if (k <= W - 7) {                        // steps whose beta[k+1] is not replaced by the re-run
+            sm.get(k - ka, tid, a);
+            u32 x = ext_fast(a, b, c);
+            if (UPD) x = __vadd2(x, d1(k));
+            ext[c4_word(k, 0)] = x;
+          }
+          beta_fast(b, c);
+          if ((k & PM) == 0) renorm(b);
         }
       }
+      loaded = false;
+      continue;
     }
-    if (seg == 0) {          // alpha[0..5] come from the re-run chain
+    if (!loaded) { load_segment(seg); loaded = true; }
+    // ---- recompute alpha of the segment; even steps go to shared memory ----
 #pragma unroll
-      for (int s = 0; s < 8; ++s) a[s] = seed[s];
-      for (int k = 0; k <= RERUN_STEPS && k < k1; ++k) {
-        if ((k & PM) == 0) renorm(a);
-        sm.put(k, tid, a);
-        if (k < RERUN_STEPS) alpha_fast(a, sm.getc(k, tid));
+    for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = j * 4 + q;
+        if ((e & PM) == 0 && e != 0) renorm(a);
+        if ((e & 1) == 0) sm.put(e >> 1, tid, a);
+        if (e != S - 1) alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
     }
-    // next segment's checkpoint: in flight during this segment's beta phase
-    uint4 cka = make_uint4(0, 0, 0, 0), ckb = cka;
+    if (seg == 0) {          // alpha[0..5] come from the re-run chain: entries 0, 2, 4 (1, 3, 5 follow from them)
+      ckpt_get(ck + nseg * 32, a);
+#pragma unroll
+      for (int k = 0; k < RERUN_STEPS; ++k) {
+        if ((k & PM) == 0) renorm(a);
+        if ((k & 1) == 0) sm.put(k >> 1, tid, a);
+        if (k < RERUN_STEPS - 1) alpha_fast(a, fconst(pick4(sb[k >> 2], k & 3), pk(pb[k >> 2], k & 3)));
+      }
+    }
+    // next segment: checkpoint and chunk 0 (needed first, freed last -> spare registers) are requested now
+    uint4 cka = make_uint4(0, 0, 0, 0), ckb = cka, sx = cka, px = cka, zx = cka;
     if (seg > 0) {
       cka = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[0];
       ckb = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[1];
+      const int cn = (seg - 1) * NCH;
+      sx = ldg_hint(sys4 + cn * 4, pol_stream); px = ldp(cn);
+      if (UPD) zx = ldz(cn);
     }
-    if (steady) {
-      // software pipeline: the shared-memory loads of step e-1 are issued before the arithmetic of step e
+    // ---- beta / ext sweep over the segment, two steps (even e, odd e+1) per round ----
+    {
       u32 an[8];
-      FC cn = sm.getc(S - 1, tid);
-      u32 dn = UPD ? sm.getd(S - 1, tid) : 0u;
-      sm.get(S - 1, tid, an);
+      sm.get((S >> 1) - 1, tid, an);
 #pragma unroll
       for (int j = NCH - 1; j >= 0; --j) {
         u32 e4[4];
 #pragma unroll
-        for (int q = 3; q >= 0; --q) {
-          const int e = j * 4 + q;
-          const FC c = cn;
-          const u32 dcur = dn;
+        for (int h = 1; h >= 0; --h) {
+          const int ee = j * 4 + 2 * h, eo = ee + 1;
+          u32 ae[8], ao[8];
 #pragma unroll
-          for (int s = 0; s < 8; ++s) a[s] = an[s];
-          if (e > 0) {
-            cn = sm.getc(e - 1, tid);
-            if (UPD) dn = sm.getd(e - 1, tid);
-            sm.get(e - 1, tid, an);
-          }
-          e4[q] = ext_fast(a, b, c);
-          if (UPD) e4[q] = __vadd2(e4[q], dcur);
-          beta_fast(b, c);
-          if ((e & PM) == 0) renorm(b);
+          for (int s = 0; s < 8; ++s) { ae[s] = an[s]; ao[s] = an[s]; }
+          if (ee > 0) sm.get((ee >> 1) - 1, tid, an);          // in flight during this round's arithmetic
+          const u32 sve = pick4(sb[j], 2 * h), svo = pick4(sb[j], 2 * h + 1);
+          const FC ce = fconst(sve, pk(pb[j], 2 * h)), co = fconst(svo, pk(pb[j], 2 * h + 1));
+          alpha_fast(ao, ce);                                   // alpha[eo] from alpha[ee]
+          if ((eo & PM) == 0) renorm(ao);
+          u32 xo = ext_fast(ao, b, co);
+          if (UPD) xo = __vadd2(xo, __vsub2(pk(zb[j], 2 * h + 1), svo));
+          beta_fast(b, co);
+          if ((eo & PM) == 0) renorm(b);
+          u32 xe = ext_fast(ae, b, ce);
+          if (UPD) xe = __vadd2(xe, __vsub2(pk(zb[j], 2 * h), sve));
+          beta_fast(b, ce);
+          if ((ee & PM) == 0) renorm(b);
+          e4[2 * h + 1] = xo; e4[2 * h] = xe;
         }
         stg_hint(reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16), make_uint4(e4[0], e4[1], e4[2], e4[3]), pol_stream);
-      }
-    } else {
-      for (int k = k1 - 1; k >= k0; --k) {
-        const FC c = sm.getc(k - k0, tid);
-        if (k <= W - 7) {
-          sm.get(k - k0, tid, a);
-          u32 x = ext_fast(a, b, c);
-          if (UPD) x = __vadd2(x, sm.getd(k - k0, tid));
-          ext[c4_word(k, 0)] = x;
+        if (seg > 0 && j > 0) {                                  // chunk j is consumed: refill with the next segment's
+          const int cn = (seg - 1) * NCH + j;
+          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
+          if (UPD) zb[j] = ldz(cn);
         }
-        beta_fast(b, c);
-        if ((k & PM) == 0) renorm(b);
       }
     }
+    sb[0] = sx; pb[0] = px; zb[0] = zx;
     a[0] = cka.x; a[1] = cka.y; a[2] = cka.z; a[3] = cka.w; a[4] = ckb.x; a[5] = ckb.y; a[6] = ckb.z; a[7] = ckb.w;
   }
 
@@ -706,28 +673,22 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     ckpt_get(ck + sa * 32, a);
     for (int k = sa * S; k < W; ++k) {
       if ((k & PM) == 0 && k != sa * S) renorm(a);
-      const u32 sv = __ldg(sys + c4_word(k, 0));
-      const FC c = fconst(sv, ldp1(k));
-      if (k >= kk0) {
-        sm.put(k - kk0, tid, a); sm.putc(k - kk0, tid, c);
-        if (UPD) sm.putd(k - kk0, tid, __vsub2(ldz1(k), sv));
-      }
-      if (k + 1 < W) alpha_fast(a, c);
+      if (k >= kk0) sm.put(k - kk0, tid, a);
+      if (k + 1 < W) alpha_fast(a, c1(k));
     }
     if (kk0 <= RERUN_STEPS) {
-#pragma unroll
-      for (int s = 0; s < 8; ++s) a[s] = seed[s];
+      ckpt_get(ck + nseg * 32, a);
       for (int k = 0; k <= RERUN_STEPS && k < W; ++k) {
         if ((k & PM) == 0) renorm(a);
         if (k >= kk0) sm.put(k - kk0, tid, a);
-        if (k < RERUN_STEPS) alpha_fast(a, fconst(__ldg(sys + c4_word(k, 0)), ldp1(k)));
+        if (k < RERUN_STEPS) alpha_fast(a, c1(k));
       }
     }
     for (int k = W - 1; k >= kk0; --k) {
-      const FC c = sm.getc(k - kk0, tid);
+      const FC c = c1(k);
       sm.get(k - kk0, tid, a);
       u32 x = ext_fast(a, b, c);
-      if (UPD) x = __vadd2(x, sm.getd(k - kk0, tid));
+      if (UPD) x = __vadd2(x, d1(k));
       ext[c4_word(k, 0)] = x;
       if (k >= W - RERUN_STEPS) {
         beta_fast(b, c);
@@ -779,8 +740,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
 
   unsigned char* smem = reinterpret_cast<unsigned char*>(abuf);
   const u32* s0 = reinterpret_cast<const u32*>(slot + (long)ARR_S0 * p.A) + t * 4;
-  if (P == 0) {                                 // exact saturating policy, int16 arrays
-    map_pass<SatArith, S>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
+  if (P == 0) {                                 // exact saturating policy, int16 arrays, 8-step segments
+    map_pass<SatArith, MAP_ABUF_ENTRIES>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
     return;
   }
   // int8 copies of parity / s0 when the whole batch has |y| <= 127 (warp-uniform: one flag per batch)
