@@ -65,7 +65,7 @@ struct DevCtx {
   uint32_t pi_off[188], t_off[188];
   uint16_t* qpp_pool = nullptr;       // plain QPP tables pi[i] (8-bit decoder kernels)
   uint32_t qpp_off[188];
-  u32* crc_xp = nullptr;              // [4][768]
+  u32* crc_xp = nullptr;              // [4][32][CRC_NM] powers of x mod the CRC polynomials
   bool ok = false;
 };
 static DevCtx g_ctx[16];
@@ -111,25 +111,18 @@ static int ctx_get(int dev, DevCtx** out) {
     CU(cudaMemcpy(c.qpp_pool, qpool.data(), qpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.t_pool, tpool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.t_pool, tpool.data(), tpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    // per-byte CRC remainders for the four CRCs (polynomials: crc_byte.c:53-57): entry
-    // [t][m][n] = n(x) * x^(8m + w + 4) mod P for the high nibble n (0..15) and
-    // [t][m][16+n] = n(x) * x^(8m + w) mod P for the low nibble of the byte m bytes before the end
-    std::vector<u32> xp(4 * 768 * 32);
+    // powers of x modulo the four CRC polynomials (crc_byte.c:53-57): entry [t][r][m] = x^(w + r + 32 m) mod P,
+    // the weight of a 32-bit message word whose last bit is r + 32 m bits before the message end
+    std::vector<u32> xp(4 * 32 * CRC_NM);
     const u32 polys[4] = {0x864cfbu, 0x800063u, 0x1021u, 0x9Bu};
     const int ws[4] = {24, 24, 16, 8};
     for (int t = 0; t < 4; ++t) {
       u32 r = 1;
       for (int i = 0; i < ws[t]; ++i) r = gf_xtimes(r, polys[t], ws[t]);    // x^w
-      for (int m = 0; m < 768; ++m) {
-        u32 pw[8];                                                            // x^(8m+w+i), i = 0..7
-        for (int i = 0; i < 8; ++i) { pw[i] = r; r = gf_xtimes(r, polys[t], ws[t]); }
-        for (int n = 0; n < 16; ++n) {
-          u32 lo = 0, hi = 0;
-          for (int i = 0; i < 4; ++i) if (n & (1 << i)) { lo ^= pw[i]; hi ^= pw[4 + i]; }
-          xp[(t * 768 + m) * 32 + n] = hi;
-          xp[(t * 768 + m) * 32 + 16 + n] = lo;
-        }
-      }
+      std::vector<u32> pw(32 * CRC_NM + 32);
+      for (size_t e = 0; e < pw.size(); ++e) { pw[e] = r; r = gf_xtimes(r, polys[t], ws[t]); }   // x^(w+e)
+      for (int rr = 0; rr < 32; ++rr)
+        for (int m = 0; m < CRC_NM; ++m) xp[(t * 32 + rr) * CRC_NM + m] = pw[rr + 32 * m];
     }
     CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
     CU(cudaMemcpy(c.crc_xp, xp.data(), xp.size() * sizeof(u32), cudaMemcpyHostToDevice));

@@ -16,6 +16,7 @@
 namespace oai {
 
 constexpr int XCHG_THREADS = 256;
+constexpr int CRC_NM = 193;          // 32-bit words of the longest block (+1)
 
 struct XchgArgs {
   const CbMeta* meta;
@@ -26,8 +27,7 @@ struct XchgArgs {
   int nblk;
   const uint16_t* pi_pool;      // per K: H[j] (K entries) = C4 halfword index of natural position j
   const uint16_t* t_pool;       // per K: T[h] (A entries, layout order) = H[pi(pos(h))]; padding maps to itself
-  const u32* crc_xp;            // [4][768][32]: remainder of a high nibble v (entries 0..15) / low nibble (16..31)
-                                // of the byte m bytes before the end of the message: v(x) * x^(8m+w[+4]) mod P
+  const u32* crc_xp;            // [4][32][CRC_NM]: x^(w + r + 32 m) mod P for the four CRCs (block_crc_check)
   const int16_t* in_base;       // batch input (device)
   uint8_t* out_base;            // batch output (device)
   uint8_t* status_out;          // batch status bytes (device), written when a block finishes
@@ -68,6 +68,31 @@ struct MinMax2 {
     return max(max(lo16(mx), hi16(mx)), max(-lo16(mn), -hi16(mn)));      // >= 0 once a value was added
   }
 };
+
+// out word q = in word (q + r) & 3.  The QPP interleaver maps the 8 lanes of step k to the 8 lanes of step
+// pi(k) mod W (contention-free property), and pi is a bijection mod 8 when 8 | W; the shared-memory bank of
+// an element in the C4 layout is fixed by (step mod 8, lane pair).  A warp holds 8 consecutive chunks; when
+// chunk c starts at step (c>>1)&3 its 8 chunks touch 8 different steps mod 8 per instruction, so the 32
+// scattered 16-bit accesses fall into 32 different banks.
+__device__ __forceinline__ uint4 rot4(uint4 v, int r) {
+  if (r & 1) v = make_uint4(v.y, v.z, v.w, v.x);
+  if (r & 2) v = make_uint4(v.z, v.w, v.x, v.y);
+  return v;
+}
+
+// carry-less 32 x 32 -> 64 bit multiplication from 16 integer multiplications: the operands are split into
+// 4 classes of every 4th bit, so that at most 8 partial products meet in one bit position and the 3 hole
+// bits above it absorb the carries
+__device__ __forceinline__ unsigned long long clmul32(u32 x, u32 y) {
+  typedef unsigned long long u64;
+  const u32 x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+  const u32 y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+  u64 z0 = ((u64)x0 * y0) ^ ((u64)x1 * y3) ^ ((u64)x2 * y2) ^ ((u64)x3 * y1);
+  u64 z1 = ((u64)x0 * y1) ^ ((u64)x1 * y0) ^ ((u64)x2 * y3) ^ ((u64)x3 * y2);
+  u64 z2 = ((u64)x0 * y2) ^ ((u64)x1 * y1) ^ ((u64)x2 * y0) ^ ((u64)x3 * y3);
+  u64 z3 = ((u64)x0 * y3) ^ ((u64)x1 * y2) ^ ((u64)x2 * y1) ^ ((u64)x3 * y0);
+  return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) | (z3 & 0x8888888888888888ull);
+}
 
 // position p -> halfword index in the C4 layout; magic = floor(2^32/W)+1
 __device__ __forceinline__ int pos_hw(int p, int W, u32 magic) {
@@ -175,7 +200,10 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   __syncthreads();
   const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
   for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
-    const uint4 tt = __ldg(T4 + i);
+    // thread (chunk c, lane pair t) walks its 4 steps starting at step (c>>1)&3: the 8 chunks of a warp then
+    // address 8 different rows mod 8 in every instruction -> conflict-free 16-bit accesses (see rot4)
+    const int r = (i >> 3) & 3;
+    const uint4 tt = rot4(__ldg(T4 + i), r);
     const u32 tw[4] = {tt.x, tt.y, tt.z, tt.w};
     u32 o[4];
 #pragma unroll
@@ -183,7 +211,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
       const u32 lo = (uint16_t)in[tw[q] & 0xffffu], hi = (uint16_t)in[tw[q] >> 16];
       o[q] = lo | (hi << 16);
     }
-    gsys[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    gsys[i] = rot4(make_uint4(o[0], o[1], o[2], o[3]), (4 - r) & 3);
   }
   // s2 is a permutation of ext: same maximum
   warp_max_to(mm.absmax(), &smax);
@@ -193,81 +221,81 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
 
 // ------------------------------------------------------------------------------------
 // Hard decision of 32 consecutive natural positions j0..j0+31 (clipped to K) from the natural-order
-// C4 array in shared memory: bit = (sat8(x) > 0) = (x > 0), first position in bit 31
-// (reference TD16:1267-1302: MSB-first packing).
+// C4 array in shared memory, generic form (any W): bit = (sat8(x) > 0) = (x > 0), first position in
+// bit 31 (reference TD16:1267-1302: MSB-first packing).
 __device__ __forceinline__ u32 hd_word32(const int16_t* nat, int j0, int K, int W) {
   int lane = j0 / W, k = j0 - lane * W;
   u32 bits = 0;
-  if ((W & 3) == 0) {
-    // K is a multiple of 32: all 32 positions exist and every group of 4 steps of one lane sits in
-    // one 16-byte chunk of the C4 layout (4 words, the lane's halfword selected by its parity)
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 v = *reinterpret_cast<const uint4*>(nat + 2 * (((k >> 2) << 4) + ((lane >> 1) << 2)));
-      const int sh = (lane & 1) ? 0 : 16;
-      bits = (bits << 4) | ((int)(v.x << sh) >= 0x10000 ? 8u : 0u) | ((int)(v.y << sh) >= 0x10000 ? 4u : 0u) |
-             ((int)(v.z << sh) >= 0x10000 ? 2u : 0u) | ((int)(v.w << sh) >= 0x10000 ? 1u : 0u);
-      k += 4;
-      if (k >= W) { k = 0; ++lane; }
-    }
-  } else {
-    for (int q = 0; q < 32; ++q) {
-      const bool bit = (j0 + q < K) && (nat[c4_hw(k, lane)] > 0);
-      bits = (bits << 1) | (bit ? 1u : 0u);
-      if (++k >= W) { k = 0; ++lane; }
-    }
+  for (int q = 0; q < 32; ++q) {
+    const bool bit = (j0 + q < K) && (nat[c4_hw(k, lane)] > 0);
+    bits = (bits << 1) | (bit ? 1u : 0u);
+    if (++k >= W) { k = 0; ++lane; }
   }
   return bits;
 }
 
-// CRC early-termination test of one block.  Thread w < ceil(K/32) owns decoded bytes 4w..4w+3
-// (`word`, first byte in the low 8 bits); all threads of the CTA call this; the result is valid in
-// thread 0.  Also writes the bytes to the output.  The reference walks `bits` bits starting at byte
-// f0 (CRC24A skips the F filler bits, TD16:1312-1313) and compares with the trailing crc bytes of
-// the block.  A CRC (zero start value, no final xor) is linear over GF(2): the remainder of the
-// message is the XOR of the remainders of its bytes, each shifted by its distance from the message
-// end (two nibble look-ups per byte).
-__device__ __forceinline__ bool block_crc_check(u32 word, uint8_t* sbytes, uint8_t* outp, const CbMeta& m,
+// the two 4-bit hard-decision groups of one C4 uint4 (4 steps x lanes 2t, 2t+1): returns the nibble of lane
+// 2t in bits 0..3 and of lane 2t+1 in bits 16..19, first step in the nibble's bit 3
+__device__ __forceinline__ u32 hd_nibbles(const uint4& d) {
+  return (__vcmpgts2(d.x, 0u) & 0x00080008u) | (__vcmpgts2(d.y, 0u) & 0x00040004u) |
+         (__vcmpgts2(d.z, 0u) & 0x00020002u) | (__vcmpgts2(d.w, 0u) & 0x00010001u);
+}
+
+// 8 nibbles stored one per byte at index n^7 (n = position/4) -> the 32 decisions, first position in bit 31
+__device__ __forceinline__ u32 nibbles_to_word(uint2 v) {
+  u32 lo = v.x & 0x0F0F0F0Fu, hi = v.y & 0x0F0F0F0Fu;
+  lo = (lo | (lo >> 4)) & 0x00FF00FFu; lo = (lo | (lo >> 8)) & 0xFFFFu;
+  hi = (hi | (hi >> 4)) & 0x00FF00FFu; hi = (hi | (hi >> 8)) & 0xFFFFu;
+  return (hi << 16) | lo;
+}
+
+// CRC early-termination test of one block.  Thread w < ceil(K/32) owns the decisions of positions
+// 32w..32w+31 (`bits`, first position in bit 31); all threads of the CTA call this; the result is valid
+// in thread 0.  Also writes the decoded bytes to the output.  The reference walks n-w(-F) bits starting
+// at byte F>>3 (CRC24A skips the filler bits, TD16:1312-1313) and compares with the trailing crc bytes.
+// A CRC with zero start value and no final xor is the polynomial remainder M(x) x^w mod P, linear over
+// GF(2): thread w multiplies its 32 message bits by x^(distance to the message end + w) mod P (one
+// coalesced table read + a carry-less multiplication), the products are XORed over the CTA and thread 0
+// reduces the 32+w-bit sum once.  This also covers message lengths that are not a multiple of 8
+// (crc_byte.c:130-131).
+__device__ __forceinline__ bool block_crc_check(u32 bits, uint8_t* sbytes, uint8_t* outp, const CbMeta& m,
                                                 const u32* crc_tab, u32* xred) {
+  typedef unsigned long long u64;
   const int K = m.K, nb = K >> 3, nw = (nb + 3) >> 2;
   const int ct = m.crc_type;
   const int w = (ct <= 1) ? 24 : (ct == 2 ? 16 : 8);
   const int j_lo = (ct == 0) ? ((m.F >> 3) << 3) : 0;
   const int j_hi = j_lo + K - w - ((ct == 0) ? m.F : 0);       // message = bits [j_lo, j_hi)
-  const int f0 = j_lo >> 3, full = (j_hi - j_lo) >> 3, resbit = (j_hi - j_lo) & 7;
-  const u32* RB = crc_tab + ct * (768 * 32);
-  u32 acc = 0;
+  const int Q = j_hi >> 5, r = j_hi & 31;
+  u64 acc = 0;
   const int wi = threadIdx.x;
   if (wi < nw) {
+    const u32 word = __byte_perm(bits, 0, 0x0123);             // first byte in the low 8 bits
     reinterpret_cast<u32*>(sbytes)[wi] = word;
     const int b0 = wi << 2;
     if (b0 + 3 < nb && ((reinterpret_cast<uintptr_t>(outp) & 3) == 0)) reinterpret_cast<u32*>(outp)[wi] = word;
     else
       for (int q = 0; q < 4 && b0 + q < nb; ++q) outp[b0 + q] = (uint8_t)(word >> (8 * q));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int b = b0 + q;
-      const u32 v = (word >> (8 * q)) & 0xffu;
-      const int mdist = f0 + full - 1 - b;                       // bytes between this one and the message end
-      if (b < nb && b >= f0 && mdist >= 0) acc ^= __ldg(RB + mdist * 32 + (v >> 4)) ^ __ldg(RB + mdist * 32 + 16 + (v & 15u));
-    }
+    u32 mb = bits;
+    const int lead = j_lo - (wi << 5);                         // positions before the message start
+    if (lead > 0) mb = (lead < 32) ? (mb & (0xffffffffu >> lead)) : 0u;
+    if (wi < Q) acc = clmul32(mb, __ldg(crc_tab + (ct * 32 + r) * CRC_NM + (Q - wi - 1)));
+    else if (wi == Q && r > 0) acc = clmul32(mb >> (32 - r), __ldg(crc_tab + (ct * 32) * CRC_NM));
   }
+  u32 alo = (u32)acc, ahi = (u32)(acc >> 32);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) xred[threadIdx.x >> 5] = acc;
+  for (int o = 16; o > 0; o >>= 1) { alo ^= __shfl_xor_sync(0xffffffffu, alo, o); ahi ^= __shfl_xor_sync(0xffffffffu, ahi, o); }
+  if ((threadIdx.x & 31) == 0) { xred[2 * (threadIdx.x >> 5)] = alo; xred[2 * (threadIdx.x >> 5) + 1] = ahi; }
   __syncthreads();
   bool pass = false;
   if (threadIdx.x == 0) {
     const u32 poly = (ct == 0) ? 0x864cfbu : (ct == 1) ? 0x800063u : (ct == 2) ? 0x1021u : 0x9Bu;
-    const u32 mask = (w == 24) ? 0xffffffu : (w == 16 ? 0xffffu : 0xffu), topbit = 1u << (w - 1);
-    u32 crc = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) crc ^= xred[i];
-    for (int jb = 0; jb < resbit; ++jb) {                      // residual bits, crc_byte.c:130-131
-      const u32 bit = (sbytes[f0 + full] >> (7 - jb)) & 1u;
-      const u32 top = ((crc & topbit) ? 1u : 0u) ^ bit;
-      crc = (crc << 1) & mask;
-      if (top) crc ^= poly;
-    }
+    const u64 pfull = ((u64)1 << w) | poly;
+    u64 V = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) V ^= ((u64)xred[2 * i + 1] << 32) | xred[2 * i];
+    for (int bit = 31 + w; bit >= w; --bit)
+      if ((V >> bit) & 1) V ^= pfull << (bit - w);
+    const u32 crc = (u32)V & (u32)(((u64)1 << w) - 1);
     // received CRC as the reference assembles it: big-endian for the 24-bit CRCs (after its
     // byte swap, TD16:1314-1326), a little-endian 16-bit load for CRC16 (:1329-1333)
     u32 rx;
@@ -283,8 +311,9 @@ __device__ __forceinline__ bool block_crc_check(u32 word, uint8_t* sbytes, uint8
 __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
-  __shared__ u32 xred[XCHG_THREADS / 32];
+  __shared__ u32 xred[2 * XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
+  __shared__ __align__(16) uint8_t snib[1536 + 16];              // hard decisions, one 4-step group per byte
   const int blk = blockIdx.x;
   if (blk >= p.nblk) return;
   const CbMeta m = p.meta[blk];
@@ -303,7 +332,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   int16_t* nat = sm;
   const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
   for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // ext2 back to natural order (scatter)
-    const uint4 v = gext2[i], tt = __ldg(T4 + i);
+    const int r = (i >> 3) & 3;                                 // rotated step order: conflict-free banks (rot4)
+    const uint4 v = rot4(gext2[i], r), tt = rot4(__ldg(T4 + i), r);
     const u32 vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -317,9 +347,20 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   // saturating operations below are plain adds: 4 instead of 14 instructions per word.
   const bool nosat = (guardB <= p.guard_b) && (12 * (guardB + 1) + 276 + st->max_ext + st->max_in <= 32767);
   MinMax2 mm;
+  // hard decisions (iteration_cnt > 1 only, :1267): when 4 | W every uint4 of the natural-order array holds two
+  // complete 4-position groups; they are parked one per byte (index n^7, n = position/4) and packed below
+  const bool hd = p.iter > 1, hd4 = hd && ((m.W & 3) == 0);
+  const int Wq = m.W >> 2;
+  auto park = [&](int i, const uint4& d) {
+    const u32 nb2 = hd_nibbles(d);
+    const int c = i >> 2, l0 = (i & 3) << 1;
+    snib[(l0 * Wq + c) ^ 7] = (uint8_t)(nb2 & 0xffu);
+    snib[((l0 + 1) * Wq + c) ^ 7] = (uint8_t)(nb2 >> 16);
+  };
   if (nosat) {
     for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 - ext) + s0, :1241-1265
       const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
+      if (hd4) park(i, d);
       uint4 r;
       r.x = __vadd2(d.x, __vsub2(s0.x, e.x));
       r.y = __vadd2(d.y, __vsub2(s0.y, e.y));
@@ -331,6 +372,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   } else {
     for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 (-) ext) (+) s0
       const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
+      if (hd4) park(i, d);
       uint4 r;
       r.x = __vaddss2(__vsubss2(d.x, e.x), s0.x);
       r.y = __vaddss2(__vsubss2(d.y, e.y), s0.y);
@@ -343,13 +385,13 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   warp_max_to(mm.absmax(), &smax);
 
   bool pass = false;
-  if (p.iter > 1) {                                            // :1267-1351
+  if (hd) {                                                    // :1267-1351
     uint8_t* outp = p.out_base + m.out_off;
-    const uint16_t* H = p.pi_pool + m.pi_off;
+    if (hd4) __syncthreads();
     // bit = ext2 > 0 at natural position j, MSB first: thread w packs positions 32w..32w+31
     u32 word = 0;
     if ((int)threadIdx.x < ((K >> 3) + 3) >> 2)
-      word = __byte_perm(hd_word32(nat, threadIdx.x << 5, K, m.W), 0, 0x0123);
+      word = hd4 ? nibbles_to_word(reinterpret_cast<const uint2*>(snib)[threadIdx.x]) : hd_word32(nat, threadIdx.x << 5, K, m.W);
     pass = block_crc_check(word, sbytes, outp, m, p.crc_xp, xred);
   } else {
     __syncthreads();

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_8(Td8Args p) {
 
 __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
   extern __shared__ int8_t sm8[];
-  __shared__ u32 xred[XCHG_THREADS / 32];
+  __shared__ u32 xred[2 * XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
   const int blk = blockIdx.x;
   if (blk >= p.nblk) return;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
       const int j0 = threadIdx.x << 5;
       u32 bits = 0;
       for (int q = 0; q < 32; ++q) bits = (bits << 1) | ((j0 + q < n && natdec[j0 + q] > 0) ? 1u : 0u);
-      word = __byte_perm(bits, 0, 0x0123);
+      word = bits;
     }
     pass = block_crc_check(word, sbytes, p.out_base + m.out_off, m, p.crc_xp, xred);
   }
