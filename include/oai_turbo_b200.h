@@ -17,6 +17,7 @@
 #ifndef OAI_TURBO_B200_H
 #define OAI_TURBO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -134,6 +135,13 @@ int oai_turbo_submit_batch(const oai_cb_desc_t *cbs, int ncb, unsigned flags, in
 /* Blocks until the batch is finished, scatters decoded_bytes/status/w back to the
  * host pointers of the descriptors and frees the handle. */
 int oai_turbo_wait(oai_turbo_batch_t *handle);
+
+/* Page-locked host memory for batch inputs / outputs.  Buffers from this allocator (or any
+ * other cudaHostAlloc / cudaHostRegister memory) are copied from and to directly; pageable
+ * memory goes through the library's own pinned staging area.  Large batches are pipelined:
+ * the input copy of one part of the batch overlaps the decode of the previous part. */
+void *oai_turbo_host_alloc(size_t bytes);
+void oai_turbo_host_free(void *p);
 
 /* ------------------------------------------------------------------------------------
  * 3. Device-resident decode (throughput mode: inputs already in HBM)

@@ -28,7 +28,7 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
-           "oai_turbo_dev_plan_profile",
+           "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
            "oai_turbo_debug_map16"]
 
@@ -58,6 +58,10 @@ lib.sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, C.c_void_
 lib.sub_block_deinterleaving_turbo.restype = None
 lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
+lib.oai_turbo_host_alloc.argtypes = [C.c_size_t]
+lib.oai_turbo_host_alloc.restype = C.c_void_p
+lib.oai_turbo_host_free.argtypes = [C.c_void_p]
+lib.oai_turbo_host_free.restype = None
 lib.oai_turbo_dev_plan_create.argtypes = [C.c_int, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.POINTER(C.c_void_p)]
 lib.oai_turbo_dev_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
 lib.oai_turbo_dev_plan_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -181,6 +185,25 @@ def debug_map16(y, K, term, policy=0):
     return ext
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from oai_turbo_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        self._p = lib.oai_turbo_host_alloc(nbytes)
+        if not self._p:
+            raise MemoryError("oai_turbo_host_alloc(%d) failed: %s" % (nbytes, last_error()))
+        buf = (C.c_uint8 * nbytes).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.array[...] = 0
+
+    def __del__(self):
+        if getattr(self, "_p", None) and lib is not None:
+            lib.oai_turbo_host_free(self._p)
+            self._p = None
+
+
 class HostBatchCall:
     """A prepared oai_turbo_submit_batch call over equal-parameter blocks laid out back to
     back in ONE host buffer (ideally page-locked): descriptors are built once, run() is
@@ -190,7 +213,8 @@ class HostBatchCall:
         n = y_host.shape[0]
         assert y_host.dtype == np.int16 and y_host.shape[1] == 3 * K + 12 and y_host.flags["C_CONTIGUOUS"]
         self.y, self.n, self.K, self.flags, self.gpu = y_host, n, K, flags, gpu
-        self.out = np.zeros((n, K // 8), dtype=np.uint8)
+        self._pin_out = PinnedArray((n, K // 8), np.uint8)     # page-locked: results are copied straight into it
+        self.out = self._pin_out.array
         self.status = np.zeros(n, dtype=np.uint8)
         self.descs = (CbDesc * n)()
         base, ob, sb = y_host.ctypes.data, self.out.ctypes.data, self.status.ctypes.data

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <algorithm>
 
@@ -139,7 +140,7 @@ static int ctx_get(int dev, DevCtx** out) {
 constexpr int CKPT_S = MAP_CKPT_STEPS;
 constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
 constexpr int MAX_PARTS = 8;      // pipeline stages of one host batch (copy of part i+1 overlaps the decode of part i)
-constexpr int MIN_PART_BLOCKS = 2960;
+constexpr int MIN_PART_BLOCKS = 2960;   // smaller parts leave the MAP kernel latency-bound (measured: 16 parts 25 ms, 8 parts 18.6 ms per 23680 blocks)
 
 // optional per-launch CUDA-event timing (bench.py's roofline leg): class 0 demux, 1 map, 2 x1, 3 x2
 struct Profiler {
@@ -393,8 +394,8 @@ struct HostBatch {
   Batch8 b8;                       // 8-bit decoder blocks of the same submit (placed after the 16-bit ones)
   int cap8_blocks = 0, cap8_K = 0, n16 = 0;
   cudaStream_t st = nullptr;
-  cudaStream_t st_copy = nullptr;                        // input copies of the pipelined form
-  cudaEvent_t ev_part[MAX_PARTS] = {};
+  cudaStream_t st_copy = nullptr, st_out = nullptr;      // input / output copies of the pipelined form
+  cudaEvent_t ev_part[MAX_PARTS] = {}, ev_done[MAX_PARTS] = {}, ev_out = nullptr;
   bool direct_out = false;
   int dev = -1;
   int cap_blocks = 0, cap_K = 0;
@@ -487,7 +488,12 @@ struct HostBatch {
     if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); h_out = nullptr; d_out = nullptr; }
     if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
-    if (st_copy) { cudaStreamDestroy(st_copy); st_copy = nullptr; for (auto& e : ev_part) { cudaEventDestroy(e); e = nullptr; } }
+    if (st_copy) {
+      cudaStreamDestroy(st_copy); st_copy = nullptr; cudaStreamDestroy(st_out); st_out = nullptr;
+      for (auto& e : ev_part) { cudaEventDestroy(e); e = nullptr; }
+      for (auto& e : ev_done) { cudaEventDestroy(e); e = nullptr; }
+      cudaEventDestroy(ev_out); ev_out = nullptr;
+    }
     cap_blocks = cap_K = 0; cap_in = cap_out = 0;
   }
 
@@ -573,13 +579,33 @@ struct HostBatch {
       g_launches += 2;
       CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     }
+    // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
+    // every block decoded) in page-locked memory, the result is copied straight into them
+    direct_out = false;
+    {
+      uint8_t* base = descs[order[0]].decoded_bytes;
+      bool ok = base != nullptr;
+      for (int i = 0; ok && i < n; ++i) {
+        const oai_cb_desc_t& d = descs[order[i]];
+        ok = d.decode_enable && d.max_iterations >= 2 && d.decoded_bytes == base + out_off[i];
+      }
+      if (ok) {
+        cudaPointerAttributes at;
+        ok = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+      }
+      direct_out = ok;
+    }
     // Pipelined form (plain 16-bit batches that are large enough): the batch is cut into `parts` ranges of
     // blocks; the input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).
     int parts = 1;
     if (rm.empty() && n == n16 && !getenv("OAI_TURBO_NO_PIPELINE")) parts = std::max(1, std::min(MAX_PARTS, n16 / MIN_PART_BLOCKS));
     if (parts > 1 && !st_copy) {
       CU(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
       for (auto& e : ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
     }
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
     if (n16 > 0) {
@@ -610,6 +636,11 @@ struct HostBatch {
         CU(cudaStreamWaitEvent(st, ev_part[part], 0));
         rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
         if (rc < 0) return rc;
+        // this part's decoded bytes go back while the next parts are still being copied in / decoded
+        CU(cudaEventRecord(ev_done[part], st));
+        CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
+        const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
+        CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
       }
     }
     if (trace) cudaEventRecord(ev[1], st);
@@ -624,25 +655,13 @@ struct HostBatch {
       if (rc < 0) return rc;
     }
     if (trace) cudaEventRecord(ev[2], st);
-    // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
-    // every block decoded) in page-locked memory, the result is copied straight into them
-    direct_out = false;
-    {
-      uint8_t* base = descs[order[0]].decoded_bytes;
-      bool ok = base != nullptr;
-      for (int i = 0; ok && i < n; ++i) {
-        const oai_cb_desc_t& d = descs[order[i]];
-        ok = d.decode_enable && d.max_iterations >= 2 && d.decoded_bytes == base + out_off[i];
-      }
-      if (ok) {
-        cudaPointerAttributes at;
-        ok = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-      }
-      direct_out = ok;
-    }
     const size_t out_used = (size_t)out_off[n - 1] + (descs[order[n - 1]].K >> 3);
-    CU(cudaMemcpyAsync(direct_out ? descs[order[0]].decoded_bytes : h_out, d_out, direct_out ? out_used : out_b, cudaMemcpyDeviceToHost, st));
+    if (parts > 1) {
+      CU(cudaEventRecord(ev_out, st_out));
+      CU(cudaStreamWaitEvent(st, ev_out, 0));
+    } else {
+      CU(cudaMemcpyAsync(direct_out ? descs[order[0]].decoded_bytes : h_out, d_out, direct_out ? out_used : out_b, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
     if (trace) cudaEventRecord(ev[3], st);
     return 0;
@@ -672,14 +691,13 @@ struct HostBatch {
     if (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) {
       // dlsch_decoding.c:400,417,448-451: after the first failing block of a transport block the
       // remaining ones are not decoded and their c[r] stays zeroed
+      std::unordered_map<uint32_t, bool> failed;             // transport block -> a block of it has failed already
       for (size_t i = 0; i < descs.size(); ++i) {
         const oai_cb_desc_t& d = descs[i];
         if (!d.status) continue;
-        bool after_fail = false;
-        for (size_t j = 0; j < i; ++j)
-          if (descs[j].tb_id == d.tb_id && descs[j].status && *descs[j].status != 0xFE &&
-              *descs[j].status >= 1 + descs[j].max_iterations) { after_fail = true; break; }
-        if (after_fail) { *d.status = 0xFE; if (d.decoded_bytes) memset(d.decoded_bytes, 0, d.K >> 3); }
+        bool& f = failed[d.tb_id];
+        if (f) { *d.status = 0xFE; if (d.decoded_bytes) memset(d.decoded_bytes, 0, d.K >> 3); }
+        else if (*d.status != 0xFE && *d.status >= 1 + d.max_iterations) f = true;
       }
     }
     return 0;
@@ -770,6 +788,13 @@ int oai_turbo_wait(oai_turbo_batch_t* h) {
 }
 
 int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4);
+
+void* oai_turbo_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(-100, "cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+  return p;
+}
+void oai_turbo_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 void init_td16(void) {
   DevCtx* c;

@@ -393,13 +393,6 @@ struct FastSmem {
   }
 };
 
-// prmt with the sign-replication selector bit (__byte_perm only honours 3 bits per nibble)
-__device__ __forceinline__ u32 prmt_sx(u32 a, u32 sel) {
-  u32 d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
-  return d;
-}
-
 __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
 
 // Fast MAP pass.  PM = P-1 with P the renormalisation period (1, 4 or 16 steps; compile time so
@@ -466,6 +459,15 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = ldp(j); }
   const int nfull = W / S;                                     // segments with all 16 steps
   const unsigned long long pol_stream = l2_policy_stream();
+#ifndef MAP_FWD_DIST2
+#define MAP_FWD_DIST2 0
+#endif
+#if MAP_FWD_DIST2
+  uint4 sc[NCH], pc[NCH];                                      // segment seg+1 (registers are free in this phase)
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+    if (NCH + j < nchunk) { sc[j] = __ldg(sys4 + (NCH + j) * 4); pc[j] = ldp(NCH + j); }
+#endif
   for (int seg = 0; seg < nfull; ++seg) {
     if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
       const int cp = (seg + PF) * NCH + (t % NCH);
@@ -479,8 +481,14 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
         alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
+#if MAP_FWD_DIST2
+      sb[j] = sc[j]; pb[j] = pc[j];
+      const int cn = (seg + 2) * NCH + j;
+      if (cn < nchunk) { sc[j] = ldg_hint(sys4 + cn * 4, pol_stream); pc[j] = ldp(cn); }
+#else
       const int cn = (seg + 1) * NCH + j;
       if (cn < nchunk) { sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn); }
+#endif
     }
     renorm(a);                                                 // checkpoints are stored normalised
   }
@@ -698,8 +706,11 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   }
 }
 
+#ifndef MAP_MAX_REGS
+#define MAP_MAX_REGS 168          // 6 CTAs (12 warps) per SM; measured against 128 / 144 / 184 / 200 / 216 / 243
+#endif
 template <int S>
-__global__ void __launch_bounds__(MAP_THREADS) k_map16(MapArgs p) {
+__global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   extern __shared__ uint4 abuf[];
   const int tid = threadIdx.x;
   const int gt = blockIdx.x * MAP_THREADS + tid;

@@ -71,4 +71,16 @@ __device__ __forceinline__ int lo16(u32 x) { return (int)(int16_t)(x & 0xffffu);
 __device__ __forceinline__ int hi16(u32 x) { return (int)(int16_t)(x >> 16); }
 __device__ __forceinline__ int sat16i(int v) { return max(-32768, min(32767, v)); }
 
+// prmt with the sign-replication selector bit (__byte_perm only honours 3 bits per nibble)
+__device__ __forceinline__ u32 prmt_sx(u32 a, u32 sel) {
+  u32 d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+
+// 8 int8 (4 steps x 2 lanes, C4 order) -> the 4 packed int16 pairs
+__device__ __forceinline__ uint4 widen8(uint2 v) {
+  return make_uint4(prmt_sx(v.x, 0x9180u), prmt_sx(v.x, 0xB3A2u), prmt_sx(v.y, 0x9180u), prmt_sx(v.y, 0xB3A2u));
+}
+
 }  // namespace oai
