@@ -154,7 +154,7 @@ def run_reference(args):
     rng = np.random.default_rng(1234)
     nd = 64
     y = rng.integers(-16, 17, size=(nd, 3 * K_BITS + 12)).astype(np.int16)
-    per_step = max(threads * 16, 256)
+    per_step = max(threads * 256, 1024)     # ~0.1 s per step on 16 threads
     for _ in range(args.warmup):
         cpu_decode_rate(y, max(threads, 64), threads)
     t_tot, kind = 0.0, "port"
@@ -186,6 +186,7 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from openair4g_b200 import capi
     capi.init_td16()
@@ -246,8 +247,8 @@ def run_b200(args):
     Be = args.e2e_blocks
     y_pin = torch.empty((Be, row), dtype=torch.int16).pin_memory()
     y_pin.copy_(y_dev[:Be].cpu())
-    # one submit + wait per step.  (Keeping two batches in flight was measured and is NOT used: on this
-    # box kernels run ~2.5x slower while a host->device copy of another batch is in flight, see DESIGN.md.)
+    # one submit + wait per step; inside the call the batch is pipelined in parts (input copy of part i+1 overlaps the
+    # decode of part i, decoded bytes of part i go back meanwhile) and lands in page-locked caller memory
     call = capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE)
     for _ in range(2):
         call.run()
@@ -282,21 +283,42 @@ def run_b200(args):
     bytes_per_launch = B * algorithmic_bytes_per_block(K) / (2.0 * MAX_ITER)
     achieved = bytes_per_launch / (map_ms * 1e-3) / 1e9 if n_map else 0.0
     kernel_ms_total = sum(prof_ms)
+    # dram__bytes_read.sum + dram__bytes_write.sum per k_map16 launch of 23680 blocks, ncu --set full capture
+    # profiles/r1h_ncu_full_summary.txt (mean of the three captured launches), scaled to this batch size
+    traffic = 1.444e9 * B / 23680.0 if K == K_BITS else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_map16", "avg_launch_ms": map_ms, "launches_timed": n_map,
+                "traffic": traffic, "kernel": "k_map16", "avg_launch_ms": map_ms, "launches_timed": n_map,
                 "share_of_step": prof_ms[1] / kernel_ms_total if kernel_ms_total else None,
                 "kernel_ms": {"demux": prof_ms[0], "map": prof_ms[1], "x1": prof_ms[2], "x2": prof_ms[3]},
                 "peak_source": peak_src,
-                "note": "algorithmic bytes per launch = blocks x (2(3K+12)+K/8+1)/12; the kernel is bound by "
-                        "integer-SIMD issue, not HBM (see int_simd)"}
-    # integer-SIMD view: SURVEY 8(d) counts 123 int16 ops / info bit / MAP pass
+                "actual_dram_gbs": (traffic / (map_ms * 1e-3) / 1e9) if (traffic and n_map) else None,
+                "note": "algorithmic bytes per launch = blocks x (2(3K+12)+K/8+1)/12 (SURVEY 8d: y read once, bytes + "
+                        "status written once, spread over the 12 MAP passes); the decoder streams its per-block state "
+                        "through HBM on every pass, so the traffic actually moved per launch (`traffic`, ncu) is ~11x "
+                        "the algorithmic figure; `actual_dram_gbs` = traffic / launch time.  The kernel is co-limited "
+                        "by the ALU pipe (VIADDMNMX issues every 2nd clock), the L1/shared-memory data pipe and HBM "
+                        "latency (ncu: 62 % / 60 % / 50 % of peak), see DESIGN.md and int_simd"}
+    # integer-SIMD view: SURVEY 8(d) counts 123 int16 ops / info bit / MAP pass; the peak is the MEASURED issue rate of
+    # the k_map16 instruction mix (tools/int16_peak.cu, profiles/int16_peak.json), scaled by the sampled SM clock
     ops = B * K * 123.0
-    int_peak = 148 * 64 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None   # 64 lanes/clk/SM x 2 halfwords
+    try:
+        ipk = json.load(open(os.path.join(ROOT, "profiles", "int16_peak.json")))
+        int_peak = ipk["int16_ops_peak_gops_kmap16_mix"] * 1e9 * ((clocks and clocks["sm_mhz"]) or 1965.0) / 1965.0
+        int_note = "peak = measured issue rate of the 2 VIADDMNMX + VIADD + IMAD mix (tools/int16_peak.cu) at the sampled SM clock"
+    except Exception:
+        int_peak = 148 * 128 * 2 * 1965.0e6
+        int_note = "paper peak = 148 SM x 128 lanes x 2 halfwords x 1965 MHz (profiles/int16_peak.json missing)"
     int_simd = {"achieved_int16_gops": ops / (map_ms * 1e-3) / 1e9 if n_map else None,
-                "paper_peak_int16_gops": int_peak / 1e9 if int_peak else None,
-                "note": "paper peak = 148 SM x 64 INT lanes x 2 halfwords x sampled SM clock"}
-    if int_simd["achieved_int16_gops"] and int_simd["paper_peak_int16_gops"]:
-        int_simd["frac"] = int_simd["achieved_int16_gops"] / int_simd["paper_peak_int16_gops"]
+                "measured_peak_int16_gops": int_peak / 1e9, "note": int_note}
+    if int_simd["achieved_int16_gops"]:
+        int_simd["frac"] = int_simd["achieved_int16_gops"] / int_simd["measured_peak_int16_gops"]
+    # issue-slot view from executed instructions: ncu (profiles/r1h) counts 207.8 M warp instructions per k_map16
+    # launch of 23680 blocks at K=6144 = 8776 per block (the fast path needs 44 thread instructions per bit and pass,
+    # not SURVEY's nominal 123 ops); the SM issues at most 4 warp instructions per clock
+    if K == K_BITS and n_map:
+        sm_hz = ((clocks and clocks["sm_mhz"]) or 1965.0) * 1e6
+        int_simd["executed_warp_instr_per_block_pass"] = 8776
+        int_simd["issue_frac"] = B * 8776.0 / (map_ms * 1e-3) / (148 * 4 * sm_hz)
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -323,7 +345,8 @@ def run_b200(args):
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
-                    "api": "oai_turbo_submit_batch + oai_turbo_wait per step, pinned host input, host output"},
+                    "api": "oai_turbo_submit_batch + oai_turbo_wait per step, page-locked host input and output buffers; "
+                           "bound by the PCIe copy of 36.9 KB of int16 LLRs per 6144 decoded bits"},
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -364,11 +387,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks", type=int, default=23680,
-                    help="code blocks per GPU per step (device-resident); 23680 = 2 full waves of the MAP kernel "
-                         "(148 SMs x 5 resident CTAs x 16 blocks)")
-    ap.add_argument("--e2e-blocks", type=int, default=23680, help="code blocks per GPU per step (host-buffer API)")
-    ap.add_argument("--cpu-blocks", type=int, default=32768, help="bounded CPU-baseline sample (blocks), ~12-25 s of CPU work")
+    ap.add_argument("--blocks", type=int, default=42624,
+                    help="code blocks per GPU per step (device-resident); 42624 = 3 full waves of the MAP kernel "
+                         "(148 SMs x 6 resident CTAs x 16 blocks)")
+    ap.add_argument("--e2e-blocks", type=int, default=42624, help="code blocks per GPU per step (host-buffer API)")
+    ap.add_argument("--cpu-blocks", type=int, default=262144,
+                    help="bounded CPU-baseline sample (blocks): ~4 s of wall time on 16 host threads (~60 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
     ap.add_argument("--K", type=int, default=K_BITS, help="block size for --llr8 / side measurements")

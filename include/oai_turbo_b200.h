@@ -93,6 +93,14 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t *w, uint8_t *du
  * 3*D+2] (callers pass &d[r][96], dlsch_decoding.c:380). */
 void sub_block_deinterleaving_turbo(uint32_t D, int16_t *d, int16_t *w);
 
+/* Parameter part of lte_segmentation (openair1/PHY/CODING/lte_segmentation.c:52-134; the
+ * reference also copies the transport block into c[r], a TX-side job): C, C+, C-, K+, K-, F
+ * for a transport block of B bits (CRC24A included).  Host integer rule, no kernel; the
+ * batched callers use it to build their descriptors.  Returns 0, or -1 when C > 16 or
+ * B'/C > 6144 like the reference.  Keeps the reference's quirk K- = B'/C - 8 for B'/C <= 512. */
+int oai_lte_segmentation_params(uint32_t B, uint32_t *C, uint32_t *Cplus, uint32_t *Cminus,
+                                uint32_t *Kplus, uint32_t *Kminus, uint32_t *F);
+
 /* ------------------------------------------------------------------------------------
  * 2. Batched submit (new): all code blocks of a subframe / of many subframes and cells
  * ---------------------------------------------------------------------------------- */

@@ -28,7 +28,7 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
-           "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free",
+           "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
            "oai_turbo_debug_map16"]
 
@@ -58,6 +58,8 @@ lib.sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, C.c_void_
 lib.sub_block_deinterleaving_turbo.restype = None
 lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
+lib.oai_lte_segmentation_params.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 6
+lib.oai_lte_segmentation_params.restype = C.c_int
 lib.oai_turbo_host_alloc.argtypes = [C.c_size_t]
 lib.oai_turbo_host_alloc.restype = C.c_void_p
 lib.oai_turbo_host_free.argtypes = [C.c_void_p]
@@ -183,6 +185,13 @@ def debug_map16(y, K, term, policy=0):
     if rc != 0:
         raise RuntimeError("oai_turbo_debug_map16 failed (%d): %s" % (rc, last_error()))
     return ext
+
+
+def lte_segmentation_params(B):
+    """oai_lte_segmentation_params: returns (rc, dict(C, Cplus, Cminus, Kplus, Kminus, F))."""
+    v = [C.c_uint32(0) for _ in range(6)]
+    rc = lib.oai_lte_segmentation_params(B, *[C.byref(x) for x in v])
+    return rc, dict(zip(("C", "Cplus", "Cminus", "Kplus", "Kminus", "F"), [int(x.value) for x in v]))
 
 
 class PinnedArray:

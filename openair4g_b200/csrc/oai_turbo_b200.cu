@@ -789,6 +789,39 @@ int oai_turbo_wait(oai_turbo_batch_t* h) {
 
 int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4);
 
+// lte_segmentation.c:52-134, parameter part
+int oai_lte_segmentation_params(uint32_t B, uint32_t* C, uint32_t* Cplus, uint32_t* Cminus, uint32_t* Kplus,
+                                uint32_t* Kminus, uint32_t* F) {
+  if (!C || !Cplus || !Cminus || !Kplus || !Kminus || !F) return fail(-1, "null output pointer");
+  uint32_t Bp = B;
+  *C = 1;
+  if (B > 6144) {                                   // :58-70: L = 24 per block once the block is split
+    *C = (B + 6119) / 6120;
+    Bp = B + 24 * (*C);
+  }
+  if (*C > 16) return -1;                           // MAX_NUM_DLSCH_SEGMENTS, :72-76
+  const uint32_t q = Bp / (*C);
+  uint32_t step;
+  if (q <= 40) { *Kplus = 40; *Kminus = 0; step = 0; }
+  else if (q <= 512) { *Kplus = q & ~7u; *Kminus = q - 8; step = 0; }      // :78-82 (sic: K- from q, not from K+)
+  else if (q <= 1024) step = 16;
+  else if (q <= 2048) step = 32;
+  else if (q <= 6144) step = 64;
+  else return -1;                                   // :110-113
+  if (step) {
+    *Kplus = q & ~(step - 1);
+    if (*Kplus < q) *Kplus += step;
+    *Kminus = *Kplus - step;
+  }
+  if (*C == 1) { *Cplus = 1; *Kminus = 0; *Cminus = 0; }
+  else {
+    *Cminus = ((*C) * (*Kplus) - Bp) / (*Kplus - *Kminus);
+    *Cplus = *C - *Cminus;
+  }
+  *F = (*Cplus) * (*Kplus) + (*Cminus) * (*Kminus) - Bp;
+  return 0;
+}
+
 void* oai_turbo_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(-100, "cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }

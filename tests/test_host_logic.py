@@ -1,0 +1,21 @@
+"""CPU-only: host-side integer logic of the C ABI (no kernels involved) against the oracle."""
+import ctypes as C
+
+import pytest
+
+
+def test_segmentation_params_match_oracle(port):
+    """oai_lte_segmentation_params follows lte_segmentation.c:52-134 (parameter part): compared with the oracle
+    port (itself pinned to the compiled reference in test_oracle_pin.py) over small, boundary and large B."""
+    from openair4g_b200 import capi
+    Bs = list(range(24, 6300, 7)) + list(range(6100, 100000, 211)) + [40, 41, 512, 513, 1024, 1025, 2048, 2049, 6144, 6145,
+                                                                     75376 + 24, 30576 + 24, 7736 + 24, 97920, 97921, 200000]
+    for B in Bs:
+        v = [C.c_uint32(0) for _ in range(6)]
+        r2 = port.orc_lte_segmentation(B, *[C.byref(x) for x in v])
+        want = tuple(x.value for x in v)
+        r1, got = capi.lte_segmentation_params(B)
+        assert r1 == r2, B
+        if r1 == 0:
+            assert tuple(got[k] for k in ("C", "Cplus", "Cminus", "Kplus", "Kminus", "F")) == want, (B, got, want)
+    assert capi.lte_segmentation_params(75376 + 24)[1] == {"C": 13, "Cplus": 13, "Cminus": 0, "Kplus": 5824, "Kminus": 5760, "F": 0}
