@@ -367,6 +367,7 @@ def run_llr8(args, capi, B, K, rank, world, dist):
     for _ in range(args.warmup):
         plan.decode(y_dev.data_ptr(), row, out_dev.data_ptr(), K // 8, st_dev.data_ptr(), stream)
     torch.cuda.synchronize()
+    plan.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -374,7 +375,9 @@ def run_llr8(args, capi, B, K, rank, world, dist):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    prof_ms, _ = plan.profile(False, fetch=True)
     print(json.dumps({"metric": "turbo_decoded_info_mbit_per_s_8bit_decoder", "value": B * K * args.steps / (ms * 1e-3) / 1e6,
+                      "kernel_ms": {"demux": prof_ms[0], "map": prof_ms[1], "x1": prof_ms[2], "x2": prof_ms[3]},
                       "unit": "Mbit/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                       "dtype": "int8", "data": "synthetic",
                       "config": {"workload": "8-bit decoder, K=%d, max_iterations=6, noise regime" % K, "blocks": B},

@@ -269,30 +269,31 @@ struct Batch {
 
 // ---- 8-bit decoder batch (TD8): int8 per-position arrays + full alpha/beta arrays in HBM ----
 struct Batch8 {
+  Profiler prof;
   DevCtx* ctx = nullptr;
   int cap = 0, n = 0, A = 0, max_iter = 0;
-  long slot_b = 0, ab_b = 0;
+  long slot_b = 0, ck_words = 0;
   CbMeta* d_meta = nullptr;
   CbState* d_state = nullptr;
   int8_t* d_ws = nullptr;
-  int8_t* d_ab = nullptr;
+  u32* d_ck = nullptr;
   std::vector<CbMeta> h_meta;
   int alloc(DevCtx* c, int ncb, int Kmax) {
     ctx = c; cap = ncb;
-    A = (Kmax + 15) & ~15;
+    A = (Kmax + 127) & ~127;              // C8 layout: whole 8-step chunks of 128 bytes
     slot_b = (long)A8_COUNT * A;
-    ab_b = 2L * 128 * (Kmax / 16 + 1);
+    ck_words = ckpt8_words(Kmax / 16);
     CU(cudaMalloc(&d_meta, sizeof(CbMeta) * ncb));
     CU(cudaMalloc(&d_state, sizeof(CbState) * ncb));
     CU(cudaMalloc(&d_ws, slot_b * ncb));
-    CU(cudaMalloc(&d_ab, ab_b * ncb));
+    CU(cudaMalloc(&d_ck, sizeof(u32) * ck_words * ncb));
     CU(cudaMemset(d_ws, 0, slot_b * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     return 0;
   }
   void release() {
-    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ab);
-    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ab = nullptr; cap = 0;
+    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ck);
+    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ck = nullptr; cap = 0;
   }
   int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
     h_meta = m;
@@ -305,23 +306,31 @@ struct Batch8 {
   int decode8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
     int launches = 0;
     Td8Args a;
-    a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ab = d_ab; a.ab_b = ab_b;
+    a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ck = d_ck; a.ck_words = ck_words;
     a.nblk = n; a.qpp = ctx->qpp_pool; a.crc_xp = ctx->crc_xp; a.in_base = in_dev; a.out_base = out_dev;
     a.status_out = status_dev; a.iter = 0; a.sys_arr = a.par_arr = a.out_arr = 0;
-    const int map_grid = (n * 16 + MAP8_THREADS - 1) / MAP8_THREADS;
+    const int map_grid = (n * 8 + MAP8_THREADS - 1) / MAP8_THREADS;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int iter) {
       a.sys_arr = sys_arr; a.par_arr = par_arr; a.out_arr = out_arr; a.iter = iter;
-      k_map8<<<map_grid, MAP8_THREADS, 0, st>>>(a);
+      prof.begin(1, st);
+      k_map8<<<map_grid, MAP8_THREADS, MAP8_SMEM_BYTES, st>>>(a);
+      prof.end(st);
       ++launches;
     };
+    prof.begin(0, st);
     k_demux8<<<n, XCHG_THREADS, 3 * A, st>>>(a);
+    prof.end(st);
     ++launches;
     map(A8_S0, A8_P1, A8_EXT, 1);                                // TD8:1325
     for (int it = 1; it <= max_iter; ++it) {                    // TD8:1327
       a.iter = it;
+      prof.begin(2, st);
       k_x1_8<<<n, XCHG_THREADS, A, st>>>(a);
+      prof.end(st);
       map(A8_SYS, A8_P2, A8_EXT2, it);                           // TD8:1386
+      prof.begin(3, st);
       k_x2_8<<<n, XCHG_THREADS, 2 * A, st>>>(a);
+      prof.end(st);
       launches += 2;
       if (it < max_iter) map(A8_SYS, A8_P1, A8_EXT, it + 1);     // TD8:1634
     }
@@ -1021,12 +1030,13 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
 // accumulated totals per kernel class {demux, map, x1, x2} (the stream must be idle)
 int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4) {
   if (!p) return fail(-1, "null plan");
-  p->b.prof.collect();
+  Profiler& pr = p->llr8 ? p->b8.prof : p->b.prof;
+  pr.collect();
   if (ms4 && count4) {
-    for (int i = 0; i < 4; ++i) { ms4[i] = p->b.prof.ms[i]; count4[i] = p->b.prof.count[i]; }
-    p->b.prof.reset();
+    for (int i = 0; i < 4; ++i) { ms4[i] = pr.ms[i]; count4[i] = pr.count[i]; }
+    pr.reset();
   }
-  p->b.prof.on = enable != 0;
+  pr.on = enable != 0;
   return 0;
 }
 

@@ -1,15 +1,21 @@
-// 8-bit max-log-MAP turbo decoder (reference: openair1/PHY/CODING/3gpplte_turbo_decoder_sse_8bit.c),
-// first GPU version: a direct, always-saturating restatement.  int8 arithmetic saturates
-// routinely (metrics live in [-128,127]), so there is no non-saturating fast path as in the
-// 16-bit kernel; every add/sub is clamped like _mm_adds_epi8/_mm_subs_epi8.
+// 8-bit max-log-MAP turbo decoder (reference: openair1/PHY/CODING/3gpplte_turbo_decoder_sse_8bit.c).
+// int8 arithmetic saturates routinely (metrics live in [-128,127]), so there is no non-saturating
+// fast path as in the 16-bit kernel; every add/sub is clamped like _mm_adds_epi8/_mm_subs_epi8.
 //
-// Mapping: 16 threads per code block, thread l = the reference's SIMD lane l (trellis
-// positions [l*W,(l+1)*W), W = n/16, TD8:874-881); 2 blocks per warp.  alpha and beta are
-// stored for every step in HBM exactly like the reference's stack arrays (TD8:928-929), in
-// the reference layout [(step*8+state)*16 + lane] so that the 16 lanes of a block read and
-// write 16 consecutive bytes; the boundary re-seeds (TD8:299-316, 652-666) read the
-// neighbouring lane's metrics from those arrays.  Per-position arrays are int8 in the
-// reference lane layout st8(p) = (p mod W)*16 + p/W.
+// k_map8 mapping: 8 threads per code block, thread t = the reference's SIMD lanes 2t, 2t+1 (lane l covers
+// trellis positions [l*W,(l+1)*W), W = n/16, TD8:874-881) packed in the halfwords of a register, the 8 states
+// in 8 registers; 4 blocks per warp.  Metrics are kept in OFFSET form (value + 128, range 0..255) in int16
+// halfwords, so that one saturating int8 operation is one DPX instruction with the relu flag:
+//     sat8(x + g) + 128 = max(min(x' + g, 255), 0)                       (__viaddmin_s16x2_relu)
+// and, clamping being monotone, an add-compare-select max(sat8(x+g), sat8(y-g)) is
+//     clamp(max(x' + g, y' - g), 0, 255) = VIADD + VIADDMNMX + VIMNMX.relu.
+// Memory: like the 16-bit kernel, alpha is checkpointed every 8 steps in HBM during the forward sweep and
+// recomputed per 8-step segment into shared memory in the backward sweep; beta is never stored.  (The
+// reference stores both arrays for every step, TD8:928-929.)
+//
+// Data layout of the int8 per-position arrays ("C8"): chunk = 8 steps = 128 bytes,
+//     byte(k, l) = (k>>3)*128 + (l>>1)*16 + (k&7)*2 + (l&1)
+// so thread t reads the 8 steps of its two lanes with one LDG.128.
 //
 //   k_demux8 : input scaling int16 -> int8 (TD8:1000-1029) and demux (TD8:1062-1077)
 //   k_map8   : log_map8 = gamma/alpha/beta/ext (TD8:95-149, 151-827)
@@ -19,15 +25,24 @@
 // reference's output and are not read.
 #pragma once
 #include "td_common.cuh"
+#include "td16_map.cuh"
 #include "td16_xchg.cuh"
 
 namespace oai {
 
-constexpr int MAP8_THREADS = 128;     // 8 code blocks per CTA
+constexpr int MAP8_THREADS = 64;      // 8 code blocks per CTA
+constexpr int MAP8_SMEM_BYTES = 8 * MAP8_THREADS * 32;   // alpha of the 8 steps of a segment, 32 B per thread and step
 constexpr int INIT8 = -63;            // -MAX8/2 (TD8:92,234)
 constexpr int RERUN8 = 16;            // L (TD8:211)
 
 enum { A8_S0 = 0, A8_P1 = 1, A8_P2 = 2, A8_SYS = 3, A8_EXT = 4, A8_EXT2 = 5, A8_COUNT = 6 };
+
+__host__ __device__ inline int h8(int k, int lane) { return ((k >> 3) << 7) + ((lane >> 1) << 4) + ((k & 7) << 1) + (lane & 1); }
+__host__ __device__ inline int c8_bytes(int W) { return ((W + 7) >> 3) << 7; }          // bytes per array actually used
+// trellis position -> byte index (lane = pos / W, step = pos % W)
+__device__ __forceinline__ int st8(int pos, int W) { const int lane = pos / W; return h8(pos - lane * W, lane); }
+// checkpoint pool per block: one 256-byte slot (8 threads x 32 B) per 8-step segment + 4 special slots
+__host__ __device__ inline long ckpt8_words(int W) { return (long)(((W + 7) >> 3) + 4) * 64; }
 
 struct Td8Args {
   const CbMeta* meta;
@@ -35,8 +50,8 @@ struct Td8Args {
   int8_t* ws;            // per block: A8_COUNT arrays of `A` bytes
   long slot_b;
   int A;                 // bytes per array (>= n, multiple of 16)
-  int8_t* ab;            // per block: alpha then beta, each 128*(W+1) bytes
-  long ab_b;             // bytes per block in `ab`
+  u32* ck;               // alpha checkpoint pool
+  long ck_words;         // words per block in `ck`
   int nblk;
   const uint16_t* qpp;   // plain QPP tables pi[i]
   const u32* crc_xp;
@@ -80,7 +95,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux8(Td8Args p) {
   const int bracket = round_avg < 16 ? 0 : (round_avg < 32 ? 1 : (round_avg < 64 ? 2 : (round_avg < 128 ? 3 : 4)));
   int8_t* s0 = sm8, *p1 = sm8 + A, *p2 = sm8 + 2 * A;
   for (int pos = threadIdx.x; pos < n; pos += XCHG_THREADS) {
-    const int h = ((pos % W) << 4) + pos / W;
+    const int h = st8(pos, W);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int i = 3 * pos + c;
@@ -91,7 +106,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux8(Td8Args p) {
   }
   __syncthreads();
   int8_t* slot = p.ws + (long)blk * p.slot_b;
-  for (int i = threadIdx.x; i < n / 16; i += XCHG_THREADS) {
+  for (int i = threadIdx.x; i < c8_bytes(W) / 16; i += XCHG_THREADS) {
     reinterpret_cast<uint4*>(slot + (long)A8_S0 * A)[i] = reinterpret_cast<uint4*>(s0)[i];
     reinterpret_cast<uint4*>(slot + (long)A8_P1 * A)[i] = reinterpret_cast<uint4*>(p1)[i];
     reinterpret_cast<uint4*>(slot + (long)A8_P2 * A)[i] = reinterpret_cast<uint4*>(p2)[i];
@@ -103,127 +118,231 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux8(Td8Args p) {
 }
 
 // ------------------------------------------------------------------------------------
-// one trellis step of the forward recursion for one lane (TD8:251-297)
-__device__ __forceinline__ void alpha8_step(int (&a)[8], int g1, int g0) {
-  int n0 = max(s8(a[1] + g1), s8(a[0] - g1));
-  int n1 = max(s8(a[3] - g0), s8(a[2] + g0));
-  int n2 = max(s8(a[5] + g0), s8(a[4] - g0));
-  int n3 = max(s8(a[7] - g1), s8(a[6] + g1));
-  int n4 = max(s8(a[1] - g1), s8(a[0] + g1));
-  int n5 = max(s8(a[3] + g0), s8(a[2] - g0));
-  int n6 = max(s8(a[5] - g0), s8(a[4] + g0));
-  int n7 = max(s8(a[7] + g1), s8(a[6] - g1));
-  const int mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
-  a[0] = s8(n0 - mx); a[1] = s8(n1 - mx); a[2] = s8(n2 - mx); a[3] = s8(n3 - mx);
-  a[4] = s8(n4 - mx); a[5] = s8(n5 - mx); a[6] = s8(n6 - mx); a[7] = s8(n7 - mx);
+// packed (2 lanes) offset-form arithmetic
+constexpr u32 K255 = 0x00ff00ffu, K128 = 0x00800080u;
+struct G8 { u32 g1, g0, n1, n0; };      // m11, m10 and their negatives (signed halfwords)
+__device__ __forceinline__ G8 gamma8(u32 s, u32 p) {   // TD8:178-185: widen, add/sub, >>1 (exact floor halves, no saturation)
+  G8 g;
+  g.g1 = vsra1(__vadd2(s, p));
+  g.g0 = vsra1(__vsub2(s, p));
+  g.n1 = __vneg2(g.g1);
+  g.n0 = __vneg2(g.g0);
+  return g;
+}
+// clamp(max(x + gx, y + gy), 0, 255) = max(sat8(x+gx), sat8(y+gy)) in offset form
+__device__ __forceinline__ u32 acs8(u32 x, u32 gx, u32 y, u32 gy) {
+  return __vimin_s16x2_relu(__viaddmax_s16x2(x, gx, __vadd2(y, gy)), K255);
+}
+// out = sat8(n - max_s n) in offset form: max(n' - mx' + 128, 0)
+__device__ __forceinline__ void norm8(u32 (&v)[8], const u32 (&n)[8]) {
+  const u32 mx = __vmaxs2(__vimax3_s16x2(n[0], n[1], n[2]), __vimax3_s16x2(n[3], n[4], __vimax3_s16x2(n[5], n[6], n[7])));
+  const u32 c = __vsub2(K128, mx);
+#pragma unroll
+  for (int s = 0; s < 8; ++s) v[s] = __viaddmax_s16x2(n[s], c, 0u);
+}
+// forward recursion (TD8:251-297)
+__device__ __forceinline__ void alpha8_step(u32 (&a)[8], const G8& g) {
+  u32 n[8];
+  n[0] = acs8(a[1], g.g1, a[0], g.n1);
+  n[1] = acs8(a[3], g.n0, a[2], g.g0);
+  n[2] = acs8(a[5], g.g0, a[4], g.n0);
+  n[3] = acs8(a[7], g.n1, a[6], g.g1);
+  n[4] = acs8(a[1], g.n1, a[0], g.g1);
+  n[5] = acs8(a[3], g.g0, a[2], g.n0);
+  n[6] = acs8(a[5], g.n0, a[4], g.g0);
+  n[7] = acs8(a[7], g.g1, a[6], g.n1);
+  norm8(a, n);
 }
 // backward recursion (TD8:579-650)
-__device__ __forceinline__ void beta8_step(int (&b)[8], int g1, int g0) {
-  int n0 = max(s8(b[4] + g1), s8(b[0] - g1));
-  int n1 = max(s8(b[4] - g1), s8(b[0] + g1));
-  int n2 = max(s8(b[5] - g0), s8(b[1] + g0));
-  int n3 = max(s8(b[5] + g0), s8(b[1] - g0));
-  int n4 = max(s8(b[6] + g0), s8(b[2] - g0));
-  int n5 = max(s8(b[6] - g0), s8(b[2] + g0));
-  int n6 = max(s8(b[7] - g1), s8(b[3] + g1));
-  int n7 = max(s8(b[7] + g1), s8(b[3] - g1));
-  const int mx = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
-  b[0] = s8(n0 - mx); b[1] = s8(n1 - mx); b[2] = s8(n2 - mx); b[3] = s8(n3 - mx);
-  b[4] = s8(n4 - mx); b[5] = s8(n5 - mx); b[6] = s8(n6 - mx); b[7] = s8(n7 - mx);
+__device__ __forceinline__ void beta8_step(u32 (&b)[8], const G8& g) {
+  u32 n[8];
+  n[0] = acs8(b[4], g.g1, b[0], g.n1);
+  n[1] = acs8(b[4], g.n1, b[0], g.g1);
+  n[2] = acs8(b[5], g.n0, b[1], g.g0);
+  n[3] = acs8(b[5], g.g0, b[1], g.n0);
+  n[4] = acs8(b[6], g.g0, b[2], g.n0);
+  n[5] = acs8(b[6], g.n0, b[2], g.g0);
+  n[6] = acs8(b[7], g.n1, b[3], g.g1);
+  n[7] = acs8(b[7], g.g1, b[3], g.n1);
+  norm8(b, n);
+}
+// max of four saturated sums a_i (+) b_j, offset form (a signed = offset - 128, b offset)
+__device__ __forceinline__ u32 max4sum8(u32 a0, u32 b0, u32 a1, u32 b1, u32 a2, u32 b2, u32 a3, u32 b3) {
+  u32 x = __vadd2(a0, b0);
+  x = __viaddmax_s16x2(a1, b1, x);
+  x = __viaddmax_s16x2(a2, b2, x);
+  x = __viaddmax_s16x2(a3, b3, x);
+  return __vimin_s16x2_relu(x, K255);
+}
+// a-posteriori LLR of one step (TD8:715-770); a, b in offset form; returns SIGNED int8-range halfwords
+__device__ __forceinline__ u32 ext8_step(const u32 (&ao)[8], const u32 (&b)[8], const G8& g) {
+  u32 a[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) a[s] = __vsub2(ao[s], K128);
+  u32 m00 = max4sum8(a[0], b[0], a[1], b[4], a[6], b[7], a[7], b[3]);
+  u32 m11 = max4sum8(a[0], b[4], a[1], b[0], a[6], b[3], a[7], b[7]);
+  u32 m01 = max4sum8(a[2], b[5], a[3], b[1], a[4], b[2], a[5], b[6]);
+  u32 m10 = max4sum8(a[2], b[1], a[3], b[5], a[4], b[6], a[5], b[2]);
+  m01 = __viaddmin_s16x2_relu(m01, g.n0, K255);
+  m00 = __viaddmin_s16x2_relu(m00, g.n1, K255);
+  m10 = __viaddmin_s16x2_relu(m10, g.g0, K255);
+  m11 = __viaddmin_s16x2_relu(m11, g.g1, K255);
+  const u32 d = __vsub2(__vmaxs2(m10, m11), __vmaxs2(m01, m00));        // in [-255, 255]
+  return __vsub2(__viaddmin_s16x2_relu(d, K128, K255), K128);           // sat8
+}
+
+// step e (0..7) of a chunk register: two int8 -> packed sign-extended int16 pair
+__device__ __forceinline__ u32 unp8(const uint4& v, int e) {
+  const u32 w = (e >> 1) == 0 ? v.x : ((e >> 1) == 1 ? v.y : ((e >> 1) == 2 ? v.z : v.w));
+  return prmt_sx(w, (e & 1) ? 0xB3A2u : 0x9180u);
 }
 
 __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
-  const int gt = blockIdx.x * MAP8_THREADS + threadIdx.x;
-  const int blk = gt >> 4, l = gt & 15;
-  const unsigned hmask = 0xffffu << (threadIdx.x & 16);        // the 16 threads of this block
+  extern __shared__ uint4 abuf8[];
+  const int tid = threadIdx.x;
+  const int gt = blockIdx.x * MAP8_THREADS + tid;
+  const int blk = gt >> 3, t = gt & 7;
+  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);            // the 8 threads of this block
   if (blk >= p.nblk) return;
   const CbMeta m = p.meta[blk];
   const CbState* st = &p.state[blk];
   if (st->status != 0 || !(m.flags & 1) || p.iter > m.max_iter) return;
-  const int n = m.K, W = n >> 4;
-  const int8_t* slot = p.ws + (long)blk * p.slot_b;
-  const int8_t* sys = slot + (long)p.sys_arr * p.A + l;
-  const int8_t* par = slot + (long)p.par_arr * p.A + l;
-  int8_t* ext = const_cast<int8_t*>(slot) + (long)p.out_arr * p.A + l;
-  int8_t* alpha = p.ab + (long)blk * p.ab_b + l;               // element (k,s) at (k*8+s)*16
-  int8_t* beta = alpha + 128 * (W + 1);
-  auto G1 = [&](int k) { return ((int)sys[k * 16] + (int)par[k * 16]) >> 1; };   // TD8:178-185, exact halves
-  auto G0 = [&](int k) { return ((int)sys[k * 16] - (int)par[k * 16]) >> 1; };
-  int a[8], b[8];
+  const int n = m.K, W = n >> 4, nseg = (W + 7) >> 3;
+  int8_t* slot = p.ws + (long)blk * p.slot_b;
+  const uint4* sys4 = reinterpret_cast<const uint4*>(slot + (long)p.sys_arr * p.A) + t;      // chunk c at [c*8]
+  const uint4* par4 = reinterpret_cast<const uint4*>(slot + (long)p.par_arr * p.A) + t;
+  int8_t* ext = slot + (long)p.out_arr * p.A + t * 16;                                       // chunk c at + c*128
+  u32* ck = p.ck + (long)blk * p.ck_words + t * 8;                                           // slot i at + i*64
+  const int CH0 = nseg, CH8 = nseg + 1, CH16 = nseg + 2, A0 = nseg + 3;
+  auto put = [&](int e, const u32 (&a)[8]) {
+    abuf8[(2 * e) * MAP8_THREADS + tid] = make_uint4(a[0], a[1], a[2], a[3]);
+    abuf8[(2 * e + 1) * MAP8_THREADS + tid] = make_uint4(a[4], a[5], a[6], a[7]);
+  };
+  auto get = [&](int e, u32 (&a)[8]) {
+    const uint4 x = abuf8[(2 * e) * MAP8_THREADS + tid], y = abuf8[(2 * e + 1) * MAP8_THREADS + tid];
+    a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
+  };
+  auto ckput = [&](int i, const u32 (&a)[8]) { ckpt_put(ck + i * 64, a); };
+  auto ckget = [&](int i, u32 (&a)[8]) { ckpt_get(ck + i * 64, a); };
+  const u32 kInit = pack2(INIT8 + 128, INIT8 + 128);
+  u32 a[8], b[8];
 
-  // ---- alpha: init, W steps, re-seed, 16 steps, re-seed (TD8:234-316) -----------------------
+  // ---- alpha pass 1 (TD8:234-297): W steps from (0,-63..) in lane 0 and -63 elsewhere; checkpoint per segment ----
 #pragma unroll
-  for (int s = 0; s < 8; ++s) a[s] = (l == 0 && s == 0) ? 0 : INIT8;
+  for (int s = 0; s < 8; ++s) a[s] = kInit;
+  if (t == 0) a[0] = pack2(128, INIT8 + 128);
+  {
+    uint4 S = __ldg(sys4), P = __ldg(par4);
+    for (int seg = 0; seg < nseg; ++seg) {
+      ckput(seg, a);
+      const uint4 Sc = S, Pc = P;
+      if (seg + 1 < nseg) { S = __ldg(sys4 + (seg + 1) * 8); P = __ldg(par4 + (seg + 1) * 8); }
 #pragma unroll
-  for (int s = 0; s < 8; ++s) alpha[s * 16] = (int8_t)a[s];
-  for (int k = 0; k < W; ++k) {
-    alpha8_step(a, G1(k), G0(k));
-#pragma unroll
-    for (int s = 0; s < 8; ++s) alpha[((k + 1) * 8 + s) * 16] = (int8_t)a[s];
+      for (int e = 0; e < 8; ++e)
+        if (seg * 8 + e < W) alpha8_step(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+    }
   }
-  for (int pass = 0; pass < 2; ++pass) {
-    // re-seed: lane l <- alpha[W] of lane l-1, lane 0 <- (0,-63,...): `a` holds this lane's alpha[W]
-    int seed[8];
+  // ---- re-seed (TD8:299-316): lane l <- alpha[W] of lane l-1, lane 0 <- (0,-63..); 16-step re-run ----
+  auto shift_up = [&](u32 (&dst)[8], const u32 (&src)[8]) {
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-      const int prev = __shfl_up_sync(hmask, a[s], 1, 16);
-      seed[s] = (l == 0) ? (s == 0 ? 0 : INIT8) : prev;
-      alpha[s * 16] = (int8_t)seed[s];
+      u32 prev = __shfl_sync(gmask, src[s], (t + 7) & 7, 8);
+      if (t == 0) prev = pack2(0, (s == 0) ? 128 : INIT8 + 128);     // hi half is what gets used
+      dst[s] = __byte_perm(prev, src[s], 0x5432);                     // lo <- prev.hi, hi <- mine.lo
     }
-    if (pass == 1) break;
+  };
+  {
+    u32 c[8];
+    shift_up(c, a);
+    ckput(CH0, c);
+    const uint4 S0 = __ldg(sys4), P0 = __ldg(par4), S1 = __ldg(sys4 + 8), P1 = __ldg(par4 + 8);
 #pragma unroll
-    for (int s = 0; s < 8; ++s) b[s] = seed[s];                 // b: scratch for the re-run chain
-    for (int k = 0; k < RERUN8; ++k) {
-      alpha8_step(b, G1(k), G0(k));
+    for (int e = 0; e < 8; ++e) alpha8_step(c, gamma8(unp8(S0, e), unp8(P0, e)));
+    ckput(CH8, c);
 #pragma unroll
-      for (int s = 0; s < 8; ++s) alpha[((k + 1) * 8 + s) * 16] = (int8_t)b[s];
+    for (int e = 0; e < 8; ++e) alpha8_step(c, gamma8(unp8(S1, e), unp8(P1, e)));
+    ckput(CH16, c);
+    if (W == RERUN8) {                          // the re-run reached alpha[W] (K = 256): it is the new final vector
+#pragma unroll
+      for (int s = 0; s < 8; ++s) a[s] = c[s];
     }
-    if (W == RERUN8) {                                          // the re-run reached alpha[W] (K=256)
-#pragma unroll
-      for (int s = 0; s < 8; ++s) a[s] = b[s];
-    }
+    shift_up(c, a);                             // second re-seed: the final alpha[0]
+    ckput(A0, c);
   }
 
-  // ---- beta: from alpha[W]; lane 15 <- 0 before each pass; shift re-seed after each (TD8:505-666) ----
+  // alpha[k0 .. k1) of segment `seg` (final values) -> shared memory entries 0..; leaves the chunk inputs in S, P
+  uint4 S, P;
+  auto fill_alpha = [&](int seg) {
+    const int k0 = seg * 8;
+    S = __ldg(sys4 + seg * 8); P = __ldg(par4 + seg * 8);
+    u32 x[8];
+    ckget(seg == 0 ? CH0 : (seg == 1 ? CH8 : seg), x);          // steps 1..16 come from the re-run chain
 #pragma unroll
-  for (int s = 0; s < 8; ++s) b[s] = (l == 15) ? 0 : a[s];
-  int b0[8];                                                    // beta[0] of the latest pass that reached step 0
-  for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-    for (int s = 0; s < 8; ++s) beta[(W * 8 + s) * 16] = (int8_t)b[s];
-    const int kend = (pass == 0) ? 0 : W - RERUN8;
-    for (int k = W - 1; k >= kend; --k) {
-      beta8_step(b, G1(k), G0(k));
-#pragma unroll
-      for (int s = 0; s < 8; ++s) beta[(k * 8 + s) * 16] = (int8_t)b[s];
+    for (int e = 0; e < 8; ++e) {
+      if (k0 + e < W) {
+        put(e, x);
+        if (e < 7) alpha8_step(x, gamma8(unp8(S, e), unp8(P, e)));
+      }
     }
-    if (kend == 0) {
+    if (seg == 0) { ckget(A0, x); put(0, x); }                  // alpha[0]: the value of the second re-seed
+    if (seg == 2) { ckget(CH16, x); put(0, x); }                // alpha[16]: last value of the chain
+  };
+  // backward over one segment with beta[k1] in b: ext for k in [elo, ehi], beta steps for k >= blo
+  auto back_segment = [&](int seg, int elo, int ehi, int blo) {
+    const int k0 = seg * 8;
+    fill_alpha(seg);
+    u32 o[8];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) b0[s] = b[s];
+    for (int e = 7; e >= 0; --e) {
+      o[e] = 0;
+      const int k = k0 + e;
+      if (k < W) {
+        const G8 g = gamma8(unp8(S, e), unp8(P, e));
+        if (k >= elo && k <= ehi) {
+          u32 x[8];
+          get(e, x);
+          o[e] = ext8_step(x, b, g);
+        }
+        if (k >= blo) beta8_step(b, g);
+      }
     }
-    // re-seed beta[W]: lane l <- beta[0] of lane l+1, lane 15 <- 0
+    int8_t* dst = ext + seg * 128;
+    if (k0 >= elo && k0 + 7 <= ehi && k0 + 7 < W) {             // whole segment: one 16-byte store
+      *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420),
+                                                  __byte_perm(o[4], o[5], 0x6420), __byte_perm(o[6], o[7], 0x6420));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        if (k < W && k >= elo && k <= ehi) *reinterpret_cast<uint16_t*>(dst + 2 * e) = (uint16_t)__byte_perm(o[e], 0, 0x4420);
+      }
+    }
+  };
+
+  // ---- beta pass 1 (TD8:505-650): from alpha[W], lane 15 <- 0; all W steps; ext where beta[k+1] is final ----
+#pragma unroll
+  for (int s = 0; s < 8; ++s) b[s] = (t == 7) ? ((a[s] & 0xffffu) | (128u << 16)) : a[s];
+  for (int seg = nseg - 1; seg >= 0; --seg) back_segment(seg, 0, W - RERUN8 - 2, 0);
+  // ---- re-seed (TD8:652-666): lane l <- beta[0] of lane l+1, lane 15 <- 0; re-run of the last 16 steps ----
+  auto shift_down = [&](u32 (&dst)[8], const u32 (&src)[8]) {
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-      const int next = __shfl_down_sync(hmask, b0[s], 1, 16);
-      b[s] = (l == 15) ? 0 : next;
+      u32 next = __shfl_sync(gmask, src[s], (t + 1) & 7, 8);
+      if (t == 7) next = 128u;                                        // lo half is what gets used
+      dst[s] = __byte_perm(src[s], next, 0x5432);                     // lo <- mine.hi, hi <- next.lo
     }
-  }
+  };
+  u32 bw[8];                                    // beta[W] after the first re-seed
+  shift_down(bw, b);
 #pragma unroll
-  for (int s = 0; s < 8; ++s) beta[(W * 8 + s) * 16] = (int8_t)b[s];
-  __syncwarp(hmask);
-
-  // ---- ext (TD8:715-770): alpha[k], beta[k+1]; each lane reads back only its own column ----
-  for (int k = 0; k < W; ++k) {
+  for (int s = 0; s < 8; ++s) b[s] = bw[s];
+  const int klo = max(W - RERUN8 - 1, 0);       // ext(W-2 .. W-17) uses the re-run's beta[W-1 .. W-16]
+  for (int seg = nseg - 1; seg >= 0 && seg * 8 + 7 >= klo; --seg) back_segment(seg, klo, W - 2, W - RERUN8);
+  // ---- ext(W-1) uses beta[W] of the SECOND re-seed: the same vector unless the re-run reached step 0 (K = 256) ----
+  if (W == RERUN8) shift_down(bw, b);
 #pragma unroll
-    for (int s = 0; s < 8; ++s) { a[s] = alpha[(k * 8 + s) * 16]; b[s] = beta[((k + 1) * 8 + s) * 16]; }
-    const int g1 = G1(k), g0 = G0(k);
-    int m00 = max(max(s8(a[0] + b[0]), s8(a[1] + b[4])), max(s8(a[6] + b[7]), s8(a[7] + b[3])));
-    int m11 = max(max(s8(a[0] + b[4]), s8(a[1] + b[0])), max(s8(a[6] + b[3]), s8(a[7] + b[7])));
-    int m01 = max(max(s8(a[2] + b[5]), s8(a[3] + b[1])), max(s8(a[4] + b[2]), s8(a[5] + b[6])));
-    int m10 = max(max(s8(a[2] + b[1]), s8(a[3] + b[5])), max(s8(a[4] + b[6]), s8(a[5] + b[2])));
-    m01 = s8(m01 - g0); m00 = s8(m00 - g1); m10 = s8(m10 + g0); m11 = s8(m11 + g1);
-    ext[k * 16] = (int8_t)s8(max(m10, m11) - max(m01, m00));
-  }
+  for (int s = 0; s < 8; ++s) b[s] = bw[s];
+  back_segment(nseg - 1, W - 1, W - 1, W);
 }
 
 // ------------------------------------------------------------------------------------
@@ -237,7 +356,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_8(Td8Args p) {
   int8_t* slot = p.ws + (long)blk * p.slot_b;
   int8_t* gext = slot + (long)A8_EXT * A, *gsys = slot + (long)A8_SYS * A;
   const int8_t* gs0 = slot + (long)A8_S0 * A;
-  for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {
+  const int An = c8_bytes(W);          // elementwise work covers the padded extent (holes of a partial last chunk are never used)
+  for (int i = threadIdx.x; i < An; i += XCHG_THREADS) {
     int e = gext[i];
     if (p.iter > 1) {                 // ext = (ext (-) s1) (+) s0, TD8:1632-1653
       e = s8(s8(e - gsys[i]) + gs0[i]);
@@ -249,7 +369,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_8(Td8Args p) {
   const uint16_t* pi = p.qpp + m.pi_off;
   for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {         // s2[st8(i)] = ext[st8(pi(i))], TD8:1341-1379
     const int j = pi[i];
-    gsys[((i % W) << 4) + i / W] = sm8[((j % W) << 4) + j / W];
+    gsys[st8(i, W)] = sm8[st8(j, W)];
   }
 }
 
@@ -268,7 +388,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
   int8_t* gsys = slot + (long)A8_SYS * A;
   int8_t* e2 = sm8, *dec = sm8 + A;           // ext2 (interleaved order); decision variable (same order)
   const bool mode1 = (n & 0x7f) == 0;         // TD8:1392 / 1488
-  for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {
+  const int An = c8_bytes(W);
+  for (int i = threadIdx.x; i < An; i += XCHG_THREADS) {
     const int v = gext2[i];
     e2[i] = (int8_t)v;
     dec[i] = (int8_t)(mode1 ? v : s8(v + gsys[i]));             // ext2 (+) sys2, TD8:1456
@@ -277,7 +398,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
   const uint16_t* pi = p.qpp + m.pi_off;
   for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {         // s1 = (ext2 o pi^-1 (-) ext) (+) s0, TD8:1392-1459
     const int pj = pi[i];
-    const int j = ((pj % W) << 4) + pj / W, hi = ((i % W) << 4) + i / W;
+    const int j = st8(pj, W), hi = st8(i, W);
     gsys[j] = (int8_t)s8(s8((int)e2[hi] - gext[j]) + gs0[j]);
   }
   bool pass = false;
@@ -287,7 +408,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
     // inverse permutation -- obtained by scattering the decision variable to natural order first
     int8_t* natdec = e2;                       // reuse (e2 no longer needed after the barrier below)
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += XCHG_THREADS) natdec[pi[i]] = dec[((i % W) << 4) + i / W];
+    for (int i = threadIdx.x; i < n; i += XCHG_THREADS) natdec[pi[i]] = dec[st8(i, W)];
     __syncthreads();
     u32 word = 0;                              // thread w packs natural positions 32w..32w+31, MSB first
     if ((int)threadIdx.x < ((n >> 3) + 3) >> 2) {
