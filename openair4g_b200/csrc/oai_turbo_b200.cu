@@ -66,6 +66,8 @@ struct DevCtx {
   uint32_t pi_off[188], t_off[188];
   uint16_t* qpp_pool = nullptr;       // plain QPP tables pi[i] (8-bit decoder kernels)
   uint32_t qpp_off[188];
+  uint16_t* t8_pool = nullptr;        // 8-bit decoder: T8 tables (C8 byte index -> C8 byte index of the QPP image)
+  uint32_t t8_off[188];
   u32* crc_xp = nullptr;              // [4][32][CRC_NM] powers of x mod the CRC polynomials
   bool ok = false;
 };
@@ -87,7 +89,7 @@ static int ctx_get(int dev, DevCtx** out) {
     int prev = 0;
     CU(cudaGetDevice(&prev));
     CU(cudaSetDevice(dev));
-    std::vector<uint16_t> pool, tpool, qpool;
+    std::vector<uint16_t> pool, tpool, qpool, t8pool;
     for (int i = 0; i < 188; ++i) {
       const int K = qpp_K(i), W = K / 8, A = c4_words(W) * 2;
       c.pi_off[i] = (uint32_t)pool.size();
@@ -102,6 +104,17 @@ static int ctx_get(int dev, DevCtx** out) {
         T[H[j]] = H[pj];
         qpool.push_back((uint16_t)pj);
       }
+      c.t8_off[i] = (uint32_t)t8pool.size();
+      if (K >= 256 && (K & 15) == 0) {                                       // the 8-bit decoder's domain
+        const int W8 = K / 16, A8 = c8_bytes(W8);
+        std::vector<uint16_t> T8(A8);
+        for (int h = 0; h < A8; ++h) T8[h] = (uint16_t)h;
+        for (uint64_t j = 0; j < (uint64_t)K; ++j) {
+          const uint64_t pj = (f1 * j + f2 * j * j) % (uint64_t)K;
+          T8[h8((int)(j % W8), (int)(j / W8))] = (uint16_t)h8((int)(pj % W8), (int)(pj / W8));
+        }
+        t8pool.insert(t8pool.end(), T8.begin(), T8.end());                   // A8 is a multiple of 128
+      }
       pool.insert(pool.end(), H.begin(), H.end());
       while (pool.size() & 7) pool.push_back(0);
       tpool.insert(tpool.end(), T.begin(), T.end());                         // A is a multiple of 32
@@ -110,6 +123,8 @@ static int ctx_get(int dev, DevCtx** out) {
     CU(cudaMemcpy(c.pi_pool, pool.data(), pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.qpp_pool, qpool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.qpp_pool, qpool.data(), qpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c.t8_pool, t8pool.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(c.t8_pool, t8pool.data(), t8pool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c.t_pool, tpool.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(c.t_pool, tpool.data(), tpool.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     // powers of x modulo the four CRC polynomials (crc_byte.c:53-57): entry [t][r][m] = x^(w + r + 32 m) mod P,
@@ -307,7 +322,7 @@ struct Batch8 {
     int launches = 0;
     Td8Args a;
     a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ck = d_ck; a.ck_words = ck_words;
-    a.nblk = n; a.qpp = ctx->qpp_pool; a.crc_xp = ctx->crc_xp; a.in_base = in_dev; a.out_base = out_dev;
+    a.nblk = n; a.qpp = ctx->qpp_pool; a.t8 = ctx->t8_pool; a.crc_xp = ctx->crc_xp; a.in_base = in_dev; a.out_base = out_dev;
     a.status_out = status_dev; a.iter = 0; a.sys_arr = a.par_arr = a.out_arr = 0;
     const int map_grid = (n * 8 + MAP8_THREADS - 1) / MAP8_THREADS;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int iter) {
@@ -350,7 +365,7 @@ static int make_meta(DevCtx* c, int K, int max_it, int crc, int F, int dec, long
   m->K = (uint16_t)K; m->W = (uint16_t)(K >> 3);
   m->max_iter = (uint8_t)max_it; m->crc_type = (uint8_t)crc; m->F = (uint8_t)F; m->flags = dec ? 1 : 0;
   m->pi_off = llr8 ? c->qpp_off[idx] : c->pi_off[idx];
-  m->t_off = c->t_off[idx];
+  m->t_off = llr8 ? c->t8_off[idx] : c->t_off[idx];
   m->in_off_lo = (uint32_t)((unsigned long long)in_off & 0xffffffffu);
   m->in_off_hi = (uint32_t)((unsigned long long)in_off >> 32);
   m->out_off = (uint32_t)out_off;

@@ -54,6 +54,7 @@ struct Td8Args {
   long ck_words;         // words per block in `ck`
   int nblk;
   const uint16_t* qpp;   // plain QPP tables pi[i]
+  const uint16_t* t8;    // per K: T8[h] = C8 byte index of the QPP image of the position stored at byte h (padding: itself)
   const u32* crc_xp;
   const int16_t* in_base;
   uint8_t* out_base;
@@ -346,6 +347,8 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
 }
 
 // ------------------------------------------------------------------------------------
+// Exchange kernels: one CTA per block, arrays staged in shared memory, 128-bit HBM accesses, the QPP
+// permutation as a byte gather / scatter through the T8 table (CbMeta::t_off).
 __global__ void __launch_bounds__(XCHG_THREADS) k_x1_8(Td8Args p) {
   extern __shared__ int8_t sm8[];
   const int blk = blockIdx.x;
@@ -354,29 +357,50 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_8(Td8Args p) {
   if (p.state[blk].status != 0 || p.iter > m.max_iter) return;
   const int n = m.K, W = n >> 4, A = p.A;
   int8_t* slot = p.ws + (long)blk * p.slot_b;
-  int8_t* gext = slot + (long)A8_EXT * A, *gsys = slot + (long)A8_SYS * A;
-  const int8_t* gs0 = slot + (long)A8_S0 * A;
-  const int An = c8_bytes(W);          // elementwise work covers the padded extent (holes of a partial last chunk are never used)
-  for (int i = threadIdx.x; i < An; i += XCHG_THREADS) {
-    int e = gext[i];
-    if (p.iter > 1) {                 // ext = (ext (-) s1) (+) s0, TD8:1632-1653
-      e = s8(s8(e - gsys[i]) + gs0[i]);
-      gext[i] = (int8_t)e;
+  uint4* gext = reinterpret_cast<uint4*>(slot + (long)A8_EXT * A);
+  const uint4* gsys4 = reinterpret_cast<const uint4*>(slot + (long)A8_SYS * A);
+  const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)A8_S0 * A);
+  const int n16 = c8_bytes(W) >> 4;     // elementwise work covers the padded extent (holes of a partial last chunk are never used)
+  for (int i = threadIdx.x; i < n16; i += XCHG_THREADS) {
+    uint4 e = gext[i];
+    if (p.iter > 1) {                   // ext = (ext (-) s1) (+) s0, TD8:1632-1653
+      const uint4 s1 = gsys4[i], z = gs0[i];
+      e.x = __vaddss4(__vsubss4(e.x, s1.x), z.x); e.y = __vaddss4(__vsubss4(e.y, s1.y), z.y);
+      e.z = __vaddss4(__vsubss4(e.z, s1.z), z.z); e.w = __vaddss4(__vsubss4(e.w, s1.w), z.w);
+      gext[i] = e;
     }
-    sm8[i] = (int8_t)e;
+    reinterpret_cast<uint4*>(sm8)[i] = e;
   }
   __syncthreads();
-  const uint16_t* pi = p.qpp + m.pi_off;
-  for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {         // s2[st8(i)] = ext[st8(pi(i))], TD8:1341-1379
-    const int j = pi[i];
-    gsys[st8(i, W)] = sm8[st8(j, W)];
+  const uint4* T4 = reinterpret_cast<const uint4*>(p.t8 + m.t_off);
+  uint2* gsys = reinterpret_cast<uint2*>(slot + (long)A8_SYS * A);
+  const uint8_t* in = reinterpret_cast<const uint8_t*>(sm8);
+  for (int i = threadIdx.x; i < 2 * n16; i += XCHG_THREADS) {   // s2[st8(i)] = ext[st8(pi(i))], TD8:1341-1379; 8 bytes per thread
+    const uint4 tt = __ldg(T4 + i);
+    uint2 o;
+    o.x = (u32)in[tt.x & 0xffffu] | ((u32)in[tt.x >> 16] << 8) | ((u32)in[tt.y & 0xffffu] << 16) | ((u32)in[tt.y >> 16] << 24);
+    o.y = (u32)in[tt.z & 0xffffu] | ((u32)in[tt.z >> 16] << 8) | ((u32)in[tt.w & 0xffffu] << 16) | ((u32)in[tt.w >> 16] << 24);
+    gsys[i] = o;
   }
+}
+
+// the four 4-position hard-decision groups of one C8 uint4 (8 steps x lanes 2t, 2t+1 of int8): byte > 0;
+// returns lane 2t steps 0-3 in bits 0..3, steps 4-7 in bits 4..7, lane 2t+1 in bits 8..15 (first step = bit 3 of its nibble)
+__device__ __forceinline__ u32 hd_nibbles8(const uint4& d) {
+  const u32 m0 = __vcmpgts4(d.x, 0u) & 0x01010101u, m1 = __vcmpgts4(d.y, 0u) & 0x01010101u;
+  const u32 m2 = __vcmpgts4(d.z, 0u) & 0x01010101u, m3 = __vcmpgts4(d.w, 0u) & 0x01010101u;
+  // word q holds steps 2q (bytes 0,1 = lanes 2t, 2t+1) and 2q+1 (bytes 2,3)
+  auto lane_bits = [](u32 m, int sh) -> u32 { const u32 x = m >> sh; return ((x & 1u) << 1) | ((x >> 16) & 1u); };   // (step 2q, step 2q+1)
+  const u32 l0 = (lane_bits(m0, 0) << 2) | lane_bits(m1, 0) | (((lane_bits(m2, 0) << 2) | lane_bits(m3, 0)) << 4);
+  const u32 l1 = (lane_bits(m0, 8) << 2) | lane_bits(m1, 8) | (((lane_bits(m2, 8) << 2) | lane_bits(m3, 8)) << 4);
+  return l0 | (l1 << 8);
 }
 
 __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
   extern __shared__ int8_t sm8[];
   __shared__ u32 xred[2 * XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
+  __shared__ __align__(16) uint8_t snib[1536 + 16];
   const int blk = blockIdx.x;
   if (blk >= p.nblk) return;
   const CbMeta m = p.meta[blk];
@@ -384,38 +408,72 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
   if (st->status != 0 || p.iter > m.max_iter) return;
   const int n = m.K, W = n >> 4, A = p.A;
   int8_t* slot = p.ws + (long)blk * p.slot_b;
-  const int8_t* gext2 = slot + (long)A8_EXT2 * A, *gext = slot + (long)A8_EXT * A, *gs0 = slot + (long)A8_S0 * A;
-  int8_t* gsys = slot + (long)A8_SYS * A;
-  int8_t* e2 = sm8, *dec = sm8 + A;           // ext2 (interleaved order); decision variable (same order)
-  const bool mode1 = (n & 0x7f) == 0;         // TD8:1392 / 1488
-  const int An = c8_bytes(W);
-  for (int i = threadIdx.x; i < An; i += XCHG_THREADS) {
-    const int v = gext2[i];
-    e2[i] = (int8_t)v;
-    dec[i] = (int8_t)(mode1 ? v : s8(v + gsys[i]));             // ext2 (+) sys2, TD8:1456
+  const uint2* gext2 = reinterpret_cast<const uint2*>(slot + (long)A8_EXT2 * A);
+  const uint2* gsys2 = reinterpret_cast<const uint2*>(slot + (long)A8_SYS * A);
+  const uint4* gext = reinterpret_cast<const uint4*>(slot + (long)A8_EXT * A);
+  const uint4* gs0 = reinterpret_cast<const uint4*>(slot + (long)A8_S0 * A);
+  uint4* gsys = reinterpret_cast<uint4*>(slot + (long)A8_SYS * A);
+  int8_t* nat = sm8, *natdec = sm8 + A;       // ext2 and the decision variable, both in natural order (C8 layout)
+  const bool mode1 = (n & 0x7f) == 0;         // TD8:1392 / 1488: decide on ext2, else on ext2 (+) sys2 (TD8:1456)
+  const bool hd = p.iter > 1;
+  const int n16 = c8_bytes(W) >> 4;
+  const uint4* T4 = reinterpret_cast<const uint4*>(p.t8 + m.t_off);
+  for (int i = threadIdx.x; i < 2 * n16; i += XCHG_THREADS) {   // scatter to natural order, 8 bytes per thread
+    const uint2 v = gext2[i];
+    const uint4 tt = __ldg(T4 + i);
+    const u32 tw[4] = {tt.x, tt.y, tt.z, tt.w};
+    const u32 vw[2] = {v.x, v.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      nat[tw[q] & 0xffffu] = (int8_t)(vw[q >> 1] >> (16 * (q & 1)));
+      nat[tw[q] >> 16] = (int8_t)(vw[q >> 1] >> (16 * (q & 1) + 8));
+    }
+    if (hd && !mode1) {
+      const uint2 s2 = gsys2[i];
+      const u32 dw[2] = {__vaddss4(v.x, s2.x), __vaddss4(v.y, s2.y)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        natdec[tw[q] & 0xffffu] = (int8_t)(dw[q >> 1] >> (16 * (q & 1)));
+        natdec[tw[q] >> 16] = (int8_t)(dw[q >> 1] >> (16 * (q & 1) + 8));
+      }
+    }
   }
   __syncthreads();
-  const uint16_t* pi = p.qpp + m.pi_off;
-  for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {         // s1 = (ext2 o pi^-1 (-) ext) (+) s0, TD8:1392-1459
-    const int pj = pi[i];
-    const int j = st8(pj, W), hi = st8(i, W);
-    gsys[j] = (int8_t)s8(s8((int)e2[hi] - gext[j]) + gs0[j]);
+  const int8_t* decv = mode1 ? nat : natdec;
+  const bool hd4 = hd && ((W & 3) == 0);
+  const int Wq = W >> 2;
+  for (int i = threadIdx.x; i < n16; i += XCHG_THREADS) {       // s1 = (ext2 o pi^-1 (-) ext) (+) s0, TD8:1392-1459
+    const uint4 d = reinterpret_cast<const uint4*>(nat)[i], e = gext[i], z = gs0[i];
+    uint4 r;
+    r.x = __vaddss4(__vsubss4(d.x, e.x), z.x); r.y = __vaddss4(__vsubss4(d.y, e.y), z.y);
+    r.z = __vaddss4(__vsubss4(d.z, e.z), z.z); r.w = __vaddss4(__vsubss4(d.w, e.w), z.w);
+    gsys[i] = r;
+    if (hd4) {                                                  // park the four 4-position decision groups of this uint4
+      const u32 nb4 = hd_nibbles8(mode1 ? d : reinterpret_cast<const uint4*>(natdec)[i]);
+      const int c = i >> 3, l0 = (i & 7) << 1;
+      const int n0 = l0 * Wq + 2 * c, n1 = (l0 + 1) * Wq + 2 * c;
+      snib[n0 ^ 7] = (uint8_t)(nb4 & 15u);
+      snib[n1 ^ 7] = (uint8_t)((nb4 >> 8) & 15u);
+      if (8 * c + 4 < W) {                                      // steps 4..7 of a partial last chunk do not exist
+        snib[(n0 + 1) ^ 7] = (uint8_t)((nb4 >> 4) & 15u);
+        snib[(n1 + 1) ^ 7] = (uint8_t)((nb4 >> 12) & 15u);
+      }
+    }
   }
   bool pass = false;
-  if (p.iter > 1) {
-    // hard decision at natural position pi(i): written bit by bit through shared-memory atomics
-    // would be slow; instead each warp ballots 32 consecutive NATURAL positions, which needs the
-    // inverse permutation -- obtained by scattering the decision variable to natural order first
-    int8_t* natdec = e2;                       // reuse (e2 no longer needed after the barrier below)
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += XCHG_THREADS) natdec[pi[i]] = dec[st8(i, W)];
-    __syncthreads();
-    u32 word = 0;                              // thread w packs natural positions 32w..32w+31, MSB first
+  if (hd) {
+    if (hd4) __syncthreads();
+    u32 word = 0;                              // thread w packs natural positions 32w..32w+31, first position in bit 31
     if ((int)threadIdx.x < ((n >> 3) + 3) >> 2) {
-      const int j0 = threadIdx.x << 5;
-      u32 bits = 0;
-      for (int q = 0; q < 32; ++q) bits = (bits << 1) | ((j0 + q < n && natdec[j0 + q] > 0) ? 1u : 0u);
-      word = bits;
+      if (hd4) word = nibbles_to_word(reinterpret_cast<const uint2*>(snib)[threadIdx.x]);
+      else {
+        const int j0 = threadIdx.x << 5;
+        int lane = j0 / W, k = j0 - lane * W;
+        for (int q = 0; q < 32; ++q) {
+          word = (word << 1) | ((j0 + q < n && decv[h8(k, lane)] > 0) ? 1u : 0u);
+          if (++k >= W) { k = 0; ++lane; }
+        }
+      }
     }
     pass = block_crc_check(word, sbytes, p.out_base + m.out_off, m, p.crc_xp, xred);
   }
