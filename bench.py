@@ -137,6 +137,19 @@ def cpu_decode_rate(y_blocks, total_blocks, threads):
     return total_blocks * K_BITS / dt / 1e6, kind, dt, results
 
 
+def coded_inputs(K, nd, sigma_over_A, seed, A=8):
+    """nd distinct code blocks (random payload + CRC24B, 36.212 turbo code, BPSK LLR = A(2b-1) + sigma N(0,1), SURVEY 8d
+    config 3) from the product's own TX chain (openair4g_b200/sim/txchain.py)."""
+    import numpy as np
+    from openair4g_b200.sim import txchain
+    rng = np.random.default_rng(seed)
+    payload = rng.integers(0, 2, size=(nd, K - 24)).astype(np.uint8)
+    c = np.concatenate([payload, txchain.crc24b(payload)], axis=1)
+    bits = txchain.turbo_encode(c).astype(np.int64)
+    y = A * (2 * bits - 1) + np.rint(sigma_over_A * A * rng.standard_normal(bits.shape)).astype(np.int64)
+    return np.clip(y, -32768, 32767).astype(np.int16), np.packbits(c, axis=1)
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -267,6 +280,40 @@ def run_b200(args):
     if not same:
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
 
+    # ---- side measurement: early-exit regimes of config 3 (device-resident, same plan, same timing rules) ----
+    regimes = None
+    if world == 1 and not args.no_regimes:
+        regimes = {}
+        for name, sig in (("clean", 0.5), ("waterfall", 1.08)):
+            nd = 64
+            ys, info = coded_inputs(K, nd, sig, 4242)
+            idx = (torch.arange(B, device="cuda") * 29) % nd
+            y_r = torch.from_numpy(ys).cuda()[idx].contiguous()
+            out_r = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
+            st_r = torch.zeros(B, dtype=torch.uint8, device="cuda")
+
+            def step_r():
+                return plan.decode(y_r.data_ptr(), row, out_r.data_ptr(), K // 8, st_r.data_ptr(), stream)
+            for _ in range(3):
+                step_r()
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(args.steps):
+                step_r()
+            r1.record()
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1)
+            hist = torch.bincount(st_r.long(), minlength=MAX_ITER + 2).tolist()
+            ok_mask = (st_r <= MAX_ITER).cpu().numpy()
+            good = bool((out_r.cpu().numpy()[ok_mask] == info[idx.cpu().numpy()][ok_mask]).all())
+            regimes[name] = {"value": B * K * args.steps / (rms * 1e-3) / 1e6, "unit": "Mbit/s", "sigma_over_A": sig,
+                             "return_value_histogram": {str(i): h for i, h in enumerate(hist) if h},
+                             "mean_iterations": float(sum(min(i, MAX_ITER) * h for i, h in enumerate(hist)) / max(sum(hist), 1)),
+                             "crc_passing_blocks_equal_transmitted_bytes": good,
+                             "distinct_blocks": nd}
+            del y_r, out_r, st_r
+
     # final result gather (outside every timed region): per-rank block / bit / status counts
     from openair4g_b200 import sharding
     recs = sharding.gather_results(st_dev, B * K, dist)
@@ -342,7 +389,7 @@ def run_b200(args):
                              % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6),
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
                        "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
-            "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu,
+            "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
                     "api": "oai_turbo_submit_batch + oai_turbo_wait per step, page-locked host input and output buffers; "
@@ -397,6 +444,7 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=262144,
                     help="bounded CPU-baseline sample (blocks): ~4 s of wall time on 16 host threads (~60 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the clean / waterfall side measurements")
     ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
     ap.add_argument("--K", type=int, default=K_BITS, help="block size for --llr8 / side measurements")
     args = ap.parse_args()
