@@ -197,6 +197,8 @@ struct Batch {
   int16_t* d_ws = nullptr;
   u32* d_ckpt = nullptr;
   int* d_batch_max = nullptr;
+  int* d_active = nullptr;     // compacted indices of the running blocks (per pipeline part: relative to the part)
+  int* d_nactive = nullptr;    // one counter per part
   std::vector<CbMeta> h_meta;
 
   int alloc(DevCtx* c, int ncb, int Kmax) {
@@ -211,13 +213,15 @@ struct Batch {
     CU(cudaMalloc(&d_ws, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
     CU(cudaMalloc(&d_batch_max, sizeof(int) * MAX_PARTS));
+    CU(cudaMalloc(&d_active, sizeof(int) * ncb * 2));            // two lists (current / next)
+    CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 2));
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     return 0;
   }
   void release() {
-    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt); cudaFree(d_batch_max);
-    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr; d_batch_max = nullptr;
+    cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt); cudaFree(d_batch_max); cudaFree(d_active); cudaFree(d_nactive);
+    d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr; d_batch_max = nullptr; d_active = nullptr; d_nactive = nullptr;
   }
   int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
     h_meta = m;
@@ -239,15 +243,26 @@ struct Batch {
     int16_t* d_ws = this->d_ws + (long)lo * slot_hw;
     u32* d_ckpt = this->d_ckpt + (long)lo * ckpt_words;
     int* d_batch_max = this->d_batch_max + part;
+    int* act[2] = {this->d_active + lo, this->d_active + cap + lo};      // packed lists of running blocks
+    int* nact[2] = {this->d_nactive + 2 * part, this->d_nactive + 2 * part + 1};
+    int cur = 0;
     if (status_dev) status_dev += lo;
     XchgArgs x;
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
+    x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
+    cudaMemsetAsync(nact[0], 0, sizeof(int), st);
     cudaMemsetAsync(d_batch_max, 0, sizeof(int), st);
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
+    // packs the running blocks into list c (its counter is zero: memset above / k_x1_16) and makes it current
+    auto compact_into = [&](int c) {
+      k_compact<<<(n + COMPACT_THREADS - 1) / COMPACT_THREADS, COMPACT_THREADS, 0, st>>>(d_state, n, act[c], nact[c]);
+      ++launches;
+      mp.active = act[c]; mp.nactive = nact[c]; x.active = act[c]; x.nactive = nact[c]; x.nactive_next = nact[1 - c];
+    };
     const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
     const size_t map_smem = MAP_SMEM_BYTES;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
@@ -261,6 +276,7 @@ struct Batch {
     k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
     prof.end(st);
     ++launches;
+    compact_into(cur);
     map(ARR_S0, ARR_P1, ARR_EXT, 0, 1, 0);                       // reference :1199
     for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
       x.iter = it;
@@ -272,7 +288,10 @@ struct Batch {
       k_x2_16<<<n, XCHG_THREADS, A * sizeof(int16_t), st>>>(x);
       prof.end(st);
       launches += 2;
-      if (it < max_iter) map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1, 1);   // :1354-1375 (feedback fused)
+      if (it < max_iter) {
+        if (it > 1) { cur = 1 - cur; compact_into(cur); }        // the CRC check (iterations >= 2) may have retired blocks
+        map(ARR_SYS, ARR_P1, ARR_EXT, 0, it + 1, 1);             // :1354-1375 (feedback fused)
+      }
     }
     g_launches += launches;
     cudaError_t e = cudaGetLastError();
@@ -423,7 +442,7 @@ struct HostBatch {
   bool direct_out = false;
   int dev = -1;
   int cap_blocks = 0, cap_K = 0;
-  size_t cap_in = 0, cap_out = 0;
+  size_t cap_in = 0, cap_out = 0, cap_h_in = 0, cap_h_out = 0;   // device buffers / pinned staging (staging only on demand)
   int16_t* h_in = nullptr;  int16_t* d_in = nullptr;
   uint8_t* h_out = nullptr; uint8_t* d_out = nullptr;
   uint8_t* h_status = nullptr; uint8_t* d_status = nullptr; int cap_status = 0;
@@ -468,16 +487,31 @@ struct HostBatch {
     }
     b.ctx = c; b8.ctx = c;
     if (in_hw > cap_in) {
-      if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); }
+      if (d_in) cudaFree(d_in);
       cap_in = in_hw;
-      CU(cudaMallocHost(&h_in, cap_in * sizeof(int16_t)));
       CU(cudaMalloc(&d_in, cap_in * sizeof(int16_t)));
     }
     if (out_bytes > cap_out) {
-      if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); }
+      if (d_out) cudaFree(d_out);
       cap_out = out_bytes;
-      CU(cudaMallocHost(&h_out, cap_out));
       CU(cudaMalloc(&d_out, cap_out));
+    }
+    return 0;
+  }
+  // pinned staging for pageable caller memory; page-locked caller memory never needs it
+  int ensure_stage_in() {
+    if (cap_h_in < cap_in) {
+      if (h_in) cudaFreeHost(h_in);
+      cap_h_in = cap_in;
+      CU(cudaMallocHost(&h_in, cap_h_in * sizeof(int16_t)));
+    }
+    return 0;
+  }
+  int ensure_stage_out() {
+    if (cap_h_out < cap_out) {
+      if (h_out) cudaFreeHost(h_out);
+      cap_h_out = cap_out;
+      CU(cudaMallocHost(&h_out, cap_h_out));
     }
     return 0;
   }
@@ -508,8 +542,11 @@ struct HostBatch {
     if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); h_w = nullptr; d_w = nullptr; }
     if (d_rm) { cudaFree(d_rm); d_rm = nullptr; }
     cap_e = cap_w = 0; cap_rm = 0;
-    if (h_in) { cudaFreeHost(h_in); cudaFree(d_in); h_in = nullptr; d_in = nullptr; }
-    if (h_out) { cudaFreeHost(h_out); cudaFree(d_out); h_out = nullptr; d_out = nullptr; }
+    if (h_in) { cudaFreeHost(h_in); h_in = nullptr; }
+    if (d_in) { cudaFree(d_in); d_in = nullptr; }
+    if (h_out) { cudaFreeHost(h_out); h_out = nullptr; }
+    if (d_out) { cudaFree(d_out); d_out = nullptr; }
+    cap_h_in = cap_h_out = 0;
     if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (st_copy) {
@@ -539,10 +576,11 @@ struct HostBatch {
     }
     // 16-bit blocks first, then 8-bit ones; equal-K blocks next to each other (a warp of the MAP
     // kernel carries 8 blocks)
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+    auto before = [&](int a, int c) {
       if ((descs[a].llr8 != 0) != (descs[c].llr8 != 0)) return descs[a].llr8 == 0;
       return descs[a].K < descs[c].K;
-    });
+    };
+    if (!std::is_sorted(order.begin(), order.end(), before)) std::stable_sort(order.begin(), order.end(), before);
     const int n = (int)order.size();
     if (n == 0) return 0;
     n16 = 0;
@@ -619,6 +657,7 @@ struct HostBatch {
         cudaGetLastError();
       }
       direct_out = ok;
+      if (!direct_out) { rc = ensure_stage_out(); if (rc) return rc; }
     }
     // Pipelined form (plain 16-bit batches that are large enough): the batch is cut into `parts` ranges of
     // blocks; the input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).
@@ -651,7 +690,11 @@ struct HostBatch {
         bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
         cudaGetLastError();
         const int16_t* src = base;
-        if (!pinned) { memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i]; }
+        if (!pinned) {
+          rc = ensure_stage_in();
+          if (rc) return rc;
+          memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i];
+        }
         CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
         i = j;
       }
@@ -996,6 +1039,8 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   size_t in_hw = ((size_t)3 * K + 12 + 7) & ~(size_t)7;
   int rc = hb.ensure(-1, 1, K, in_hw, 1024);
   if (rc) return rc;
+  rc = hb.ensure_stage_in();
+  if (rc) return rc;
   memcpy(hb.h_in, y, sizeof(int16_t) * (3 * (size_t)K + 12));
   std::vector<CbMeta> meta(1);
   make_meta(hb.b.ctx, K, 1, 1, 0, 1, 0, 0, &meta[0]);
@@ -1006,7 +1051,7 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   XchgArgs x;
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
   x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
-  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max;
+  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max; x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;
   cudaMemsetAsync(b.d_batch_max, 0, sizeof(int), hb.st);
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
   MapArgs mp;
@@ -1014,26 +1059,12 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1; mp.batch_max = (policy == 3) ? b.d_batch_max : nullptr;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
   mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1; mp.upd = 0;
+  mp.active = nullptr; mp.nactive = nullptr;
   k_map16<MAP_SEG><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
   g_launches += 2;
   std::vector<int16_t> tmp(b.A);
   CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));
   CU(cudaStreamSynchronize(hb.st));
-  if (getenv("OAI_TURBO_DEBUG_B8")) {
-    std::vector<int16_t> p1(b.A), b8(b.A);
-    cudaMemcpy(p1.data(), b.d_ws + (long)ARR_P1 * b.A, b.A * 2, cudaMemcpyDeviceToHost);
-    cudaMemcpy(b8.data(), b.d_ws + (long)ARR_B8A * b.A, b.A * 2, cudaMemcpyDeviceToHost);
-    const int8_t* q = (const int8_t*)b8.data();
-    int bad = 0, bm = -1;
-    cudaMemcpy(&bm, b.d_batch_max, 4, cudaMemcpyDeviceToHost);
-    for (int i = 0; i < b.A; ++i) if ((int)q[i] != (int)p1[i]) { if (bad < 5) fprintf(stderr, "b8 mismatch at %d: %d vs %d\n", i, q[i], p1[i]); ++bad; }
-    fprintf(stderr, "B8A check: A=%d bad=%d batch_max=%d\n", b.A, bad, bm);
-  }
-  if (getenv("OAI_TURBO_DEBUG_T")) {
-    CbState stt;
-    cudaMemcpy(&stt, b.d_state, sizeof(stt), cudaMemcpyDeviceToHost);
-    for (int q = 0; q < 2; ++q) { fprintf(stderr, "T[%d]:", q); for (int i = 0; i < 8; ++i) fprintf(stderr, " %d", stt.T[q][i]); fprintf(stderr, "  max_in %d\n", stt.max_in); }
-  }
   const int W = K / 8;
   for (int k = 0; k < W; ++k)
     for (int l = 0; l < 8; ++l) ext_out[k * 8 + l] = tmp[c4_hw(k, l)];

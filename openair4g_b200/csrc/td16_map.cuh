@@ -58,6 +58,8 @@ struct MapArgs {
   int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
   const int* batch_max;  // max |y| over the batch: <= 127 selects the int8 parity / s0 copies
   int upd;               // 1: write ext = (ext (-) sys) (+) s0 (the feedback step, reference :1354-1375)
+  const int* active;     // compacted list of running blocks (k_compact) or nullptr = all nblk blocks
+  const int* nactive;
 };
 
 template <class AR>
@@ -280,14 +282,8 @@ struct FC { u32 X, Y, Z; };
 #ifndef MAP_CACHE_HINTS
 #define MAP_CACHE_HINTS 0
 #endif
-// L2 policy hints: the forward sweep's LAST reads are the backward sweep's FIRST reads, so the
-// tail of the forward stream is kept (evict_last) and everything that is not reused soon streams
-// through (evict_first): the backward sweep's reads and the ext output.
-__device__ __forceinline__ unsigned long long l2_policy_keep() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
+// Optional L2 evict_first hints for data that is not reused soon (the backward sweep's reads, the ext
+// output); measured neutral to slightly negative, off by default.
 __device__ __forceinline__ unsigned long long l2_policy_stream() {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -714,8 +710,10 @@ __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   extern __shared__ uint4 abuf[];
   const int tid = threadIdx.x;
   const int gt = blockIdx.x * MAP_THREADS + tid;
-  const int blk = gt >> 2, t = gt & 3;
+  const int t = gt & 3;
+  int blk = gt >> 2;
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
+  if (p.active) blk = (blk < *p.nactive) ? p.active[blk] : p.nblk;
 
   bool active = false;
   int W = 0, P = 64;           // P: largest renormalisation period this block's guard allows (0: exact path)

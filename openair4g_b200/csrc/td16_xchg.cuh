@@ -34,7 +34,47 @@ struct XchgArgs {
   int iter;                     // iteration_cnt of the reference loop (1..max)
   int guard_b;                  // MAP fast-path guard (same value as MapArgs::guard_b)
   int* batch_max;               // max |y| over the whole batch (atomicMax by k_demux16)
+  const int* active;            // packed list of the blocks still being decoded, or nullptr = all nblk blocks
+  const int* nactive;
+  int* nactive_next;            // k_x1_16 zeroes the counter of the list that k_compact builds after k_x2_16
 };
+
+// Active-block compaction: the kernels address blocks through a packed list of the blocks that are still being
+// decoded, so that the MAP kernel's warps (8 blocks each) stay full when blocks of a batch leave at different
+// iterations (early termination).  k_compact rebuilds the list after k_demux16 and after every k_x2_16: each CTA
+// packs its 1024 blocks (ascending) and reserves its range with one atomicAdd, so neighbouring list entries stay
+// neighbours in memory; k_x1_16 zeroes the counter of the list that is built next.
+constexpr int COMPACT_THREADS = 1024;
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count) {
+  __shared__ int wsum[COMPACT_THREADS / 32];
+  __shared__ int base;
+  const int i = blockIdx.x * COMPACT_THREADS + threadIdx.x;
+  const bool on = (i < nblk) && (state[i].status == 0);
+  const unsigned bal = __ballot_sync(0xffffffffu, on);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int c = wsum[w]; wsum[w] = t; t += c; }
+    base = t ? atomicAdd(count, t) : 0;
+  }
+  __syncthreads();
+  if (on) list[base + wsum[wid] + __popc(bal & ((1u << lane) - 1u))] = i;
+}
+
+// block handled by this CTA of an exchange kernel (-1: none)
+#ifndef XCHG_LIST_MODE
+#define XCHG_LIST_MODE 0      // bit 0: k_x1_16 uses the packed list, bit 1: k_x2_16.  Measured: the two dependent loads at
+                              // CTA start cost k_x2_16 21 % and k_x1_16 4 %, while a CTA of a finished block exits at once
+                              // anyway -- so only k_map16 (whose warps carry 8 blocks) goes through the list
+#endif
+__device__ __forceinline__ int xchg_block(const XchgArgs& p, bool use_list = true) {
+  const int bi = blockIdx.x;
+  if (!use_list) return (bi < p.nblk) ? bi : -1;
+  if (p.active) return (bi < *p.nactive) ? p.active[bi] : -1;
+  return (bi < p.nblk) ? bi : -1;
+}
 
 __device__ __forceinline__ int blk_max_reduce(int v, int* red) {
 #pragma unroll
@@ -92,12 +132,6 @@ __device__ __forceinline__ unsigned long long clmul32(u32 x, u32 y) {
   u64 z2 = ((u64)x0 * y2) ^ ((u64)x1 * y1) ^ ((u64)x2 * y0) ^ ((u64)x3 * y3);
   u64 z3 = ((u64)x0 * y3) ^ ((u64)x1 * y2) ^ ((u64)x2 * y1) ^ ((u64)x3 * y0);
   return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) | (z3 & 0x8888888888888888ull);
-}
-
-// position p -> halfword index in the C4 layout; magic = floor(2^32/W)+1
-__device__ __forceinline__ int pos_hw(int p, int W, u32 magic) {
-  int lane = (int)__umulhi((u32)p, magic);
-  return c4_hw(p - lane * W, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -177,8 +211,9 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
 __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
-  const int blk = blockIdx.x;
-  if (blk >= p.nblk) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.nactive_next) *p.nactive_next = 0;    // the list k_compact fills next
+  const int blk = xchg_block(p, (XCHG_LIST_MODE & 1) != 0);
+  if (blk < 0) return;
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;
@@ -314,8 +349,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
   __shared__ u32 xred[2 * XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
   __shared__ __align__(16) uint8_t snib[1536 + 16];              // hard decisions, one 4-step group per byte
-  const int blk = blockIdx.x;
-  if (blk >= p.nblk) return;
+  const int blk = xchg_block(p, (XCHG_LIST_MODE & 2) != 0);
+  if (blk < 0) return;
   const CbMeta m = p.meta[blk];
   CbState* st = &p.state[blk];
   if (st->status != 0 || p.iter > m.max_iter) return;

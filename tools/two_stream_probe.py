@@ -22,9 +22,8 @@ def run(nplans, B, steps=5):
     dt = (time.perf_counter() - t0) / steps
     print("plans %d x %d blocks: %.2f ms/step -> %.0f Mbit/s" % (nplans, B, dt*1e3, nplans*B*K/dt/1e6))
     for p in plans: p.close()
-run(1, 23680)
-run(2, 11840)
-run(2, 23680)
-run(4, 5920)
-run(1, 35520)
-run(3, 11840)
+run(1, 42624)
+run(2, 21312)
+run(3, 14208)
+run(4, 10656)
+run(6, 7104)
