@@ -260,15 +260,31 @@ def run_b200(args):
     Be = args.e2e_blocks
     y_pin = torch.empty((Be, row), dtype=torch.int16).pin_memory()
     y_pin.copy_(y_dev[:Be].cpu())
-    # one submit + wait per step; inside the call the batch is pipelined in parts (input copy of part i+1 overlaps the
-    # decode of part i, decoded bytes of part i go back meanwhile) and lands in page-locked caller memory
-    call = capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE)
-    for _ in range(2):
-        call.run()
+    # Every step is one oai_turbo_submit_batch (copies the step's inputs from page-locked host memory, decodes, copies the
+    # decoded bytes and status back) and one oai_turbo_wait.  Inside a call the batch is pipelined in parts (input copy of
+    # part i+1 overlaps the decode of part i).  One call at a time by default; --e2e-in-flight 2 keeps two batches in flight
+    # (submit of step i+1 before the wait of step i) -- measured SLOWER on this box (7.2 vs 8.2 Gbit/s): two concurrent
+    # host->device copy streams share the link and kernels run slower while copies are in flight.
+    args.e2e_serial = args.e2e_in_flight < 2
+    calls = [capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE) for _ in range(1 if args.e2e_serial else 2)]
+    for c in calls:
+        for _ in range(2):
+            c.run()
+    call = calls[0]
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_h, st_h = call.run()
+    if args.e2e_serial:
+        for _ in range(args.steps):
+            out_h, st_h = call.run()
+    else:
+        pending = None
+        for i in range(args.steps):
+            c = calls[i & 1]
+            h = c.submit()
+            if pending is not None:
+                pending[0].wait(pending[1])
+            pending = (c, h)
+        out_h, st_h = pending[0].wait(pending[1])
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -392,6 +408,7 @@ def run_b200(args):
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
+                    "in_flight": 1 if args.e2e_serial else 2,
                     "api": "oai_turbo_submit_batch + oai_turbo_wait per step, page-locked host input and output buffers; "
                            "bound by the PCIe copy of 36.9 KB of int16 LLRs per 6144 decoded bits"},
             "gpu_launches": launches, "clocks": clocks}
@@ -443,6 +460,7 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=42624, help="code blocks per GPU per step (host-buffer API)")
     ap.add_argument("--cpu-blocks", type=int, default=262144,
                     help="bounded CPU-baseline sample (blocks): ~4 s of wall time on 16 host threads (~60 s of CPU work)")
+    ap.add_argument("--e2e-in-flight", type=int, default=1, choices=[1, 2], help="host-buffer batches in flight in the e2e loop")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-regimes", action="store_true", help="skip the clean / waterfall side measurements")
     ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
