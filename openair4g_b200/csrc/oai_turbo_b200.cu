@@ -600,6 +600,52 @@ struct HostBatch {
     int rc = ensure(gpu, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
     if (rc) return rc;
     if (trace) { for (auto& e : ev) if (!e) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
+    // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
+    // page-locked caller memory is copied from directly, pageable memory through the pinned stage
+    auto enqueue_inputs = [&](int lo, int hi, cudaStream_t cs) -> int {
+      for (int i = lo; i < hi;) {
+        if (descs[order[i]].dematch_enable) { ++i; continue; }     // y is produced on the device by k_deint
+        const int16_t* base = descs[order[i]].in;
+        size_t len = (size_t)3 * descs[order[i]].K + 12;
+        int j = i + 1;
+        while (j < hi && !descs[order[j]].dematch_enable && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
+        cudaPointerAttributes at;
+        bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const int16_t* src = base;
+        if (!pinned) {
+          int r2 = ensure_stage_in();
+          if (r2) return r2;
+          memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i];
+        }
+        CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+        i = j;
+      }
+      return 0;
+    };
+    // Pipelined form (plain 16-bit batches that are large enough): the batch is cut into `parts` ranges of blocks; the
+    // input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).  The last part is the
+    // smallest one, because its decode is the only one that is not hidden behind a copy.
+    int parts = 1;
+    {
+      bool plain = (n == n16) && !getenv("OAI_TURBO_NO_PIPELINE");
+      for (int i = 0; plain && i < n; ++i) plain = !descs[order[i]].dematch_enable;
+      if (plain) parts = std::max(1, std::min(MAX_PARTS, n16 / MIN_PART_BLOCKS));
+    }
+    auto part_lo = [&](int part) -> int {                    // parts-1 equal ranges, then one of MIN_PART_BLOCKS
+      if (part >= parts) return n;
+      if (parts == 1) return 0;
+      return (int)((long)(n - MIN_PART_BLOCKS) * part / (parts - 1));
+    };
+    if (parts > 1) {
+      if (!st_copy) {
+        CU(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
+        for (auto& e : ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+      }
+    }
     std::vector<CbMeta> meta(n);
     rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
@@ -659,56 +705,33 @@ struct HostBatch {
       direct_out = ok;
       if (!direct_out) { rc = ensure_stage_out(); if (rc) return rc; }
     }
-    // Pipelined form (plain 16-bit batches that are large enough): the batch is cut into `parts` ranges of
-    // blocks; the input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).
-    int parts = 1;
-    if (rm.empty() && n == n16 && !getenv("OAI_TURBO_NO_PIPELINE")) parts = std::max(1, std::min(MAX_PARTS, n16 / MIN_PART_BLOCKS));
-    if (parts > 1 && !st_copy) {
-      CU(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
-      CU(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
-      for (auto& e : ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      for (auto& e : ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
-    }
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
     if (n16 > 0) {
       rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
       if (rc) return rc;
     }
-    // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
-    // page-locked caller memory is copied from directly, pageable memory through the pinned stage
-    for (int part = 0; part < parts; ++part) {
-      const int lo = (int)((long)n * part / parts), hi = (int)((long)n * (part + 1) / parts);
-      cudaStream_t cs = (parts > 1) ? st_copy : st;
-      for (int i = lo; i < hi;) {
-        if (descs[order[i]].dematch_enable) { ++i; continue; }     // y is produced on the device by k_deint
-        const int16_t* base = descs[order[i]].in;
-        size_t len = (size_t)3 * descs[order[i]].K + 12;
-        int j = i + 1;
-        while (j < hi && !descs[order[j]].dematch_enable && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
-        cudaPointerAttributes at;
-        bool pinned = (cudaPointerGetAttributes(&at, base) == cudaSuccess) && at.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        const int16_t* src = base;
-        if (!pinned) {
-          rc = ensure_stage_in();
-          if (rc) return rc;
-          memcpy(h_in + in_off[i], base, len * sizeof(int16_t)); src = h_in + in_off[i];
-        }
-        CU(cudaMemcpyAsync(d_in + in_off[i], src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
-        i = j;
-      }
-      if (parts > 1) {
-        CU(cudaEventRecord(ev_part[part], st_copy));
-        CU(cudaStreamWaitEvent(st, ev_part[part], 0));
-        rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
-        if (rc < 0) return rc;
-        // this part's decoded bytes go back while the next parts are still being copied in / decoded
-        CU(cudaEventRecord(ev_done[part], st));
-        CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
-        const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
-        CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
-      }
+    if (parts == 1) {
+      rc = enqueue_inputs(0, n, st);
+      if (rc) return rc;
+    }
+    // all input copies are enqueued before the first kernel launch, AFTER the small metadata copy above: copies of one
+    // direction execute in issue order, and a metadata copy queued behind the inputs would serialise everything
+    // (measured: 48 instead of 32 ms per 42624 blocks)
+    for (int part = 0; parts > 1 && part < parts; ++part) {
+      rc = enqueue_inputs(part_lo(part), part_lo(part + 1), st_copy);
+      if (rc) return rc;
+      CU(cudaEventRecord(ev_part[part], st_copy));
+    }
+    for (int part = 0; parts > 1 && part < parts; ++part) {
+      const int lo = part_lo(part), hi = part_lo(part + 1);
+      CU(cudaStreamWaitEvent(st, ev_part[part], 0));
+      rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
+      if (rc < 0) return rc;
+      // this part's decoded bytes go back while the next parts are still being copied in / decoded
+      CU(cudaEventRecord(ev_done[part], st));
+      CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
+      const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
+      CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
     }
     if (trace) cudaEventRecord(ev[1], st);
     if (n16 > 0 && parts == 1) {
