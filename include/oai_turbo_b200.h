@@ -130,7 +130,23 @@ typedef struct {
   uint32_t  Nsoft;
   uint8_t   C, r, rvidx, clear, Qm, Nl, Mdlharq, Kmimo;
   uint32_t  tb_id;             /* blocks with equal tb_id form one transport block */
+  /* device-resident HARQ soft buffer (optional, front end only): when harq_pool != NULL the circular buffer w of
+   * this block lives in slot harq_slot of the pool on the GPU, `w` is ignored and nothing of it crosses PCIe */
+  struct oai_turbo_harq_pool *harq_pool;
+  uint32_t  harq_slot;
 } oai_cb_desc_t;
+
+/* HARQ soft-buffer pool in HBM.  The reference keeps w[r] (int16[3*Kpi]) per (UE, HARQ process, code block) in host
+ * memory across retransmissions (LTE_TRANSPORT/defs.h:428,531) and rate dematching accumulates into it; a GPU front end
+ * that treats the host copy as authoritative moves 2 x 3*Kpi int16 over PCIe per block and round.  A pool keeps
+ * n_slots buffers of 3*Kpi(max_K) int16 on the device (zeroed at creation; `clear` in the descriptor resets a slot
+ * like the reference's memset); the caller maps (cell, UE, harq_pid, r) to a slot index.  All pool-backed blocks of
+ * one submit must use the same pool, on the GPU the batch runs on. */
+typedef struct oai_turbo_harq_pool oai_turbo_harq_pool_t;
+int oai_turbo_harq_pool_create(int gpu, uint32_t n_slots, uint16_t max_K, oai_turbo_harq_pool_t **pool);
+/* copies the first n int16 of a slot to host memory (tests, migration of a UE to another GPU); synchronous */
+int oai_turbo_harq_pool_read(oai_turbo_harq_pool_t *pool, uint32_t slot, int16_t *w_host, uint32_t n);
+void oai_turbo_harq_pool_destroy(oai_turbo_harq_pool_t *pool);
 
 #define OAI_BATCH_DL_STOP_AFTER_FAILURE 1u  /* dlsch_decoding.c:417,448-451: within a
         transport block, blocks after the first failing one report status 0xFE ("not

@@ -29,6 +29,7 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
            "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
+           "oai_turbo_harq_pool_create", "oai_turbo_harq_pool_read", "oai_turbo_harq_pool_destroy",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
            "oai_turbo_debug_map16"]
 
@@ -41,7 +42,7 @@ class CbDesc(C.Structure):
                 ("dematch_enable", C.c_uint8), ("w", C.c_void_p), ("G", C.c_uint32),
                 ("Nsoft", C.c_uint32), ("C", C.c_uint8), ("r", C.c_uint8), ("rvidx", C.c_uint8),
                 ("clear", C.c_uint8), ("Qm", C.c_uint8), ("Nl", C.c_uint8), ("Mdlharq", C.c_uint8),
-                ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32)]
+                ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32), ("harq_pool", C.c_void_p), ("harq_slot", C.c_uint32)]
 
 
 _stats7 = [C.c_void_p] * 7
@@ -60,6 +61,10 @@ lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
 lib.oai_lte_segmentation_params.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 6
 lib.oai_lte_segmentation_params.restype = C.c_int
+lib.oai_turbo_harq_pool_create.argtypes = [C.c_int, C.c_uint32, C.c_uint16, C.POINTER(C.c_void_p)]
+lib.oai_turbo_harq_pool_read.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+lib.oai_turbo_harq_pool_destroy.argtypes = [C.c_void_p]
+lib.oai_turbo_harq_pool_destroy.restype = None
 lib.oai_turbo_host_alloc.argtypes = [C.c_size_t]
 lib.oai_turbo_host_alloc.restype = C.c_void_p
 lib.oai_turbo_host_free.argtypes = [C.c_void_p]
@@ -166,6 +171,9 @@ def decode_batch(blocks, flags=0, gpu=-1):
                 d.w = w.ctypes.data
             d.G, d.C, d.r, d.rvidx, d.clear, d.Qm = dm["G"], dm["C"], dm["r"], dm["rvidx"], dm["clear"], dm["Qm"]
             d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = dm.get("Nl", 1), dm.get("Mdlharq", 8), dm.get("Kmimo", 1), dm.get("Nsoft", 1827072)
+            if dm.get("harq_pool") is not None:          # device-resident soft buffer: (HarqPool, slot)
+                d.harq_pool = dm["harq_pool"].handle
+                d.harq_slot = dm["harq_slot"]
     h = C.c_void_p()
     rc = lib.oai_turbo_submit_batch(descs, n, flags, gpu, C.byref(h))
     if rc != 0:
@@ -192,6 +200,35 @@ def lte_segmentation_params(B):
     v = [C.c_uint32(0) for _ in range(6)]
     rc = lib.oai_lte_segmentation_params(B, *[C.byref(x) for x in v])
     return rc, dict(zip(("C", "Cplus", "Cminus", "Kplus", "Kminus", "F"), [int(x.value) for x in v]))
+
+
+class HarqPool:
+    """Device-resident HARQ soft buffers (oai_turbo_harq_pool_*): n_slots circular buffers w of 3*Kpi(max_K) int16 in HBM."""
+
+    def __init__(self, n_slots, max_K, gpu=-1):
+        self.handle = C.c_void_p()
+        rc = lib.oai_turbo_harq_pool_create(gpu, n_slots, max_K, C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError("oai_turbo_harq_pool_create failed (%d): %s" % (rc, last_error()))
+        self.n_slots = n_slots
+
+    def read(self, slot, n):
+        w = np.zeros(n, dtype=np.int16)
+        rc = lib.oai_turbo_harq_pool_read(self.handle, slot, w.ctypes.data, n)
+        if rc != 0:
+            raise RuntimeError("oai_turbo_harq_pool_read failed (%d): %s" % (rc, last_error()))
+        return w
+
+    def close(self):
+        if self.handle:
+            lib.oai_turbo_harq_pool_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PinnedArray:

@@ -411,6 +411,15 @@ static int rm_params(uint32_t K, uint32_t G, uint8_t C, uint32_t Nsoft, uint8_t 
   return 0;
 }
 
+}  // namespace oai
+// device-resident HARQ soft buffers (include/oai_turbo_b200.h section 2)
+struct oai_turbo_harq_pool {
+  int dev = -1;
+  uint32_t n_slots = 0, slot_hw = 0;     // slot size in int16: 3 * Kpi(max_K)
+  int16_t* d = nullptr;
+};
+namespace oai {
+
 // per-thread scratch for the single-call reference entry points of the front end
 struct Scratch {
   cudaStream_t st = nullptr;
@@ -649,6 +658,7 @@ struct HostBatch {
     std::vector<CbMeta> meta(n);
     rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
+    oai_turbo_harq_pool* pool = nullptr;
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
       make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i],
@@ -660,12 +670,22 @@ struct HostBatch {
         RmBlock rb;
         memset(&rb, 0, sizeof(rb));
         rb.K = d.K; rb.F = d.F; rb.RTC = q.RTC; rb.Kpi = q.Kpi; rb.ND = q.ND; rb.Ncb = q.Ncb; rb.k0 = q.k0; rb.E = q.E;
-        rb.clear = d.clear; rb.w_off = (uint32_t)w_hw;
+        rb.clear = d.clear;
+        if (d.harq_pool) {
+          if (pool && pool != d.harq_pool) return fail(-4, "block %d: all pool-backed blocks of a submit must use the same HARQ pool", order[i]);
+          pool = d.harq_pool;
+          if (pool->dev != dev) return fail(-4, "block %d: HARQ pool lives on GPU %d, the batch runs on GPU %d", order[i], pool->dev, dev);
+          if (d.harq_slot >= pool->n_slots || 3 * q.Kpi > pool->slot_hw)
+            return fail(-4, "block %d: HARQ slot %u out of range or too small for K=%d", order[i], d.harq_slot, (int)d.K);
+          rb.w_sel = 1; rb.w_off = d.harq_slot * pool->slot_hw;
+        } else {
+          rb.w_sel = 0; rb.w_off = (uint32_t)w_hw;
+        }
         rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
         rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
         e_hw += ((size_t)q.E + 7) & ~(size_t)7;
-        w_hw += (size_t)3 * q.Kpi;
+        if (!d.harq_pool) w_hw += (size_t)3 * q.Kpi;
         rm.push_back(rb); rm_desc.push_back(order[i]);
       }
     }
@@ -676,16 +696,19 @@ struct HostBatch {
         const oai_cb_desc_t& d = descs[rm_desc[j]];
         const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
         memcpy(h_e + eo, d.in, sizeof(int16_t) * rm[j].E);
+        if (rm[j].w_sel) continue;                         // soft buffer stays in HBM
         if (d.w) memcpy(h_w + rm[j].w_off, d.w, sizeof(int16_t) * 3 * rm[j].Kpi);
         else memset(h_w + rm[j].w_off, 0, sizeof(int16_t) * 3 * rm[j].Kpi);
       }
       CU(cudaMemcpyAsync(d_e, h_e, e_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+      if (w_hw) CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
       CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
-      k_rm_rx<<<(int)rm.size(), RM_THREADS, 0, st>>>(d_rm, (int)rm.size(), d_w, d_e, nullptr);
-      k_deint<<<(int)rm.size(), RM_THREADS, 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t), st>>>(d_rm, (int)rm.size(), d_w, d_in, 0);
+      int16_t* hp = pool ? pool->d : nullptr;
+      k_rm_rx<<<(int)rm.size(), RM_THREADS, 0, st>>>(d_rm, (int)rm.size(), d_w, d_e, nullptr, hp);
+      k_deint<<<(int)rm.size(), RM_THREADS, 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t), st>>>(d_rm, (int)rm.size(), d_w, d_in, 0, hp);
       g_launches += 2;
-      CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+      if (w_hw)
+        CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     }
     // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
     // every block decoded) in page-locked memory, the result is copied straight into them
@@ -776,7 +799,7 @@ struct HostBatch {
     }
     for (size_t j = 0; j < rm.size(); ++j) {                     // HARQ buffers back to their owners
       const oai_cb_desc_t& d = descs[rm_desc[j]];
-      if (d.w) memcpy(d.w, h_w + rm[j].w_off, sizeof(int16_t) * rm[j].Ncb);
+      if (d.w && !rm[j].w_sel) memcpy(d.w, h_w + rm[j].w_off, sizeof(int16_t) * rm[j].Ncb);
     }
     if (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) {
       // dlsch_decoding.c:400,417,448-451: after the first failing block of a transport block the
@@ -878,6 +901,43 @@ int oai_turbo_wait(oai_turbo_batch_t* h) {
 }
 
 int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t* p, int enable, double* ms4, long* count4);
+
+int oai_turbo_harq_pool_create(int gpu, uint32_t n_slots, uint16_t max_K, oai_turbo_harq_pool_t** pool) {
+  if (!pool || n_slots == 0 || qpp_index(max_K) < 0) return fail(-1, "bad arguments");
+  DevCtx* c;
+  int rc = ctx_get(gpu, &c);
+  if (rc) return rc;
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(c->dev));
+  oai_turbo_harq_pool* p = new oai_turbo_harq_pool();
+  p->dev = c->dev; p->n_slots = n_slots;
+  p->slot_hw = 3u * 32u * (((uint32_t)max_K + 4 + 31) / 32);
+  if ((unsigned long long)p->slot_hw * n_slots > 0xffffffffull) { delete p; cudaSetDevice(prev); return fail(-1, "pool too large for 32-bit offsets"); }
+  const size_t bytes = sizeof(int16_t) * (size_t)p->slot_hw * n_slots;
+  if (cudaMalloc(&p->d, bytes) != cudaSuccess || cudaMemset(p->d, 0, bytes) != cudaSuccess) {
+    cudaGetLastError(); delete p; cudaSetDevice(prev);
+    return fail(-100, "HARQ pool: cudaMalloc of %zu bytes failed", bytes);
+  }
+  CU(cudaSetDevice(prev));
+  *pool = p;
+  return 0;
+}
+int oai_turbo_harq_pool_read(oai_turbo_harq_pool_t* p, uint32_t slot, int16_t* w_host, uint32_t n) {
+  if (!p || !w_host || slot >= p->n_slots || n > p->slot_hw) return fail(-1, "bad arguments");
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(p->dev));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(w_host, p->d + (size_t)slot * p->slot_hw, sizeof(int16_t) * n, cudaMemcpyDeviceToHost));
+  CU(cudaSetDevice(prev));
+  return 0;
+}
+void oai_turbo_harq_pool_destroy(oai_turbo_harq_pool_t* p) {
+  if (!p) return;
+  cudaFree(p->d);
+  delete p;
+}
 
 // lte_segmentation.c:52-134, parameter part
 int oai_lte_segmentation_params(uint32_t B, uint32_t* C, uint32_t* Cplus, uint32_t* Cminus, uint32_t* Kplus,

@@ -22,7 +22,8 @@ struct RmBlock {
   uint32_t RTC, Kpi, ND;    // rows, 32*RTC, Kpi - (K+4)
   uint32_t Ncb, k0, E;      // circular buffer length, start, soft bits of this block
   uint32_t clear;
-  uint32_t w_off;           // int16 offset of this block's w in the w pool (3*Kpi entries)
+  uint32_t w_off;           // int16 offset of this block's w in its pool (3*Kpi entries)
+  uint32_t w_sel;           // 0: staging pool of the batch (host-authoritative w), 1: device-resident HARQ pool
   uint32_t e_off_lo, e_off_hi;   // int16 offset of this block's soft bits in the input pool
   uint32_t dummy_off;       // byte offset of a caller-provided NULL map, or 0xffffffff: derive from (K,F)
   uint32_t y_off_lo, y_off_hi;   // int16 offset of the decoder input y (3K+12) written by k_deint
@@ -51,12 +52,13 @@ __global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, u
 }
 
 __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
-                                                      const int16_t* e_pool, const uint8_t* dummy_pool) {
+                                                      const int16_t* e_pool, const uint8_t* dummy_pool,
+                                                      int16_t* harq_pool = nullptr) {
   __shared__ uint32_t s_cnt[RM_THREADS + 1];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
   const RmBlock b = blocks[blk];
-  int16_t* w = w_pool + b.w_off;
+  int16_t* w = (b.w_sel ? harq_pool : w_pool) + b.w_off;
   const int16_t* e = e_pool + (((long)b.e_off_hi << 32) | b.e_off_lo);
   const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
   auto is_null = [&](uint32_t ind) -> bool {
@@ -97,12 +99,12 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
 //   q = 3*idx   <- w[k], q = 3*idx+1 <- w[Kpi+2k], q = 3*idx+5 <- w[Kpi+2k+1],  k = brev5(idx&31)*RTC + (idx>>5)
 // Elements q = 2, 3*Kpi, 3*Kpi+1 are never written by the reference.  out[q - q_lo] for q in [q_lo,q_hi).
 __global__ void __launch_bounds__(RM_THREADS) k_deint(const RmBlock* blocks, int nblk, const int16_t* w_pool,
-                                                      int16_t* y_pool, int api_mode) {
+                                                      int16_t* y_pool, int api_mode, const int16_t* harq_pool = nullptr) {
   extern __shared__ int16_t sw[];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
   const RmBlock b = blocks[blk];
-  const int16_t* w = w_pool + b.w_off;
+  const int16_t* w = (b.w_sel ? harq_pool : w_pool) + b.w_off;
   for (uint32_t i = threadIdx.x; i < 3 * b.Kpi / 2; i += RM_THREADS)
     reinterpret_cast<uint32_t*>(sw)[i] = reinterpret_cast<const uint32_t*>(w)[i];
   __syncthreads();

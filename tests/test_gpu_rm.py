@@ -147,3 +147,34 @@ def test_fused_front_end_batch_with_harq_rounds(capi):
     outs, status = capi.decode_batch([{"y": e, "K": K, "max_iterations": 4, "crc_type": 0, "decode_enable": 0,
                                        "dematch": {"G": G, "C": Cb, "r": r, "rvidx": 0, "clear": 1, "Qm": Qm, "w": wg}}])
     assert status == [0xFE] and np.array_equal(wg, wr)
+
+
+def test_device_resident_harq_pool(capi):
+    """HARQ soft buffers kept in HBM (oai_turbo_harq_pool_*): three rounds (rv 0, 2, 3; the last one wraps around the
+    circular buffer) through pool slots give the same decoded bytes, return values and buffer contents as the oracle
+    chain with a host buffer, while no w crosses PCIe; `clear` re-initialises a slot; slots are independent."""
+    shapes = [(5824, 0, 90000, 13, 6, (0, 12)), (3904, 0, 14400, 2, 4, (0, 1)), (6144, 0, 57600, 5, 4, (4,)), (104, 16, 600, 1, 2, (0,))]
+    infos = [(K, F, G, Cb, Qm, r, 0 if Cb == 1 else 1) for (K, F, G, Cb, Qm, rs) in shapes for r in rs]
+    pool = capi.HarqPool(len(infos) + 3, 6144)
+    slots = [(5 * i + 2) % (len(infos) + 3) for i in range(len(infos))]
+    assert len(set(slots)) == len(slots)
+    w_ref = [None] * len(infos)
+    for rnd, (rv, clear) in enumerate([(0, 1), (2, 0), (3, 0), (0, 1)]):          # the 4th round restarts the processes
+        blocks, want = [], []
+        for i, (K, F, G, Cb, Qm, r, crc) in enumerate(infos):
+            info, e, E, RTC = _tx(K, 40 + r, F if r == 0 else 0, G, Cb, Qm, r, rv, 8, 1.5)
+            if w_ref[i] is None:
+                w_ref[i] = np.zeros(3 * 32 * RTC, dtype=np.int16)
+            blocks.append({"y": e, "K": K, "max_iterations": 6, "crc_type": crc, "F": F if r == 0 else 0,
+                           "dematch": {"G": G, "C": Cb, "r": r, "rvidx": rv, "clear": clear, "Qm": Qm, "w": None,
+                                       "harq_pool": pool, "harq_slot": slots[i]}})
+            want.append(_oracle_chain(K, F, G, Cb, Qm, r, rv, clear, e, w_ref[i], 6, crc))
+        outs, status = capi.decode_batch(blocks)
+        for i, ((wb, wrr), ob, st) in enumerate(zip(want, outs, status)):
+            assert st == wrr and np.array_equal(ob, wb), (rnd, infos[i], st, wrr)
+            K, Cb = infos[i][0], infos[i][3]
+            Kpi = 32 * ((K + 4 + 31) // 32)
+            Ncb = min(1827072 // 8 // Cb, 3 * Kpi)
+            assert np.array_equal(pool.read(slots[i], Ncb), w_ref[i][:Ncb]), (rnd, infos[i])
+    assert {w for _, w in want} != {7}
+    pool.close()
