@@ -636,10 +636,16 @@ struct HostBatch {
     // input copy of part i+1 (copy stream) overlaps the decode of part i (compute stream).  The last part is the
     // smallest one, because its decode is the only one that is not hidden behind a copy.
     int parts = 1;
+    bool fe_parts = false;                                   // pipelined parts run the front end too
     {
-      bool plain = (n == n16) && !getenv("OAI_TURBO_NO_PIPELINE");
-      for (int i = 0; plain && i < n; ++i) plain = !descs[order[i]].dematch_enable;
-      if (plain) parts = std::max(1, std::min(MAX_PARTS, n16 / MIN_PART_BLOCKS));
+      // eligible: only 16-bit blocks, and either no block uses the front end or all do with their HARQ buffers in a
+      // device pool (a host-authoritative w would have to be staged in and out around every part)
+      bool ok = (n == n16) && !getenv("OAI_TURBO_NO_PIPELINE");
+      int n_fe = 0, n_pool = 0;
+      for (int i = 0; i < n; ++i) { n_fe += descs[order[i]].dematch_enable ? 1 : 0; n_pool += (descs[order[i]].dematch_enable && descs[order[i]].harq_pool) ? 1 : 0; }
+      ok = ok && (n_fe == 0 || (n_fe == n && n_pool == n));
+      if (ok) parts = std::max(1, std::min(MAX_PARTS, n16 / (n_fe ? 2 * MIN_PART_BLOCKS : MIN_PART_BLOCKS)));
+      fe_parts = parts > 1 && n_fe == n;
     }
     auto part_lo = [&](int part) -> int {                    // parts-1 equal ranges, then one of MIN_PART_BLOCKS
       if (part >= parts) return n;
@@ -659,6 +665,7 @@ struct HostBatch {
     rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
     oai_turbo_harq_pool* pool = nullptr;
+    const int16_t* prev_e_end = nullptr;
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
       make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i],
@@ -681,34 +688,61 @@ struct HostBatch {
         } else {
           rb.w_sel = 0; rb.w_off = (uint32_t)w_hw;
         }
+        // soft bits that follow the previous block's in the caller's memory (r_offset slices of one e buffer,
+        // ulsch_decoding.c:1259) keep that spacing on the device, so that a run goes over with one copy
+        const bool cont = !rm.empty() && d.in == prev_e_end;
+        if (!cont) e_hw = (e_hw + 7) & ~(size_t)7;
+        prev_e_end = d.in + q.E;
         rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
         rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
-        e_hw += ((size_t)q.E + 7) & ~(size_t)7;
+        e_hw += (size_t)q.E;
         if (!d.harq_pool) w_hw += (size_t)3 * q.Kpi;
         rm.push_back(rb); rm_desc.push_back(order[i]);
       }
     }
+    // soft bits of rm blocks [jlo, jhi): one copy per run that is contiguous in the caller's memory, staged only if pageable
+    auto copy_e_runs = [&](size_t jlo, size_t jhi, cudaStream_t cs) -> int {
+      for (size_t j = jlo; j < jhi;) {
+        const oai_cb_desc_t& d0 = descs[rm_desc[j]];
+        const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
+        size_t len = rm[j].E, k = j + 1;
+        while (k < jhi && descs[rm_desc[k]].in == d0.in + len) { len += rm[k].E; ++k; }
+        cudaPointerAttributes at;
+        const bool pinned = (cudaPointerGetAttributes(&at, d0.in) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const int16_t* src = d0.in;
+        if (!pinned) { memcpy(h_e + eo, d0.in, sizeof(int16_t) * len); src = h_e + eo; }
+        CU(cudaMemcpyAsync(d_e + eo, src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+        j = k;
+      }
+      return 0;
+    };
+    int16_t* const hp = pool ? pool->d : nullptr;
+    const size_t deint_smem = 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t);
+    auto front_end = [&](size_t jlo, size_t jhi) {            // dematch + deinterleave of rm blocks [jlo, jhi) on st
+      const int cnt = (int)(jhi - jlo);
+      k_rm_rx<<<cnt, RM_THREADS, deint_smem / 2, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp);   // one flag byte per slot
+      k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp);
+      g_launches += 2;
+    };
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
       if (rc) return rc;
-      for (size_t j = 0; j < rm.size(); ++j) {
-        const oai_cb_desc_t& d = descs[rm_desc[j]];
-        const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
-        memcpy(h_e + eo, d.in, sizeof(int16_t) * rm[j].E);
-        if (rm[j].w_sel) continue;                         // soft buffer stays in HBM
-        if (d.w) memcpy(h_w + rm[j].w_off, d.w, sizeof(int16_t) * 3 * rm[j].Kpi);
-        else memset(h_w + rm[j].w_off, 0, sizeof(int16_t) * 3 * rm[j].Kpi);
-      }
-      CU(cudaMemcpyAsync(d_e, h_e, e_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-      if (w_hw) CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
       CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
-      int16_t* hp = pool ? pool->d : nullptr;
-      k_rm_rx<<<(int)rm.size(), RM_THREADS, 0, st>>>(d_rm, (int)rm.size(), d_w, d_e, nullptr, hp);
-      k_deint<<<(int)rm.size(), RM_THREADS, 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t), st>>>(d_rm, (int)rm.size(), d_w, d_in, 0, hp);
-      g_launches += 2;
-      if (w_hw)
-        CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+      if (!fe_parts) {
+        rc = copy_e_runs(0, rm.size(), st);
+        if (rc) return rc;
+        for (size_t j = 0; j < rm.size(); ++j) {
+          const oai_cb_desc_t& d = descs[rm_desc[j]];
+          if (rm[j].w_sel) continue;                         // soft buffer stays in HBM
+          if (d.w) memcpy(h_w + rm[j].w_off, d.w, sizeof(int16_t) * 3 * rm[j].Kpi);
+          else memset(h_w + rm[j].w_off, 0, sizeof(int16_t) * 3 * rm[j].Kpi);
+        }
+        if (w_hw) CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        front_end(0, rm.size());
+        if (w_hw) CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+      }
     }
     // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
     // every block decoded) in page-locked memory, the result is copied straight into them
@@ -741,13 +775,15 @@ struct HostBatch {
     // direction execute in issue order, and a metadata copy queued behind the inputs would serialise everything
     // (measured: 48 instead of 32 ms per 42624 blocks)
     for (int part = 0; parts > 1 && part < parts; ++part) {
-      rc = enqueue_inputs(part_lo(part), part_lo(part + 1), st_copy);
+      // (with the front end in the parts, rm block j is block j of the batch: every block is an rm block)
+      rc = fe_parts ? copy_e_runs(part_lo(part), part_lo(part + 1), st_copy) : enqueue_inputs(part_lo(part), part_lo(part + 1), st_copy);
       if (rc) return rc;
       CU(cudaEventRecord(ev_part[part], st_copy));
     }
     for (int part = 0; parts > 1 && part < parts; ++part) {
       const int lo = part_lo(part), hi = part_lo(part + 1);
       CU(cudaStreamWaitEvent(st, ev_part[part], 0));
+      if (fe_parts) front_end(lo, hi);
       rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
       if (rc < 0) return rc;
       // this part's decoded bytes go back while the next parts are still being copied in / decoded
@@ -1079,7 +1115,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
   memcpy(h + o_dm, dummy_w, q.Ncb);
   memcpy(h + o_e, soft_input, (size_t)q.E * 2);
   CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, sc.st));
-  k_rm_rx<<<1, RM_THREADS, 0, sc.st>>>((const RmBlock*)d, 1, (int16_t*)(d + o_w), (const int16_t*)(d + o_e), (const uint8_t*)(d + o_dm));
+  k_rm_rx<<<1, RM_THREADS, q.Ncb + 16, sc.st>>>((const RmBlock*)d, 1, (int16_t*)(d + o_w), (const int16_t*)(d + o_e), (const uint8_t*)(d + o_dm));
   ++g_launches;
   CU(cudaMemcpyAsync(h + o_w, d + o_w, (size_t)q.Ncb * 2, cudaMemcpyDeviceToHost, sc.st));
   CU(cudaStreamSynchronize(sc.st));

@@ -33,13 +33,14 @@ __device__ __forceinline__ uint32_t brev5(uint32_t c) { return __brev(c) >> 27; 
 
 // NULL predicate of generate_dummy_w for circular-buffer index `ind` (reference :329-370).
 // Only rows 0..2 are ever marked for streams 0/1 and row 0 for stream 2 -- restated as is.
-__device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F) {
+// magic = floor(2^32 / RTC) + 1: ind / RTC as one multiply-high (exact for ind < 2^16, RTC <= 193).
+__device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F, uint32_t magic) {
   if (ind < Kpi) {                                   // stream 0: w[k], k = col*RTC + row
-    const uint32_t col = ind / RTC, row = ind - col * RTC;
+    const uint32_t col = __umulhi(ind, magic), row = ind - col * RTC;
     return row <= 2 && brev5(col) + 32 * row < ND + F;
   }
   const uint32_t j = ind - Kpi, k = j >> 1;
-  const uint32_t col = k / RTC, row = k - col * RTC;
+  const uint32_t col = __umulhi(k, magic), row = k - col * RTC;
   if ((j & 1) == 0) return row <= 2 && brev5(col) + 32 * row < ND + F;       // stream 1: w[Kpi+2k]
   if (ND > 0 && ind == 3 * Kpi - 1) return true;                               // :369-370
   return row == 0 && brev5(col) + 1 < ND;                                      // stream 2: w[Kpi+2k+1]
@@ -47,51 +48,66 @@ __device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32
 
 // generate_dummy_w on a device copy of the caller's buffer: only SETS LTE_NULL (=2)
 __global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F) {
+  const uint32_t magic = 0xffffffffu / RTC + 1;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * Kpi; i += gridDim.x * blockDim.x)
-    if (dummy_is_null(i, RTC, Kpi, ND, F)) w[i] = 2;
+    if (dummy_is_null(i, RTC, Kpi, ND, F, magic)) w[i] = 2;
 }
 
+// Dynamic shared memory: one flag byte per circular-buffer slot (Ncb <= 3*Kpi bytes).
+// Pass 1 marks the slots that carry soft bits and counts them (N in [0,Ncb), and those before the start index);
+// pass 2 walks the buffer in coalesced chunks of 256 slots with a running block-wide prefix count, so that every
+// thread knows the rank of its slot on the reference's walk and adds e[rank], e[rank+N], ... to it.
 __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
                                                       const int16_t* e_pool, const uint8_t* dummy_pool,
                                                       int16_t* harq_pool = nullptr) {
-  __shared__ uint32_t s_cnt[RM_THREADS + 1];
+  extern __shared__ uint8_t sflag[];
+  __shared__ uint32_t s_w[RM_THREADS / 32], s_a[RM_THREADS / 32], s_b[RM_THREADS / 32];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
   const RmBlock b = blocks[blk];
   int16_t* w = (b.w_sel ? harq_pool : w_pool) + b.w_off;
   const int16_t* e = e_pool + (((long)b.e_off_hi << 32) | b.e_off_lo);
   const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
-  auto is_null = [&](uint32_t ind) -> bool {
-    return dm ? (dm[ind] == 2) : dummy_is_null(ind, b.RTC, b.Kpi, b.ND, b.F);
-  };
-  // each thread owns a contiguous run of the circular buffer
-  const uint32_t per = (b.Ncb + RM_THREADS - 1) / RM_THREADS;
-  const uint32_t lo = min(b.Ncb, threadIdx.x * per), hi = min(b.Ncb, lo + per);
-  uint32_t cnt = 0;
-  for (uint32_t i = lo; i < hi; ++i) cnt += is_null(i) ? 0u : 1u;
-  s_cnt[threadIdx.x + 1] = cnt;
-  if (threadIdx.x == 0) s_cnt[0] = 0;
-  __syncthreads();
-  if (threadIdx.x == 0)                                // 256 values: a serial scan is negligible here
-    for (int i = 1; i <= RM_THREADS; ++i) s_cnt[i] += s_cnt[i - 1];
-  __syncthreads();
-  const uint32_t N = s_cnt[RM_THREADS];                 // non-NULL slots in [0,Ncb)
-  if (N == 0) return;                                   // (the reference would loop forever)
-  // non-NULL slots before `start`; the first reference loop runs only when k0 < Ncb (:747)
+  const uint32_t magic = 0xffffffffu / b.RTC + 1;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // the first reference loop runs only when k0 < Ncb (:747)
   const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
-  const uint32_t st_t = min((uint32_t)RM_THREADS - 1, start / per);
-  uint32_t before_start = s_cnt[st_t];
-  for (uint32_t i = st_t * per; i < start; ++i) before_start += is_null(i) ? 0u : 1u;
-  uint32_t c = s_cnt[threadIdx.x];
-  for (uint32_t i = lo; i < hi; ++i) {
-    const bool nul = is_null(i);
-    int acc = (b.clear == 1) ? 0 : (int)w[i];          // memset(w,0,Ncb) when clear==1 (:741-742)
-    if (!nul) {
-      const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
-      for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
-      ++c;
+  uint32_t cnt = 0, cntb = 0;
+  for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
+    const bool nul = dm ? (dm[i] == 2) : dummy_is_null(i, b.RTC, b.Kpi, b.ND, b.F, magic);
+    sflag[i] = nul ? 0 : 1;
+    cnt += nul ? 0u : 1u;
+    cntb += (!nul && i < start) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); cntb += __shfl_xor_sync(0xffffffffu, cntb, o); }
+  if (lane == 0) { s_a[wid] = cnt; s_b[wid] = cntb; }
+  __syncthreads();
+  uint32_t N = 0, before_start = 0;                     // non-NULL slots in [0,Ncb) / before `start`
+#pragma unroll
+  for (int i = 0; i < RM_THREADS / 32; ++i) { N += s_a[i]; before_start += s_b[i]; }
+  if (N == 0) return;                                   // (the reference would loop forever)
+  uint32_t base = 0;
+  for (uint32_t c0 = 0; c0 < b.Ncb; c0 += RM_THREADS) {
+    const uint32_t i = c0 + threadIdx.x;
+    const bool f = (i < b.Ncb) && sflag[i];
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < RM_THREADS / 32; ++k) { const uint32_t v = s_w[k]; tot += v; woff += (k < wid) ? v : 0u; }
+    if (i < b.Ncb) {
+      int acc = (b.clear == 1) ? 0 : (int)w[i];          // memset(w,0,Ncb) when clear==1 (:741-742)
+      if (f) {
+        const uint32_t c = base + woff + __popc(bal & ((1u << lane) - 1u));
+        const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
+        for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+      }
+      w[i] = (int16_t)acc;                               // wraps like the reference's int16 +=
     }
-    w[i] = (int16_t)acc;                               // wraps like the reference's int16 +=
+    base += tot;
+    __syncthreads();
   }
 }
 
