@@ -117,3 +117,60 @@ def test_td8_large_batch_device_resident(capi):
             assert st[i] == want[i % nd][1], (K, i)
             assert np.array_equal(out[i], want[i % nd][0]), (K, i)
         plan.close()
+
+
+def test_pipelined_host_batch_from_pageable_memory(capi):
+    """Same as above from ordinary (pageable) numpy memory: inputs go through the library's pinned staging area part by
+    part, outputs through the staged copy-back."""
+    K, n, nd = 6144, 6100, 6
+    ys, want, _ = _distinct(K, nd, 9700)
+    y = np.stack([ys[(i * 5) % nd] for i in range(n)])
+    blocks = [{"y": y[i], "K": K, "max_iterations": 6, "crc_type": 1} for i in range(n)]
+    # decode_batch copies each y into its own array: build ONE contiguous pageable buffer instead
+    import ctypes as C
+    out = np.zeros((n, K // 8), dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint8)
+    descs = (capi.CbDesc * n)()
+    for i in range(n):
+        d = descs[i]
+        d.in_ = y.ctypes.data + i * y.strides[0]
+        d.decoded_bytes = out.ctypes.data + i * (K // 8)
+        d.status = status.ctypes.data + i
+        d.K, d.max_iterations, d.crc_type, d.decode_enable = K, 6, 1, 1
+    h = C.c_void_p()
+    assert capi.lib.oai_turbo_submit_batch(descs, n, 0, -1, C.byref(h)) == 0, capi.last_error()
+    assert capi.lib.oai_turbo_wait(h) == 0
+    for i in range(n):
+        j = (i * 5) % nd
+        assert status[i] == want[j][1], i
+        assert np.array_equal(out[i], want[j][0]), i
+
+
+def test_concurrent_callers(capi):
+    """The reference entry point is called from up to 10 eNB RX threads at once (lte-softmodem.c:1197-1304): every
+    thread owns its batch object and stream, the device context is shared."""
+    import threading
+    K = 2048
+    ys, want, _ = _distinct(K, 6, 9800)
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(8):
+                j = (tid + rep) % 6
+                r, b = capi.phy_threegpplte_turbo_decoder16(ys[j], K, 0, 0, 6, 1, 0)
+                if r != want[j][1] or not np.array_equal(b, want[j][0]):
+                    errors.append((tid, rep, r, want[j][1]))
+                outs, st = capi.decode_batch([{"y": ys[(j + k) % 6], "K": K, "max_iterations": 6, "crc_type": 1} for k in range(3)])
+                for k in range(3):
+                    if st[k] != want[(j + k) % 6][1] or not np.array_equal(outs[k][:K // 8], want[(j + k) % 6][0]):
+                        errors.append((tid, rep, "batch", k))
+        except Exception as ex:                           # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(10)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
