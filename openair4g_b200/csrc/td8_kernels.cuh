@@ -24,6 +24,7 @@
 // Parity domain n >= 256, n % 16 == 0; the tail LLRs never influence the
 // reference's output and are not read.
 #pragma once
+#include <type_traits>
 #include "td_common.cuh"
 #include "td16_map.cuh"
 #include "td16_xchg.cuh"
@@ -122,24 +123,30 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux8(Td8Args p) {
 // packed (2 lanes) offset-form arithmetic
 constexpr u32 K255 = 0x00ff00ffu, K128 = 0x00800080u;
 struct G8 { u32 g1, g0, n1, n0; };      // m11, m10 and their negatives (signed halfwords)
+// per-halfword arithmetic >>1 of a value in [-256, 255]: bias to non-negative, logical shift, un-bias (2 ALU-pipe
+// instructions instead of 3; the adds go to the other pipe)
+__device__ __forceinline__ u32 vsra1_9bit(u32 x) {
+  return __vsub2(((__vadd2(x, 0x01000100u)) >> 1) & 0x7fff7fffu, K128);
+}
 __device__ __forceinline__ G8 gamma8(u32 s, u32 p) {   // TD8:178-185: widen, add/sub, >>1 (exact floor halves, no saturation)
   G8 g;
-  g.g1 = vsra1(__vadd2(s, p));
-  g.g0 = vsra1(__vsub2(s, p));
-  g.n1 = __vneg2(g.g1);
-  g.n0 = __vneg2(g.g0);
+  g.g1 = vsra1_9bit(__vadd2(s, p));
+  g.g0 = vsra1_9bit(__vsub2(s, p));
+  g.n1 = __vadd2(~g.g1, 0x00010001u);
+  g.n0 = __vadd2(~g.g0, 0x00010001u);
   return g;
 }
 // clamp(max(x + gx, y + gy), 0, 255) = max(sat8(x+gx), sat8(y+gy)) in offset form
 __device__ __forceinline__ u32 acs8(u32 x, u32 gx, u32 y, u32 gy) {
   return __vimin_s16x2_relu(__viaddmax_s16x2(x, gx, __vadd2(y, gy)), K255);
 }
-// out = sat8(n - max_s n) in offset form: max(n' - mx' + 128, 0)
+// out = sat8(n - max_s n) in offset form: max(n' - mx' + 128, 0); n' + c <= 128, so the min with 255 of the
+// add-min-relu form never binds and the zero needs no register
 __device__ __forceinline__ void norm8(u32 (&v)[8], const u32 (&n)[8]) {
   const u32 mx = __vmaxs2(__vimax3_s16x2(n[0], n[1], n[2]), __vimax3_s16x2(n[3], n[4], __vimax3_s16x2(n[5], n[6], n[7])));
-  const u32 c = __vsub2(K128, mx);
+  const u32 c = __vadd2(~mx, 0x00810081u);              // 128 - mx per halfword
 #pragma unroll
-  for (int s = 0; s < 8; ++s) v[s] = __viaddmax_s16x2(n[s], c, 0u);
+  for (int s = 0; s < 8; ++s) v[s] = __viaddmin_s16x2_relu(n[s], c, K255);
 }
 // forward recursion (TD8:251-297)
 __device__ __forceinline__ void alpha8_step(u32 (&a)[8], const G8& g) {
@@ -198,7 +205,10 @@ __device__ __forceinline__ u32 unp8(const uint4& v, int e) {
   return prmt_sx(w, (e & 1) ? 0xB3A2u : 0x9180u);
 }
 
-__global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
+#ifndef MAP8_MAX_REGS
+#define MAP8_MAX_REGS 128      // measured: 96 / 112 / 128 / 140 -> 27.3 / 27.6 / 25.3 / 25.9 ms per 3 decodes of 21312 blocks
+#endif
+__global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
   extern __shared__ uint4 abuf8[];
   const int tid = threadIdx.x;
   const int gt = blockIdx.x * MAP8_THREADS + tid;
@@ -238,9 +248,14 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
       ckput(seg, a);
       const uint4 Sc = S, Pc = P;
       if (seg + 1 < nseg) { S = __ldg(sys4 + (seg + 1) * 8); P = __ldg(par4 + (seg + 1) * 8); }
+      if (seg * 8 + 8 <= W) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (seg * 8 + e < W) alpha8_step(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+        for (int e = 0; e < 8; ++e) alpha8_step(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (seg * 8 + e < W) alpha8_step(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+      }
     }
   }
   // ---- re-seed (TD8:299-316): lane l <- alpha[W] of lane l-1, lane 0 <- (0,-63..); 16-step re-run ----
@@ -273,14 +288,15 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
 
   // alpha[k0 .. k1) of segment `seg` (final values) -> shared memory entries 0..; leaves the chunk inputs in S, P
   uint4 S, P;
-  auto fill_alpha = [&](int seg) {
+  auto fill_alpha = [&](auto full, int seg) {
+    constexpr bool FULL = decltype(full)::value;                // all 8 steps of the segment exist
     const int k0 = seg * 8;
     S = __ldg(sys4 + seg * 8); P = __ldg(par4 + seg * 8);
     u32 x[8];
     ckget(seg == 0 ? CH0 : (seg == 1 ? CH8 : seg), x);          // steps 1..16 come from the re-run chain
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (k0 + e < W) {
+      if (FULL || k0 + e < W) {
         put(e, x);
         if (e < 7) alpha8_step(x, gamma8(unp8(S, e), unp8(P, e)));
       }
@@ -288,27 +304,29 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
     if (seg == 0) { ckget(A0, x); put(0, x); }                  // alpha[0]: the value of the second re-seed
     if (seg == 2) { ckget(CH16, x); put(0, x); }                // alpha[16]: last value of the chain
   };
-  // backward over one segment with beta[k1] in b: ext for k in [elo, ehi], beta steps for k >= blo
-  auto back_segment = [&](int seg, int elo, int ehi, int blo) {
+  // backward over one segment with beta[k1] in b: ext for k in [elo, ehi], beta steps for k >= blo.
+  // full = the segment has 8 steps, all of them in the ext range and all stepping beta (no per-step tests).
+  auto back_segment = [&](auto full, int seg, int elo, int ehi, int blo) {
+    constexpr bool FULL = decltype(full)::value;
     const int k0 = seg * 8;
-    fill_alpha(seg);
+    fill_alpha(full, seg);
     u32 o[8];
 #pragma unroll
     for (int e = 7; e >= 0; --e) {
       o[e] = 0;
       const int k = k0 + e;
-      if (k < W) {
+      if (FULL || k < W) {
         const G8 g = gamma8(unp8(S, e), unp8(P, e));
-        if (k >= elo && k <= ehi) {
+        if (FULL || (k >= elo && k <= ehi)) {
           u32 x[8];
           get(e, x);
           o[e] = ext8_step(x, b, g);
         }
-        if (k >= blo) beta8_step(b, g);
+        if (FULL || k >= blo) beta8_step(b, g);
       }
     }
     int8_t* dst = ext + seg * 128;
-    if (k0 >= elo && k0 + 7 <= ehi && k0 + 7 < W) {             // whole segment: one 16-byte store
+    if (FULL || (k0 >= elo && k0 + 7 <= ehi && k0 + 7 < W)) {   // whole segment: one 16-byte store
       *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420),
                                                   __byte_perm(o[4], o[5], 0x6420), __byte_perm(o[6], o[7], 0x6420));
     } else {
@@ -319,11 +337,16 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
       }
     }
   };
+  const std::true_type kFull{};
+  const std::false_type kPart{};
 
   // ---- beta pass 1 (TD8:505-650): from alpha[W], lane 15 <- 0; all W steps; ext where beta[k+1] is final ----
 #pragma unroll
   for (int s = 0; s < 8; ++s) b[s] = (t == 7) ? ((a[s] & 0xffffu) | (128u << 16)) : a[s];
-  for (int seg = nseg - 1; seg >= 0; --seg) back_segment(seg, 0, W - RERUN8 - 2, 0);
+  for (int seg = nseg - 1; seg >= 0; --seg) {
+    if (seg * 8 + 7 <= W - RERUN8 - 2) back_segment(kFull, seg, 0, W - RERUN8 - 2, 0);
+    else back_segment(kPart, seg, 0, W - RERUN8 - 2, 0);
+  }
   // ---- re-seed (TD8:652-666): lane l <- beta[0] of lane l+1, lane 15 <- 0; re-run of the last 16 steps ----
   auto shift_down = [&](u32 (&dst)[8], const u32 (&src)[8]) {
 #pragma unroll
@@ -338,12 +361,12 @@ __global__ void __launch_bounds__(MAP8_THREADS) k_map8(Td8Args p) {
 #pragma unroll
   for (int s = 0; s < 8; ++s) b[s] = bw[s];
   const int klo = max(W - RERUN8 - 1, 0);       // ext(W-2 .. W-17) uses the re-run's beta[W-1 .. W-16]
-  for (int seg = nseg - 1; seg >= 0 && seg * 8 + 7 >= klo; --seg) back_segment(seg, klo, W - 2, W - RERUN8);
+  for (int seg = nseg - 1; seg >= 0 && seg * 8 + 7 >= klo; --seg) back_segment(kPart, seg, klo, W - 2, W - RERUN8);
   // ---- ext(W-1) uses beta[W] of the SECOND re-seed: the same vector unless the re-run reached step 0 (K = 256) ----
   if (W == RERUN8) shift_down(bw, b);
 #pragma unroll
   for (int s = 0; s < 8; ++s) b[s] = bw[s];
-  back_segment(nseg - 1, W - 1, W - 1, W);
+  back_segment(kPart, nseg - 1, W - 1, W - 1, W);
 }
 
 // ------------------------------------------------------------------------------------
