@@ -143,6 +143,7 @@ static int ctx_get(int dev, DevCtx** out) {
     CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
     CU(cudaMemcpy(c.crc_xp, xp.data(), xp.size() * sizeof(u32), cudaMemcpyHostToDevice));
     CU(cudaFuncSetAttribute(k_map16<MAP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAP_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_demux16_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 6208 * (int)sizeof(int16_t)));
     c.dev = dev;
     c.ok = true;
     CU(cudaSetDevice(prev));
@@ -190,7 +191,7 @@ struct Profiler {
 struct Batch {
   Profiler prof;
   DevCtx* ctx = nullptr;
-  int cap = 0, n = 0, A = 0, max_iter = 0;
+  int cap = 0, n = 0, A = 0, max_iter = 0, max_K = 0;
   long slot_hw = 0, ckpt_words = 0;
   CbMeta* d_meta = nullptr;
   CbState* d_state = nullptr;
@@ -205,6 +206,7 @@ struct Batch {
     ctx = c;
     cap = ncb;
     int W = Kmax / 8;
+    max_K = Kmax;
     A = c4_words(W) * 2;
     slot_hw = (long)ARR_COUNT * A;
     ckpt_words = (long)((W + CKPT_S - 1) / CKPT_S + 1) * 32;
@@ -233,8 +235,10 @@ struct Batch {
   }
   // enqueue the whole 16-bit decode of blocks [lo, lo+cnt) (cnt < 0: all); returns #kernels launched or <0.
   // `part` selects the batch-maximum cell, so that parts of one batch can run as independent pipeline stages.
+  // fe_rm != nullptr: block i (of the whole batch) is rm block i and k_demux16 reads its input out of the dematched
+  // circular buffers (fused sub-block deinterleaving) instead of in_dev
   int decode16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st, int lo = 0, int cnt = -1,
-               int part = 0) {
+               int part = 0, const RmBlock* fe_rm = nullptr, const int16_t* fe_w = nullptr, const int16_t* fe_harq = nullptr) {
     int launches = 0;
     const int n = (cnt < 0) ? this->n : cnt;
     if (n <= 0) return 0;
@@ -252,6 +256,7 @@ struct Batch {
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
     x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
+    x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq;
     cudaMemsetAsync(nact[0], 0, sizeof(int), st);
     cudaMemsetAsync(d_batch_max, 0, sizeof(int), st);
     MapArgs mp;
@@ -273,7 +278,8 @@ struct Batch {
       ++launches;
     };
     prof.begin(0, st);
-    k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
+    if (fe_rm) k_demux16_t<true><<<n, XCHG_THREADS, (3 * A + 3 * 32 * ((max_K + 4 + 31) / 32)) * sizeof(int16_t), st>>>(x);
+    else k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
     prof.end(st);
     ++launches;
     compact_into(cur);
@@ -720,11 +726,14 @@ struct HostBatch {
     };
     int16_t* const hp = pool ? pool->d : nullptr;
     const size_t deint_smem = 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t);
-    auto front_end = [&](size_t jlo, size_t jhi) {            // dematch + deinterleave of rm blocks [jlo, jhi) on st
+    // when every block of the batch goes through the front end (and is a 16-bit block), sub-block deinterleaving is
+    // fused into k_demux16: the decoder input y is never materialised
+    const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
+    auto front_end = [&](size_t jlo, size_t jhi) {            // dematch (+ deinterleave) of rm blocks [jlo, jhi) on st
       const int cnt = (int)(jhi - jlo);
       k_rm_rx<<<cnt, RM_THREADS, deint_smem / 2, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp);   // one flag byte per slot
-      k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp);
-      g_launches += 2;
+      ++g_launches;
+      if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
@@ -784,7 +793,8 @@ struct HostBatch {
       const int lo = part_lo(part), hi = part_lo(part + 1);
       CU(cudaStreamWaitEvent(st, ev_part[part], 0));
       if (fe_parts) front_end(lo, hi);
-      rc = b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
+      rc = fuse_deint ? b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part, d_rm, d_w, hp)
+                      : b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
       if (rc < 0) return rc;
       // this part's decoded bytes go back while the next parts are still being copied in / decoded
       CU(cudaEventRecord(ev_done[part], st));
@@ -794,7 +804,7 @@ struct HostBatch {
     }
     if (trace) cudaEventRecord(ev[1], st);
     if (n16 > 0 && parts == 1) {
-      rc = b.decode16(d_in, d_out, d_status, st);
+      rc = fuse_deint ? b.decode16(d_in, d_out, d_status, st, 0, -1, 0, d_rm, d_w, hp) : b.decode16(d_in, d_out, d_status, st);
       if (rc < 0) return rc;
     }
     if (n > n16) {
@@ -1170,7 +1180,7 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   XchgArgs x;
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
   x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
-  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max; x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;
+  x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max; x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr; x.rm = nullptr; x.w_pool = nullptr; x.harq_pool = nullptr;
   cudaMemsetAsync(b.d_batch_max, 0, sizeof(int), hb.st);
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
   MapArgs mp;

@@ -12,6 +12,7 @@
 // recursions have a guarded non-saturating fast path.
 #pragma once
 #include "td_common.cuh"
+#include "rm_kernels.cuh"
 
 namespace oai {
 
@@ -37,6 +38,11 @@ struct XchgArgs {
   const int* active;            // packed list of the blocks still being decoded, or nullptr = all nblk blocks
   const int* nactive;
   int* nactive_next;            // k_x1_16 zeroes the counter of the list that k_compact builds after k_x2_16
+  // fused front end (k_demux16<true>): block i of the batch is rm block i; its decoder input is read straight out of
+  // the rate-dematched circular buffer w (sub-block deinterleaving on the fly) instead of a materialised y
+  const RmBlock* rm;
+  const int16_t* w_pool;
+  const int16_t* harq_pool;
 };
 
 // Active-block compaction: the kernels address blocks through a packed list of the blocks that are still being
@@ -135,7 +141,11 @@ __device__ __forceinline__ unsigned long long clmul32(u32 x, u32 y) {
 }
 
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
+// FE = false: y comes from the batch input.  FE = true: sub_block_deinterleaving_turbo (lte_rate_matching.c:193-243) is
+// applied on the fly to the block's circular buffer w, staged in shared memory behind the three demux arrays:
+// d[3j] = w[k(j)], d[3j+1] = w[Kpi+2k(j)], d[3j+5] = w[Kpi+2k(j)+1], k(j) = bitrev5(j&31)*RTC + (j>>5), y = d + 3*ND.
+template <bool FE>
+__global__ void __launch_bounds__(XCHG_THREADS) k_demux16_t(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int red[XCHG_THREADS / 32];
   const int blk = blockIdx.x;
@@ -146,17 +156,40 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
   const int K = m.K, A = p.A;
   const int16_t* y = p.in_base + (((long)m.in_off_hi << 32) | m.in_off_lo);
   int16_t* s0 = sm, *p1 = sm + A, *p2 = sm + 2 * A;
+  const int16_t* sw = sm + 3 * A;
+  uint32_t RTC = 0, Kpi = 0, ND = 0;
   for (int i = threadIdx.x; i < 3 * A / 2; i += XCHG_THREADS) reinterpret_cast<u32*>(sm)[i] = 0;
+  if (FE) {
+    const RmBlock b = p.rm[blk];
+    RTC = b.RTC; Kpi = b.Kpi; ND = b.ND;
+    const u32* w = reinterpret_cast<const u32*>((b.w_sel ? p.harq_pool : p.w_pool) + b.w_off);
+    u32* dst = reinterpret_cast<u32*>(sm + 3 * A);
+    for (uint32_t i = threadIdx.x; i < 3 * Kpi / 2; i += XCHG_THREADS) dst[i] = w[i];
+  }
   __syncthreads();
+  auto kof = [&](uint32_t j) -> uint32_t { return brev5(j & 31) * RTC + (j >> 5); };
+  // decoder input element idx (0 .. 3K+11): the reference's d[3*ND + idx]
+  auto ysrc = [&](int idx) -> int {
+    if (!FE) return y[idx];
+    const uint32_t q = 3 * ND + idx, r = q % 3;
+    const uint32_t k = kof(r == 2 ? (q - 5) / 3 : q / 3);
+    return r == 0 ? sw[k] : (r == 1 ? sw[Kpi + 2 * k] : sw[Kpi + 2 * k + 1]);
+  };
   int mx = 0;
   const uint16_t* H = p.pi_pool + m.pi_off;
   for (int pos = threadIdx.x; pos < K; pos += XCHG_THREADS) {
     const int h = H[pos];
-    const int v0 = y[3 * pos], v1 = y[3 * pos + 1], v2 = y[3 * pos + 2];
+    int v0, v1, v2;
+    if (FE) {
+      const uint32_t k0 = kof(ND + pos), k2 = kof(ND + pos - 1);      // ND >= 1 for every legal K (K+4 is never a multiple of 32)
+      v0 = sw[k0]; v1 = sw[Kpi + 2 * k0]; v2 = sw[Kpi + 2 * k2 + 1];
+    } else {
+      v0 = y[3 * pos]; v1 = y[3 * pos + 1]; v2 = y[3 * pos + 2];
+    }
     s0[h] = (int16_t)v0; p1[h] = (int16_t)v1; p2[h] = (int16_t)v2;
     mx = max(max(mx, abs(v0)), max(abs(v1), abs(v2)));
   }
-  if (threadIdx.x < 12) mx = max(mx, abs((int)y[3 * K + threadIdx.x]));
+  if (threadIdx.x < 12) mx = max(mx, abs(ysrc(3 * K + threadIdx.x)));
   __syncthreads();
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
   for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
@@ -176,7 +209,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
   if (threadIdx.x < 2) {
     // tail-bit beta start metrics in WRAPPING int16 (reference :474-520); the gamma of
     // the tail uses the saturating add/sub + >>1 of compute_gamma16 (:160-161)
-    const int16_t* tl = y + 3 * K + 6 * threadIdx.x;       // (x,z) x 3 of encoder 1 / 2
+    int tl[6];                                             // (x,z) x 3 of encoder 1 / 2
+    for (int i = 0; i < 6; ++i) tl[i] = ysrc(3 * K + 6 * threadIdx.x + i);
     // all values are kept as 32-bit ints and wrapped to int16 explicitly (w16): nvcc 12.9 turned
     // an int16_t max chain here into VIMNMX3.S16x2 on half-extended registers and picked a
     // wrong maximum for some inputs
@@ -206,6 +240,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_demux16(XchgArgs p) {
     if (m.max_iter == 0 && p.status_out) p.status_out[blk] = 1;
   }
 }
+
+#define k_demux16 k_demux16_t<false>
 
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
