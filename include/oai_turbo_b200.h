@@ -134,6 +134,14 @@ typedef struct {
    * this block lives in slot harq_slot of the pool on the GPU, `w` is ignored and nothing of it crosses PCIe */
   struct oai_turbo_harq_pool *harq_pool;
   uint32_t  harq_slot;
+  /* descrambling of the soft bits in the front end (optional; downlink: dlsch_unscrambling,
+   * openair1/PHY/LTE_TRANSPORT/dlsch_scrambling.c:99-138, which the UE runs on dlsch_llr right before dlsch_decoding):
+   * with scr_enable != 0, `in` holds the still scrambled soft bits of this block; scr_c_init is the codeword's c_init
+   * (36.211 6.3.1: (rnti<<14) + (q<<13) + ((Ns>>1)<<9) + Nid_cell) and scr_offset the position of the block's first
+   * soft bit in the codeword (the reference's r_offset).  Bit 0 of the sequence negates the LLR, like the reference. */
+  uint32_t  scr_c_init;
+  uint32_t  scr_offset;
+  uint8_t   scr_enable;
 } oai_cb_desc_t;
 
 /* HARQ soft-buffer pool in HBM.  The reference keeps w[r] (int16[3*Kpi]) per (UE, HARQ process, code block) in host

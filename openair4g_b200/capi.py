@@ -42,7 +42,8 @@ class CbDesc(C.Structure):
                 ("dematch_enable", C.c_uint8), ("w", C.c_void_p), ("G", C.c_uint32),
                 ("Nsoft", C.c_uint32), ("C", C.c_uint8), ("r", C.c_uint8), ("rvidx", C.c_uint8),
                 ("clear", C.c_uint8), ("Qm", C.c_uint8), ("Nl", C.c_uint8), ("Mdlharq", C.c_uint8),
-                ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32), ("harq_pool", C.c_void_p), ("harq_slot", C.c_uint32)]
+                ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32), ("harq_pool", C.c_void_p), ("harq_slot", C.c_uint32),
+                ("scr_c_init", C.c_uint32), ("scr_offset", C.c_uint32), ("scr_enable", C.c_uint8)]
 
 
 _stats7 = [C.c_void_p] * 7
@@ -171,6 +172,8 @@ def decode_batch(blocks, flags=0, gpu=-1):
                 d.w = w.ctypes.data
             d.G, d.C, d.r, d.rvidx, d.clear, d.Qm = dm["G"], dm["C"], dm["r"], dm["rvidx"], dm["clear"], dm["Qm"]
             d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = dm.get("Nl", 1), dm.get("Mdlharq", 8), dm.get("Kmimo", 1), dm.get("Nsoft", 1827072)
+            if dm.get("scr_c_init") is not None:         # still scrambled soft bits: c_init of the codeword, r_offset
+                d.scr_enable, d.scr_c_init, d.scr_offset = 1, dm["scr_c_init"], dm.get("scr_offset", 0)
             if dm.get("harq_pool") is not None:          # device-resident soft buffer: (HarqPool, slot)
                 d.harq_pool = dm["harq_pool"].handle
                 d.harq_slot = dm["harq_slot"]

@@ -466,6 +466,8 @@ struct HostBatch {
   int16_t* h_e = nullptr; int16_t* d_e = nullptr;
   int16_t* h_w = nullptr; int16_t* d_w = nullptr;
   RmBlock* d_rm = nullptr;
+  GoldSeq* d_gseq = nullptr; uint32_t* d_gold = nullptr; int cap_gseq = 0; size_t cap_gold = 0;   // scrambling sequences
+  std::vector<GoldSeq> gseq;
   std::vector<RmBlock> rm;
   std::vector<int> rm_desc;        // descriptor index of each RmBlock
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // OAI_TURBO_TRACE: submit, H2D done, kernels done, D2H done
@@ -556,6 +558,9 @@ struct HostBatch {
     if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); h_e = nullptr; d_e = nullptr; }
     if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); h_w = nullptr; d_w = nullptr; }
     if (d_rm) { cudaFree(d_rm); d_rm = nullptr; }
+    if (d_gseq) { cudaFree(d_gseq); d_gseq = nullptr; }
+    if (d_gold) { cudaFree(d_gold); d_gold = nullptr; }
+    cap_gseq = 0; cap_gold = 0;
     cap_e = cap_w = 0; cap_rm = 0;
     if (h_in) { cudaFreeHost(h_in); h_in = nullptr; }
     if (d_in) { cudaFree(d_in); d_in = nullptr; }
@@ -672,6 +677,9 @@ struct HostBatch {
     size_t e_hw = 0, w_hw = 0;
     oai_turbo_harq_pool* pool = nullptr;
     const int16_t* prev_e_end = nullptr;
+    gseq.clear();
+    std::unordered_map<uint32_t, int> seq_of;                // c_init -> index in gseq
+    std::vector<int> rm_seq;                                 // per rm block: its sequence or -1
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
       make_meta(b.ctx, d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable ? 1 : 0, (long)in_off[i], (long)out_off[i], &meta[i],
@@ -704,6 +712,15 @@ struct HostBatch {
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
         e_hw += (size_t)q.E;
         if (!d.harq_pool) w_hw += (size_t)3 * q.Kpi;
+        rb.gold_off = 0xffffffffu; rb.scr_off = d.scr_offset;
+        int sq = -1;
+        if (d.scr_enable) {
+          auto it = seq_of.find(d.scr_c_init);
+          if (it == seq_of.end()) { sq = (int)gseq.size(); seq_of[d.scr_c_init] = sq; gseq.push_back(GoldSeq{d.scr_c_init, 0u, 0u}); }
+          else sq = it->second;
+          gseq[sq].nwords = std::max(gseq[sq].nwords, (d.scr_offset + q.E + 31) / 32);
+        }
+        rm_seq.push_back(sq);
         rm.push_back(rb); rm_desc.push_back(order[i]);
       }
     }
@@ -731,13 +748,23 @@ struct HostBatch {
     const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
     auto front_end = [&](size_t jlo, size_t jhi) {            // dematch (+ deinterleave) of rm blocks [jlo, jhi) on st
       const int cnt = (int)(jhi - jlo);
-      k_rm_rx<<<cnt, RM_THREADS, deint_smem / 2, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp);   // one flag byte per slot
+      k_rm_rx<<<cnt, RM_THREADS, deint_smem / 2, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);   // one flag byte per slot
       ++g_launches;
       if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
       if (rc) return rc;
+      if (!gseq.empty()) {                                   // scrambling sequences of the codewords of this batch
+        uint32_t words = 0;
+        for (auto& g : gseq) { g.off = words; words += g.nwords; }
+        for (size_t j = 0; j < rm.size(); ++j) if (rm_seq[j] >= 0) rm[j].gold_off = gseq[rm_seq[j]].off;
+        if ((int)gseq.size() > cap_gseq) { if (d_gseq) cudaFree(d_gseq); cap_gseq = (int)gseq.size(); CU(cudaMalloc(&d_gseq, sizeof(GoldSeq) * cap_gseq)); }
+        if (words > cap_gold) { if (d_gold) cudaFree(d_gold); cap_gold = words; CU(cudaMalloc(&d_gold, sizeof(uint32_t) * cap_gold)); }
+        CU(cudaMemcpyAsync(d_gseq, gseq.data(), sizeof(GoldSeq) * gseq.size(), cudaMemcpyHostToDevice, st));
+        k_gold<<<((int)gseq.size() + 63) / 64, 64, 0, st>>>(d_gseq, (int)gseq.size(), d_gold);
+        ++g_launches;
+      }
       CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
       if (!fe_parts) {
         rc = copy_e_runs(0, rm.size(), st);
@@ -1118,7 +1145,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
   RmBlock b;
   memset(&b, 0, sizeof(b));
   b.K = 32 * RTC - 4; b.F = 0; b.RTC = RTC; b.Kpi = q.Kpi; b.ND = 0; b.Ncb = q.Ncb; b.k0 = q.k0; b.E = q.E; b.clear = clear;
-  b.w_off = 0; b.e_off_lo = 0; b.e_off_hi = 0; b.dummy_off = 0;
+  b.w_off = 0; b.e_off_lo = 0; b.e_off_hi = 0; b.dummy_off = 0; b.gold_off = 0xffffffffu;
   char* h = (char*)sc.h; char* d = (char*)sc.d;
   memcpy(h, &b, sizeof(b));
   if (clear != 1) memcpy(h + o_w, w, (size_t)q.Ncb * 2);

@@ -27,7 +27,30 @@ struct RmBlock {
   uint32_t e_off_lo, e_off_hi;   // int16 offset of this block's soft bits in the input pool
   uint32_t dummy_off;       // byte offset of a caller-provided NULL map, or 0xffffffff: derive from (K,F)
   uint32_t y_off_lo, y_off_hi;   // int16 offset of the decoder input y (3K+12) written by k_deint
+  uint32_t gold_off;        // word offset of this block's scrambling sequence in the Gold pool, 0xffffffff: soft bits are not scrambled
+  uint32_t scr_off;         // position of this block's first soft bit in that sequence (r_offset, dlsch_decoding.c:333-347)
 };
+
+// Pseudo-random sequences of 36.211 7.2, 32 bits per step like the reference's lte_gold_generic
+// (LTE_REFSIG/lte_gold.c:151-180): x1 starts from 1 + 2^31, x2 from c_init completed with its 32nd bit, the
+// first 1600 outputs are skipped.  One thread per sequence (a codeword needs at most ~2 900 words); bit j of word i
+// is c(32 i + j).
+struct GoldSeq { uint32_t c_init, off, nwords; };
+__global__ void k_gold(const GoldSeq* seqs, int nseq, uint32_t* pool) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseq) return;
+  const GoldSeq q = seqs[i];
+  uint32_t x1 = 1u + (1u << 31), x2 = q.c_init;
+  x2 = x2 ^ ((x2 ^ (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3)) << 31);
+  auto step = [&]() {
+    x1 = (x1 >> 1) ^ (x1 >> 4);
+    x1 = x1 ^ (x1 << 31) ^ (x1 << 28);
+    x2 = (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3) ^ (x2 >> 4);
+    x2 = x2 ^ (x2 << 31) ^ (x2 << 30) ^ (x2 << 29) ^ (x2 << 28);
+  };
+  for (int n = 1; n < 50; ++n) step();
+  for (uint32_t w = 0; w < q.nwords; ++w) { step(); pool[q.off + w] = x1 ^ x2; }
+}
 
 __device__ __forceinline__ uint32_t brev5(uint32_t c) { return __brev(c) >> 27; }
 
@@ -57,9 +80,13 @@ __global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, u
 // Pass 1 marks the slots that carry soft bits and counts them (N in [0,Ncb), and those before the start index);
 // pass 2 walks the buffer in coalesced chunks of 256 slots with a running block-wide prefix count, so that every
 // thread knows the rank of its slot on the reference's walk and adds e[rank], e[rank+N], ... to it.
+// With gold != nullptr and b.gold_off set, the soft bits are descrambled on the fly (dlsch_unscrambling,
+// LTE_TRANSPORT/dlsch_scrambling.c:99-138): soft bit k is NEGATED where scrambling bit scr_off + k is 0.  (The reference
+// stores the product back as int16, so -32768 stays -32768; under the int16 wrap of the accumulation below, adding
+// +32768 instead is the same.)
 __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
                                                       const int16_t* e_pool, const uint8_t* dummy_pool,
-                                                      int16_t* harq_pool = nullptr) {
+                                                      int16_t* harq_pool = nullptr, const uint32_t* gold = nullptr) {
   extern __shared__ uint8_t sflag[];
   __shared__ uint32_t s_w[RM_THREADS / 32], s_a[RM_THREADS / 32], s_b[RM_THREADS / 32];
   const int blk = blockIdx.x;
@@ -69,6 +96,7 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
   const int16_t* e = e_pool + (((long)b.e_off_hi << 32) | b.e_off_lo);
   const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
   const uint32_t magic = 0xffffffffu / b.RTC + 1;
+  const uint32_t* gs = (gold && b.gold_off != 0xffffffffu) ? gold + b.gold_off : nullptr;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // the first reference loop runs only when k0 < Ncb (:747)
   const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
@@ -102,7 +130,15 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
       if (f) {
         const uint32_t c = base + woff + __popc(bal & ((1u << lane) - 1u));
         const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
-        for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+        if (gs) {
+          for (uint32_t k = rank; k < b.E; k += N) {
+            const uint32_t pos = b.scr_off + k;
+            const int v = e[k];
+            acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
+          }
+        } else {
+          for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+        }
       }
       w[i] = (int16_t)acc;                               // wraps like the reference's int16 +=
     }

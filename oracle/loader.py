@@ -53,6 +53,12 @@ def port():
         getattr(L, f).argtypes = [u8p, C.c_int]
         getattr(L, f).restype = C.c_uint32
     L.orc_lte_segmentation.argtypes = [C.c_uint32] + [u32ref] * 6
+    L.orc_lte_gold_generic.argtypes = [u32ref, u32ref, C.c_uint8]
+    L.orc_lte_gold_generic.restype = C.c_uint32
+    L.orc_gold_words.argtypes = [C.c_uint32, C.c_void_p, C.c_int]
+    L.orc_gold_words.restype = None
+    L.orc_dlsch_unscrambling.argtypes = [C.c_uint32, i16p, C.c_int]
+    L.orc_dlsch_unscrambling.restype = None
     L.orc_generate_dummy_w.argtypes = [C.c_uint32, u8p, C.c_uint8]
     L.orc_generate_dummy_w.restype = C.c_uint32
     L.orc_lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, i16p, u8p, i16p, C.c_uint8,
@@ -101,6 +107,8 @@ def ref():
         getattr(L, f).argtypes = [u8p, C.c_int]
         getattr(L, f).restype = C.c_uint32
     L.ref_lte_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [u32ref] * 6
+    L.ref_lte_gold_generic.argtypes = [u32ref, u32ref, C.c_uint8]
+    L.ref_lte_gold_generic.restype = C.c_uint32
     L.ref_generate_dummy_w.argtypes = [C.c_uint32, u8p, C.c_uint8]
     L.ref_generate_dummy_w.restype = C.c_uint32
     L.ref_lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, i16p, u8p, i16p, C.c_uint8,

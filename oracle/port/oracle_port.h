@@ -78,4 +78,9 @@ void orc_turbo_decoder16_batch(const int16_t *y, int y_stride, uint8_t *out, int
 #ifdef __cplusplus
 }
 #endif
+/* Gold sequence (LTE_REFSIG/lte_gold.c:151-180) and DL descrambling (LTE_TRANSPORT/dlsch_scrambling.c:99-138) */
+uint32_t orc_lte_gold_generic(uint32_t *x1, uint32_t *x2, uint8_t reset);
+void orc_gold_words(uint32_t c_init, uint32_t *words, int nwords);
+void orc_dlsch_unscrambling(uint32_t c_init, int16_t *llr, int n);
+
 #endif

@@ -178,3 +178,47 @@ def test_device_resident_harq_pool(capi):
             assert np.array_equal(pool.read(slots[i], Ncb), w_ref[i][:Ncb]), (rnd, infos[i])
     assert {w for _, w in want} != {7}
     pool.close()
+
+
+def test_front_end_descrambling(capi):
+    """scr_enable: the soft bits arrive still scrambled (downlink: dlsch_unscrambling runs right before dlsch_decoding in
+    the UE); the GPU front end applies the Gold-sequence signs while dematching.  Oracle = port of dlsch_unscrambling
+    (its sequence generator pinned to the compiled reference) followed by the oracle chain.  dlsim shape (13 blocks of one
+    codeword, different r_offsets) + a second codeword with another c_init + full-range values incl. -32768."""
+    P = loader.port()
+    K, F, G, Cb, Qm = 5824, 0, 90000, 13, 6
+    rng = np.random.default_rng(99)
+    blocks, want, w_gpu, w_ref = [], [], [], []
+    for cw, c_init in enumerate([(0x1234 << 14) + (0 << 13) + (7 << 9) + 101, (0xBEEF << 14) + (1 << 13) + (3 << 9) + 17]):
+        es, offs, off = [], [], 0
+        for r in range(Cb):
+            info, e, E, RTC = _tx(K, 70 + 20 * cw + r, 0, G, Cb, Qm, r, 0, 8, 0.3)
+            if cw == 1 and r == 5:
+                e = rng.integers(-32768, 32768, size=E).astype(np.int16)      # saturating / wrapping values
+                e[:4] = [-32768, 32767, -32768, 0]
+            es.append(e); offs.append(off); off += E
+        assert off == G
+        clean = np.concatenate(es)
+        n_loop = 32 * (1 + G // 32)
+        scr = np.zeros(n_loop, dtype=np.int16)
+        scr[:G] = clean
+        P.orc_dlsch_unscrambling(c_init, scr, n_loop)        # the sign flip is its own inverse (-32768 maps to itself)
+        scrambled = scr[:G].copy()
+        back = np.zeros(n_loop, dtype=np.int16)
+        back[:G] = scrambled
+        P.orc_dlsch_unscrambling(c_init, back, n_loop)       # what the reference hands to dlsch_decoding
+        for r in range(Cb):
+            E = es[r].size
+            e_descr = back[offs[r]:offs[r] + E].copy()
+            wg = np.zeros(3 * 32 * ((K + 4 + 31) // 32), dtype=np.int16)
+            wr = wg.copy()
+            blocks.append({"y": scrambled[offs[r]:offs[r] + E].copy(), "K": K, "max_iterations": 6, "crc_type": 1, "F": 0, "tb_id": cw,
+                           "dematch": {"G": G, "C": Cb, "r": r, "rvidx": 0, "clear": 1, "Qm": Qm, "w": wg,
+                                       "scr_c_init": c_init, "scr_offset": offs[r]}})
+            want.append(_oracle_chain(K, F, G, Cb, Qm, r, 0, 1, e_descr, wr, 6, 1))
+            w_gpu.append(wg); w_ref.append(wr)
+    outs, status = capi.decode_batch(blocks)
+    for i, ((wb, wrr), ob, st) in enumerate(zip(want, outs, status)):
+        assert st == wrr and np.array_equal(ob, wb), (i, st, wrr)
+        assert np.array_equal(w_gpu[i], w_ref[i]), i
+    assert 2 in [w for _, w in want]

@@ -233,3 +233,35 @@ def test_td8_all_sizes_of_its_domain(ref):
         assert loader.ref_decode16(y, 512, max_it, crc, which=8)[1] == loader.port_decode8(y, 512, max_it, crc)[1]
     y = np.zeros(3 * 40 + 12 + 64, dtype=np.int16)
     assert loader.port_decode8(y, 40, 4, 1)[1] == 254            # outside the parity domain (reference overruns)
+
+
+def test_gold_sequence_matches_reference(port, ref):
+    """lte_gold_generic (LTE_REFSIG/lte_gold.c:151-180): port vs the compiled reference, word by word, for DL c_init
+    values (rnti<<14 + q<<13 + (Ns>>1)<<9 + Nid_cell) and arbitrary 31-bit ones; plus the 36.211 7.2 definition."""
+    rng = np.random.default_rng(7)
+    inits = [0, 1, (0x1234 << 14) + (0 << 13) + (7 << 9) + 101, (0xFFFF << 14) + (1 << 13) + (9 << 9) + 503] + \
+        [int(v) for v in rng.integers(0, 1 << 31, size=12)]
+    for c_init in inits:
+        a1, a2, b1, b2 = C.c_uint32(0), C.c_uint32(c_init), C.c_uint32(0), C.c_uint32(c_init)
+        for i in range(300):
+            assert port.orc_lte_gold_generic(C.byref(a1), C.byref(a2), 1 if i == 0 else 0) == \
+                ref.ref_lte_gold_generic(C.byref(b1), C.byref(b2), 1 if i == 0 else 0), (c_init, i)
+    # the sequence is the standard's c(n) = x1(n+1600) xor x2(n+1600)
+    c_init = inits[2]
+    x1 = [1] + [0] * 30
+    x2 = [(c_init >> i) & 1 for i in range(31)]
+    for n in range(1600 + 96):
+        x1.append(x1[n + 3] ^ x1[n])
+        x2.append(x2[n + 3] ^ x2[n + 2] ^ x2[n + 1] ^ x2[n])
+    words = np.zeros(3, dtype=np.uint32)
+    port.orc_gold_words(c_init, words.ctypes.data, 3)
+    for n in range(96):
+        assert ((int(words[n >> 5]) >> (n & 31)) & 1) == (x1[n + 1600] ^ x2[n + 1600]), n
+    # descrambling: sign 2c-1, int16 wrap of -32768
+    llr = np.array([100, -100, -32768, 32767] * 16, dtype=np.int16)
+    want = llr.copy()
+    port.orc_dlsch_unscrambling(c_init, llr, llr.size)
+    for k in range(llr.size):
+        c = (int(words[k >> 5]) >> (k & 31)) & 1
+        v = int(want[k]) if c else -int(want[k])
+        assert int(llr[k]) == ((v + 32768) % 65536) - 32768, k
