@@ -10,7 +10,8 @@ The channel is AWGN per resource element with a max-log soft demapper and a fixe
 (SC-FDMA / OFDM processing, channel estimation and the UL channel interleaver are upstream
 of the hot path and not modelled).  Every subframe goes to the GPU through ONE batched submit
 with the fused front end (rate dematching + sub-block deinterleaving + turbo decoding);
-HARQ rounds use rv 0,2,3,1 and combine in the caller-owned w buffers like the reference.
+HARQ rounds use rv 0,2,3,1 and combine in the caller-owned w buffers like the reference.  On the downlink the codeword
+is scrambled (36.211 6.3.1) and the front end descrambles on the GPU (dlsch_unscrambling fused into rate dematching).
 """
 import time
 from dataclasses import dataclass
@@ -32,6 +33,15 @@ class LinkConfig:
     Nl: int = 1
     Mdlharq: int = 8
     Kmimo: int = 1
+    # downlink scrambling (36.211 6.3.1): c_init = (rnti<<14) + (q<<13) + ((Ns>>1)<<9) + Nid_cell; dlsim defaults:
+    # n_rnti 0x1234, subframe 7, Nid_cell 0
+    rnti: int = 0x1234
+    subframe: int = 7
+    nid_cell: int = 0
+
+    @property
+    def c_init(self):
+        return (self.rnti << 14) + (self.subframe << 9) + self.nid_cell
 
 
 ULSIM_25PRB_MCS16 = LinkConfig("ulsim 25 PRB MCS16", 7736, 25 * 12 * 12 * 4, 4, False)
@@ -98,17 +108,28 @@ class LinkSim:
         return cb, d.reshape(n, C, 3 * K + 12)
 
     def transmit(self, d, rv, snr_db):
-        """coded blocks (n, C, 3K+12) -> list over r of int16 soft bits e (n, E_r) after AWGN + demapping."""
+        """coded blocks (n, C, 3K+12) -> list over r of int16 soft bits e (n, E_r) after AWGN + demapping, and the
+        position of each block's first bit in the codeword.  Downlink: the codeword is scrambled before modulation
+        (dlsch_scrambling) and the soft bits are returned STILL SCRAMBLED in the reference's demodulator convention
+        (positive = bit 0), i.e. what dlsch_unscrambling expects: it multiplies by 2c-1."""
         cfg = self.cfg
         n0 = 10.0 ** (-snr_db / 10.0)
-        es = []
+        es, offs, off = [], [], 0
+        c = tx.gold_sequence(cfg.c_init, cfg.G) if cfg.downlink else None
         for r in range(self.C):
             bits, E = tx.rate_match(d[:, r], self.K, self.F if r == 0 else 0, cfg.G, self.C, cfg.Qm, cfg.Nl, r, rv,
                                     cfg.Mdlharq, cfg.Kmimo)
+            if cfg.downlink:
+                bits = bits ^ c[None, off:off + E]
             s = modulate(bits, cfg.Qm)
             s = s + np.sqrt(n0 / 2) * (self.rng.standard_normal(s.shape) + 1j * self.rng.standard_normal(s.shape))
-            es.append(demap_maxlog(s, cfg.Qm, n0, self.scale))
-        return es
+            e = demap_maxlog(s, cfg.Qm, n0, self.scale)
+            if cfg.downlink:
+                e = (-np.clip(e, -32767, 32767)).astype(np.int16)
+            es.append(e)
+            offs.append(off)
+            off += E
+        return es, offs
 
     def run(self, snr_db, n_subframes, max_rounds=1, capi=None):
         """Monte-Carlo over n_subframes transport blocks (all submitted together each HARQ round).
@@ -130,7 +151,7 @@ class LinkSim:
                 res["tb_err"].append(0)
                 res["cb_err"].append(0)
                 continue
-            es = self.transmit(d[idx], RV_SEQ[rnd % 4], snr_db)
+            es, offs = self.transmit(d[idx], RV_SEQ[rnd % 4], snr_db)
             blocks = []
             for ii, sf in enumerate(idx):
                 for r in range(C):
@@ -139,7 +160,8 @@ class LinkSim:
                                    "tb_id": int(sf),
                                    "dematch": {"G": cfg.G, "C": C, "r": r, "rvidx": RV_SEQ[rnd % 4], "clear": 1 if rnd == 0 else 0,
                                                "Qm": cfg.Qm, "Nl": cfg.Nl, "Mdlharq": cfg.Mdlharq, "Kmimo": cfg.Kmimo,
-                                               "w": w[sf, r]}})
+                                               "w": w[sf, r],
+                                               "scr_c_init": cfg.c_init if cfg.downlink else None, "scr_offset": offs[r]}})
             t0 = time.perf_counter()
             outs, status = capi.decode_batch(blocks, flags=capi.BATCH_DL_STOP_AFTER_FAILURE if cfg.downlink else 0)
             res["gpu_s"] += time.perf_counter() - t0

@@ -122,6 +122,24 @@ def turbo_encode(c):
     return out
 
 
+@functools.lru_cache(maxsize=64)
+def gold_sequence(c_init, n):
+    """Scrambling sequence c(0..n-1) of 36.211 7.2 (x1 from 1, x2 from c_init, Nc = 1600) as a 0/1 uint8 array.
+    Reference counterpart: lte_gold_generic (openair1/PHY/LTE_REFSIG/lte_gold.c:151-180)."""
+    M31 = (1 << 31) - 1
+    x1, x2 = 1, c_init & M31
+    total = 1600 + n
+    # 31-bit Fibonacci LFSRs advanced bit by bit on Python ints, output collected in blocks
+    out = np.zeros(total, dtype=np.uint8)
+    for i in range(total):
+        out[i] = (x1 ^ x2) & 1
+        f1 = ((x1 >> 3) ^ x1) & 1
+        f2 = ((x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1) ^ x2) & 1
+        x1 = (x1 >> 1) | (f1 << 30)
+        x2 = (x2 >> 1) | (f2 << 30)
+    return out[1600:].copy()
+
+
 @functools.lru_cache(maxsize=None)
 def _interleave_index(K):
     """For w index j (0..3*Kpi): index into the d stream (3*(K+4) entries) or -1 for a NULL slot."""

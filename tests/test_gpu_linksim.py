@@ -47,7 +47,15 @@ def oracle_check(rec, llr8=0):
             P.orc_generate_dummy_w(D, dw, F)
             E = C.c_uint32(0)
             w = w0.copy()
-            assert P.orc_lte_rate_matching_turbo_rx(RTC, dm["G"], w, dw, b["y"], dm["C"], 1827072, dm["Mdlharq"], dm["Kmimo"],
+            yy = b["y"]
+            if dm.get("scr_c_init") is not None:               # dlsch_unscrambling of this block's slice of the codeword
+                off, nb = dm["scr_offset"], b["y"].size
+                words = np.zeros((off + nb + 31) // 32, dtype=np.uint32)
+                P.orc_gold_words(dm["scr_c_init"], words.ctypes.data, words.size)
+                pos = off + np.arange(nb)
+                cbit = (words[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1
+                yy = np.where(cbit == 1, b["y"].astype(np.int32), -b["y"].astype(np.int32)).astype(np.int16)
+            assert P.orc_lte_rate_matching_turbo_rx(RTC, dm["G"], w, dw, yy, dm["C"], 1827072, dm["Mdlharq"], dm["Kmimo"],
                                                     dm["rvidx"], dm["clear"], dm["Qm"], dm["Nl"], dm["r"], C.byref(E)) == 0
             assert np.array_equal(w, w1), "HARQ buffer differs from the oracle"
             if flags and b["tb_id"] in failed_tb:
