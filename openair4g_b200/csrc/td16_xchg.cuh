@@ -144,8 +144,11 @@ __device__ __forceinline__ unsigned long long clmul32(u32 x, u32 y) {
 // FE = false: y comes from the batch input.  FE = true: sub_block_deinterleaving_turbo (lte_rate_matching.c:193-243) is
 // applied on the fly to the block's circular buffer w, staged in shared memory behind the three demux arrays:
 // d[3j] = w[k(j)], d[3j+1] = w[Kpi+2k(j)], d[3j+5] = w[Kpi+2k(j)+1], k(j) = bitrev5(j&31)*RTC + (j>>5), y = d + 3*ND.
+#ifndef DEMUX_MIN_CTAS
+#define DEMUX_MIN_CTAS 6
+#endif
 template <bool FE>
-__global__ void __launch_bounds__(XCHG_THREADS) k_demux16_t(XchgArgs p) {
+__global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int red[XCHG_THREADS / 32];
   const int blk = blockIdx.x;
@@ -379,7 +382,10 @@ __device__ __forceinline__ bool block_crc_check(u32 bits, uint8_t* sbytes, uint8
 }
 
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XCHG_THREADS) k_x2_16(XchgArgs p) {
+#ifndef X2_MIN_CTAS
+#define X2_MIN_CTAS 8      // 32 registers -> 8 CTAs/SM (shared-memory limit); measured 6 % faster than 40 registers / 6 CTAs
+#endif
+__global__ void __launch_bounds__(XCHG_THREADS, X2_MIN_CTAS) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
   __shared__ u32 xred[2 * XCHG_THREADS / 32];
