@@ -419,7 +419,7 @@ __device__ __forceinline__ u32 hd_nibbles8(const uint4& d) {
   return l0 | (l1 << 8);
 }
 
-__global__ void __launch_bounds__(XCHG_THREADS) k_x2_8(Td8Args p) {
+__global__ void __launch_bounds__(XCHG_THREADS, 8) k_x2_8(Td8Args p) {
   extern __shared__ int8_t sm8[];
   __shared__ u32 xred[2 * XCHG_THREADS / 32];
   __shared__ __align__(16) uint8_t sbytes[768 + 32];
