@@ -347,7 +347,7 @@ def run_b200(args):
     achieved = bytes_per_launch / (map_ms * 1e-3) / 1e9 if n_map else 0.0
     kernel_ms_total = sum(prof_ms)
     # dram__bytes_read.sum + dram__bytes_write.sum per k_map16 launch of 23680 blocks, ncu --set full capture
-    # profiles/r1h_ncu_full_summary.txt (mean of the three captured launches), scaled to this batch size
+    # profiles/r1o_ncu_full_all_summary.txt (mean of the three captured launches; unchanged since r1h), scaled to this batch size
     traffic = 1.444e9 * B / 23680.0 if K == K_BITS else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_map16", "avg_launch_ms": map_ms, "launches_timed": n_map,

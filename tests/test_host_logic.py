@@ -19,3 +19,17 @@ def test_segmentation_params_match_oracle(port):
         if r1 == 0:
             assert tuple(got[k] for k in ("C", "Cplus", "Cminus", "Kplus", "Kminus", "F")) == want, (B, got, want)
     assert capi.lte_segmentation_params(75376 + 24)[1] == {"C": 13, "Cplus": 13, "Cminus": 0, "Kplus": 5824, "Kminus": 5760, "F": 0}
+
+
+def test_harness_gold_sequence_matches_oracle(port):
+    """The harness' own 36.211 7.2 sequence generator (openair4g_b200/sim/txchain.py) against the oracle port of
+    lte_gold_generic (pinned to the compiled reference in test_oracle_pin.py)."""
+    import numpy as np
+    from openair4g_b200.sim import txchain
+    for c_init in (0, (0x1234 << 14) + (7 << 9), (0xFFFF << 14) + (1 << 13) + (9 << 9) + 503, 0x7FFFFFFF):
+        n = 32 * 40
+        words = np.zeros(n // 32, dtype=np.uint32)
+        port.orc_gold_words(c_init, words.ctypes.data, words.size)
+        pos = np.arange(n)
+        want = ((words[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1).astype(np.uint8)
+        assert np.array_equal(txchain.gold_sequence(c_init, n), want), hex(c_init)
