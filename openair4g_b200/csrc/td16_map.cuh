@@ -279,41 +279,11 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
 // =====================================================================================
 struct FC { u32 X, Y, Z; };
 
-#ifndef MAP_CACHE_HINTS
-#define MAP_CACHE_HINTS 0
-#endif
-// Optional L2 evict_first hints for data that is not reused soon (the backward sweep's reads, the ext
-// output); measured neutral to slightly negative, off by default.
-__device__ __forceinline__ unsigned long long l2_policy_stream() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint4 ldg_hint(const uint4* p, unsigned long long pol) {
-#if MAP_CACHE_HINTS
-  uint4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
-__device__ __forceinline__ void stg_hint(uint4* p, const uint4& v, unsigned long long pol) {
-#if MAP_CACHE_HINTS
-  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol));
-#else
-  *p = v;
-#endif
-}
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// one instruction warms L2 with `bytes` contiguous bytes (multiple of 16, 16-byte aligned address)
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
-}
-#ifndef MAP_PF_MODE
-#define MAP_PF_MODE 0     // 0: one prefetch.global.L2 per 64-byte chunk; 1: + the second 32-byte sector; 2: bulk per segment
-#endif
+// Measured and rejected (profiles/r1g_sweep_*, r1i_sweep_*, r1k_sweep_*): L2 evict_first / evict_last cache hints on the
+// streams (neutral to -2 %), a second prefetch per 64-byte chunk (neutral), one cp.async.bulk.prefetch.L2 per segment
+// (-9 %), prefetch distances of 2 / 4 / 5 / 6 segments (0 to -8 % against 3), register prefetch two segments ahead in
+// the forward sweep (-1 %).
 
 __device__ __forceinline__ u32 vaddmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
 
@@ -454,16 +424,6 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   for (int j = 0; j < NCH; ++j)
     if (j < nchunk) { sb[j] = __ldg(sys4 + j * 4); pb[j] = ldp(j); }
   const int nfull = W / S;                                     // segments with all 16 steps
-  const unsigned long long pol_stream = l2_policy_stream();
-#ifndef MAP_FWD_DIST2
-#define MAP_FWD_DIST2 0
-#endif
-#if MAP_FWD_DIST2
-  uint4 sc[NCH], pc[NCH];                                      // segment seg+1 (registers are free in this phase)
-#pragma unroll
-  for (int j = 0; j < NCH; ++j)
-    if (NCH + j < nchunk) { sc[j] = __ldg(sys4 + (NCH + j) * 4); pc[j] = ldp(NCH + j); }
-#endif
   for (int seg = 0; seg < nfull; ++seg) {
     if (PF > 0) {                                              // thread t warms L2 with chunk t of segment seg+PF
       const int cp = (seg + PF) * NCH + (t % NCH);
@@ -477,14 +437,8 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
         alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
-#if MAP_FWD_DIST2
-      sb[j] = sc[j]; pb[j] = pc[j];
-      const int cn = (seg + 2) * NCH + j;
-      if (cn < nchunk) { sc[j] = ldg_hint(sys4 + cn * 4, pol_stream); pc[j] = ldp(cn); }
-#else
       const int cn = (seg + 1) * NCH + j;
-      if (cn < nchunk) { sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn); }
-#endif
+      if (cn < nchunk) { sb[j] = __ldg(sys4 + cn * 4); pb[j] = ldp(cn); }
     }
     renorm(a);                                                 // checkpoints are stored normalised
   }
@@ -621,7 +575,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       cka = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[0];
       ckb = reinterpret_cast<const uint4*>(ck + (seg - 1) * 32)[1];
       const int cn = (seg - 1) * NCH;
-      sx = ldg_hint(sys4 + cn * 4, pol_stream); px = ldp(cn);
+      sx = __ldg(sys4 + cn * 4); px = ldp(cn);
       if (UPD) zx = ldz(cn);
     }
     // ---- beta / ext sweep over the segment, two steps (even e, odd e+1) per round ----
@@ -652,10 +606,10 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
           if ((ee & PM) == 0) renorm(b);
           e4[2 * h + 1] = xo; e4[2 * h] = xe;
         }
-        stg_hint(reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16), make_uint4(e4[0], e4[1], e4[2], e4[3]), pol_stream);
+        *reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
         if (seg > 0 && j > 0) {                                  // chunk j is consumed: refill with the next segment's
           const int cn = (seg - 1) * NCH + j;
-          sb[j] = ldg_hint(sys4 + cn * 4, pol_stream); pb[j] = ldp(cn);
+          sb[j] = __ldg(sys4 + cn * 4); pb[j] = ldp(cn);
           if (UPD) zb[j] = ldz(cn);
         }
       }
