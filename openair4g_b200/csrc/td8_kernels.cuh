@@ -136,9 +136,26 @@ __device__ __forceinline__ G8 gamma8(u32 s, u32 p) {   // TD8:178-185: widen, ad
   g.n0 = __vadd2(~g.g0, 0x00010001u);
   return g;
 }
-// clamp(max(x + gx, y + gy), 0, 255) = max(sat8(x+gx), sat8(y+gy)) in offset form
+// max(sat8(x+gx), sat8(y+gy)) in offset form = clamp(max(x' + gx, y' + gy), 0, 255).  Every metric that enters a
+// recursion step is max-normalised or a start value (<= 0, offset form <= 128), so a sum can exceed 255 only by one,
+// when a branch metric is +128 = -(-128), i.e. when m11 or m10 of the step is -128 (see chunk_pair_hazard).
+// SAFE = false (no such step in the segment, checked by the caller): only the lower clamp can bind and the
+// add-compare-select is VIADD + VIADDMNMX.RELU; SAFE = true: + VIMNMX.RELU against 255.
+template <bool SAFE>
 __device__ __forceinline__ u32 acs8(u32 x, u32 gx, u32 y, u32 gy) {
-  return __vimin_s16x2_relu(__viaddmax_s16x2(x, gx, __vadd2(y, gy)), K255);
+  if (SAFE) return __vimin_s16x2_relu(__viaddmax_s16x2(x, gx, __vadd2(y, gy)), K255);
+  return __viaddmax_s16x2_relu(x, gx, __vadd2(y, gy));
+}
+// m11 = (s+p)>>1 or m10 = (s-p)>>1 equals -128 only for (s,p) in {(-128,-128), (-128,-127), (-127,-128), (-128,127)}.
+// Conservative chunk-level test (8 steps x 2 lanes each): some systematic byte is <= -127 AND some parity byte is
+// <= -127 or == 127.  (Systematic inputs saturate routinely once the decoder converges; channel parity rarely does.)
+__device__ __forceinline__ u32 zero_byte_mask(u32 x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
+__device__ __forceinline__ bool chunk_pair_hazard(const uint4& sv, const uint4& pv) {
+  auto lo = [](u32 x) -> u32 { return zero_byte_mask((x ^ 0x80808080u) & 0xfefefefeu); };       // byte is 0x80 or 0x81
+  auto hi = [](u32 x) -> u32 { return zero_byte_mask(x ^ 0x7f7f7f7fu); };                       // byte is 0x7f
+  const u32 hs = lo(sv.x) | lo(sv.y) | lo(sv.z) | lo(sv.w);
+  if (hs == 0) return false;
+  return (lo(pv.x) | lo(pv.y) | lo(pv.z) | lo(pv.w) | hi(pv.x) | hi(pv.y) | hi(pv.z) | hi(pv.w)) != 0;
 }
 // out = sat8(n - max_s n) in offset form: max(n' - mx' + 128, 0); n' + c <= 128, so the min with 255 of the
 // add-min-relu form never binds and the zero needs no register
@@ -149,29 +166,31 @@ __device__ __forceinline__ void norm8(u32 (&v)[8], const u32 (&n)[8]) {
   for (int s = 0; s < 8; ++s) v[s] = __viaddmin_s16x2_relu(n[s], c, K255);
 }
 // forward recursion (TD8:251-297)
+template <bool SAFE = true>
 __device__ __forceinline__ void alpha8_step(u32 (&a)[8], const G8& g) {
   u32 n[8];
-  n[0] = acs8(a[1], g.g1, a[0], g.n1);
-  n[1] = acs8(a[3], g.n0, a[2], g.g0);
-  n[2] = acs8(a[5], g.g0, a[4], g.n0);
-  n[3] = acs8(a[7], g.n1, a[6], g.g1);
-  n[4] = acs8(a[1], g.n1, a[0], g.g1);
-  n[5] = acs8(a[3], g.g0, a[2], g.n0);
-  n[6] = acs8(a[5], g.n0, a[4], g.g0);
-  n[7] = acs8(a[7], g.g1, a[6], g.n1);
+  n[0] = acs8<SAFE>(a[1], g.g1, a[0], g.n1);
+  n[1] = acs8<SAFE>(a[3], g.n0, a[2], g.g0);
+  n[2] = acs8<SAFE>(a[5], g.g0, a[4], g.n0);
+  n[3] = acs8<SAFE>(a[7], g.n1, a[6], g.g1);
+  n[4] = acs8<SAFE>(a[1], g.n1, a[0], g.g1);
+  n[5] = acs8<SAFE>(a[3], g.g0, a[2], g.n0);
+  n[6] = acs8<SAFE>(a[5], g.n0, a[4], g.g0);
+  n[7] = acs8<SAFE>(a[7], g.g1, a[6], g.n1);
   norm8(a, n);
 }
 // backward recursion (TD8:579-650)
+template <bool SAFE = true>
 __device__ __forceinline__ void beta8_step(u32 (&b)[8], const G8& g) {
   u32 n[8];
-  n[0] = acs8(b[4], g.g1, b[0], g.n1);
-  n[1] = acs8(b[4], g.n1, b[0], g.g1);
-  n[2] = acs8(b[5], g.n0, b[1], g.g0);
-  n[3] = acs8(b[5], g.g0, b[1], g.n0);
-  n[4] = acs8(b[6], g.g0, b[2], g.n0);
-  n[5] = acs8(b[6], g.n0, b[2], g.g0);
-  n[6] = acs8(b[7], g.n1, b[3], g.g1);
-  n[7] = acs8(b[7], g.g1, b[3], g.n1);
+  n[0] = acs8<SAFE>(b[4], g.g1, b[0], g.n1);
+  n[1] = acs8<SAFE>(b[4], g.n1, b[0], g.g1);
+  n[2] = acs8<SAFE>(b[5], g.n0, b[1], g.g0);
+  n[3] = acs8<SAFE>(b[5], g.g0, b[1], g.n0);
+  n[4] = acs8<SAFE>(b[6], g.g0, b[2], g.n0);
+  n[5] = acs8<SAFE>(b[6], g.n0, b[2], g.g0);
+  n[6] = acs8<SAFE>(b[7], g.n1, b[3], g.g1);
+  n[7] = acs8<SAFE>(b[7], g.g1, b[3], g.n1);
   norm8(b, n);
 }
 // max of four saturated sums a_i (+) b_j, offset form (a signed = offset - 128, b offset)
@@ -179,8 +198,7 @@ __device__ __forceinline__ u32 max4sum8(u32 a0, u32 b0, u32 a1, u32 b1, u32 a2, 
   u32 x = __vadd2(a0, b0);
   x = __viaddmax_s16x2(a1, b1, x);
   x = __viaddmax_s16x2(a2, b2, x);
-  x = __viaddmax_s16x2(a3, b3, x);
-  return __vimin_s16x2_relu(x, K255);
+  return __viaddmax_s16x2_relu(a3, b3, x);       // a <= 0, b' <= 128: only the lower clamp can bind
 }
 // a-posteriori LLR of one step (TD8:715-770); a, b in offset form; returns SIGNED int8-range halfwords
 __device__ __forceinline__ u32 ext8_step(const u32 (&ao)[8], const u32 (&b)[8], const G8& g) {
@@ -249,8 +267,13 @@ __global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
       const uint4 Sc = S, Pc = P;
       if (seg + 1 < nseg) { S = __ldg(sys4 + (seg + 1) * 8); P = __ldg(par4 + (seg + 1) * 8); }
       if (seg * 8 + 8 <= W) {
+        if (!chunk_pair_hazard(Sc, Pc)) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) alpha8_step(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+          for (int e = 0; e < 8; ++e) alpha8_step<false>(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) alpha8_step<true>(a, gamma8(unp8(Sc, e), unp8(Pc, e)));
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
@@ -288,17 +311,18 @@ __global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
 
   // alpha[k0 .. k1) of segment `seg` (final values) -> shared memory entries 0..; leaves the chunk inputs in S, P
   uint4 S, P;
-  auto fill_alpha = [&](auto full, int seg) {
+  // (S, P must hold the segment's chunk registers; safe = std::false_type when the chunk has no extreme systematic value)
+  auto fill_alpha = [&](auto full, auto safe, int seg) {
     constexpr bool FULL = decltype(full)::value;                // all 8 steps of the segment exist
+    constexpr bool SAFE = decltype(safe)::value;
     const int k0 = seg * 8;
-    S = __ldg(sys4 + seg * 8); P = __ldg(par4 + seg * 8);
     u32 x[8];
     ckget(seg == 0 ? CH0 : (seg == 1 ? CH8 : seg), x);          // steps 1..16 come from the re-run chain
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (FULL || k0 + e < W) {
         put(e, x);
-        if (e < 7) alpha8_step(x, gamma8(unp8(S, e), unp8(P, e)));
+        if (e < 7) alpha8_step<SAFE>(x, gamma8(unp8(S, e), unp8(P, e)));
       }
     }
     if (seg == 0) { ckget(A0, x); put(0, x); }                  // alpha[0]: the value of the second re-seed
@@ -306,10 +330,11 @@ __global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
   };
   // backward over one segment with beta[k1] in b: ext for k in [elo, ehi], beta steps for k >= blo.
   // full = the segment has 8 steps, all of them in the ext range and all stepping beta (no per-step tests).
-  auto back_segment = [&](auto full, int seg, int elo, int ehi, int blo) {
+  auto back_segment_impl = [&](auto full, auto safe, int seg, int elo, int ehi, int blo) {
     constexpr bool FULL = decltype(full)::value;
+    constexpr bool SAFE = decltype(safe)::value;
     const int k0 = seg * 8;
-    fill_alpha(full, seg);
+    fill_alpha(full, safe, seg);
     u32 o[8];
 #pragma unroll
     for (int e = 7; e >= 0; --e) {
@@ -322,7 +347,7 @@ __global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
           get(e, x);
           o[e] = ext8_step(x, b, g);
         }
-        if (FULL || k >= blo) beta8_step(b, g);
+        if (FULL || k >= blo) beta8_step<SAFE>(b, g);
       }
     }
     int8_t* dst = ext + seg * 128;
@@ -339,6 +364,11 @@ __global__ void __maxnreg__(MAP8_MAX_REGS) k_map8(Td8Args p) {
   };
   const std::true_type kFull{};
   const std::false_type kPart{};
+  auto back_segment = [&](auto full, int seg, int elo, int ehi, int blo) {
+    S = __ldg(sys4 + seg * 8); P = __ldg(par4 + seg * 8);
+    if (decltype(full)::value && !chunk_pair_hazard(S, P)) back_segment_impl(full, std::false_type{}, seg, elo, ehi, blo);
+    else back_segment_impl(full, std::true_type{}, seg, elo, ehi, blo);
+  };
 
   // ---- beta pass 1 (TD8:505-650): from alpha[W], lane 15 <- 0; all W steps; ext where beta[k+1] is final ----
 #pragma unroll
