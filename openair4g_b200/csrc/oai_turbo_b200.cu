@@ -154,7 +154,7 @@ static int ctx_get(int dev, DevCtx** out) {
 
 // ---- a batch of code blocks resident on one GPU ---------------------------------------
 constexpr int CKPT_S = MAP_CKPT_STEPS;
-constexpr int GUARD_B = 2048;     // see DESIGN.md "fast-path guard"
+constexpr int GUARD_B = 2954;     // 11 B + 256 <= 32767: the reference cannot saturate (DESIGN.md "fast-path guard"); our own no-wrap rule then allows M = B+1 <= 2499
 constexpr int MAX_PARTS = 8;      // pipeline stages of one host batch (copy of part i+1 overlaps the decode of part i)
 constexpr int MIN_PART_BLOCKS = 2960;   // smaller parts leave the MAP kernel latency-bound (measured: 16 parts 25 ms, 8 parts 18.6 ms per 23680 blocks)
 
