@@ -108,6 +108,45 @@ __device__ __forceinline__ void beta_step(u32 (&b)[8], const Gam<AR>& g) {
   b[4] = AR::sub(n4, mx); b[5] = AR::sub(n5, mx); b[6] = AR::sub(n6, mx); b[7] = AR::sub(n7, mx);
 }
 
+// ---- the same recursions in the inverted representation of InvArith (td_common.cuh) ----
+constexpr u32 KINV_CAP = 0xbfffbfffu;      // R(-32768) = 49151
+__device__ __forceinline__ void norm_inv(u32 (&v)[8], const u32 (&n)[8]) {
+  const u32 mn = __vminu2(__vimin3_u16x2(n[0], n[1], n[2]), __vimin3_u16x2(n[3], n[4], __vimin3_u16x2(n[5], n[6], n[7])));   // R(max)
+  const u32 c = __vadd2(~mn, 0x40004000u);                       // 16383 - R(max)
+#pragma unroll
+  for (int s = 0; s < 8; ++s) v[s] = __viaddmin_u16x2(n[s], c, KINV_CAP);   // R(sat(n - max)) = min(n' - mn' + 16383, 49151)
+}
+// R(max(sat(x + gx), sat(y + gy))) = min(x' - gx, y' - gy, 49151); callers pass the NEGATED branch metrics
+__device__ __forceinline__ u32 acs_inv(u32 x, u32 ngx, u32 y, u32 ngy) {
+  return __vimin3_u16x2(__vadd2(x, ngx), __vadd2(y, ngy), KINV_CAP);
+}
+template <class G>
+__device__ __forceinline__ void alpha_step_inv(u32 (&a)[8], const G& g) {
+  u32 n[8];
+  n[0] = acs_inv(a[1], g.n1, a[0], g.g1);
+  n[1] = acs_inv(a[3], g.g0, a[2], g.n0);
+  n[2] = acs_inv(a[5], g.n0, a[4], g.g0);
+  n[3] = acs_inv(a[7], g.g1, a[6], g.n1);
+  n[4] = acs_inv(a[1], g.g1, a[0], g.n1);
+  n[5] = acs_inv(a[3], g.n0, a[2], g.g0);
+  n[6] = acs_inv(a[5], g.g0, a[4], g.n0);
+  n[7] = acs_inv(a[7], g.n1, a[6], g.g1);
+  norm_inv(a, n);
+}
+template <class G>
+__device__ __forceinline__ void beta_step_inv(u32 (&b)[8], const G& g) {
+  u32 n[8];
+  n[0] = acs_inv(b[4], g.n1, b[0], g.g1);
+  n[1] = acs_inv(b[4], g.g1, b[0], g.n1);
+  n[2] = acs_inv(b[5], g.g0, b[1], g.n0);
+  n[3] = acs_inv(b[5], g.n0, b[1], g.g0);
+  n[4] = acs_inv(b[6], g.n0, b[2], g.g0);
+  n[5] = acs_inv(b[6], g.g0, b[2], g.n0);
+  n[6] = acs_inv(b[7], g.g1, b[3], g.n1);
+  n[7] = acs_inv(b[7], g.n1, b[3], g.g1);
+  norm_inv(b, n);
+}
+
 // a-posteriori LLR of one step, reference :757-818
 template <class AR>
 __device__ __forceinline__ u32 ext_step(const u32 (&a)[8], const u32 (&b)[8], const Gam<AR>& g) {
@@ -150,18 +189,65 @@ template <class AR, int S>
 __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0, bool upd,
                          u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv, uint4* abuf,
                          int tid) {
+  constexpr bool INV = AR::kInv;      // alpha / beta held as R(v) = 16383 - v (InvArith), else packed signed int16
   // feedback step fused into the output: ext = (ext (-) sys) (+) s0 with the reference's saturation
   auto fb = [&](u32 x, int k) -> u32 {
     if (!upd) return x;
     return __vaddss2(__vsubss2(x, __ldg(sys + c4_word(k, 0))), __ldg(s0 + c4_word(k, 0)));
+  };
+  auto gam = [&](int k) { return gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))); };
+  // In the inverted representation a candidate a + g must stay <= 16383; a = 0 with the NEGATED branch metric
+  // -(-16384) = +16384 is the one combination that does not (it needs sat(s +- p) = -32768).  Such steps run in signed
+  // saturating arithmetic like the first beta step below.
+  auto hazard = [&](const Gam<AR>& g) -> bool {
+    auto zh = [](u32 x) -> u32 { return (x - 0x00010001u) & ~x & 0x80008000u; };     // some halfword of x is zero
+    return (zh(g.g1 ^ 0xC000C000u) | zh(g.g0 ^ 0xC000C000u)) != 0;
+  };
+  auto astep = [&](u32 (&x)[8], const Gam<AR>& g) {
+    if (!INV) { alpha_step<AR>(x, g); return; }
+    if (hazard(g)) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) x[s] = AR::dec(x[s]);
+      alpha_step<AR>(x, g);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) x[s] = AR::enc(x[s]);
+    } else {
+      alpha_step_inv(x, g);
+    }
+  };
+  // ext of one step from alpha (stored representation) and beta; b_signed: beta is still in signed form
+  auto extv = [&](const u32 (&al)[8], const u32 (&be)[8], bool b_signed, const Gam<AR>& g) -> u32 {
+    if (!INV) return ext_step<AR>(al, be, g);
+    u32 as[8], bs[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { as[s] = AR::dec(al[s]); bs[s] = b_signed ? be[s] : AR::dec(be[s]); }
+    return ext_step<AR>(as, bs, g);
+  };
+  // one backward step.  The beta vector that enters the FIRST step of a sweep contains the tail metrics of lane 7,
+  // which are computed in wrapping int16 and may be positive (TD16:474-520): that step runs in signed saturating
+  // arithmetic; its max-normalised result is <= 0 and goes on in the inverted representation.
+  auto bstep = [&](u32 (&be)[8], bool& b_signed, const Gam<AR>& g) {
+    if (!INV) { beta_step<AR>(be, g); return; }
+    if (b_signed || hazard(g)) {
+      if (!b_signed) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) be[s] = AR::dec(be[s]);
+      }
+      beta_step<AR>(be, g);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) be[s] = AR::enc(be[s]);
+      b_signed = false;
+    } else {
+      beta_step_inv(be, g);
+    }
   };
   const int nseg = (W + S - 1) / S;
   u32 a[8];
 
   // ---- forward sweep (alpha pass 1), checkpoint every S steps ----------------------
 #pragma unroll
-  for (int s = 0; s < 8; ++s) a[s] = pack2(NEG_INIT, NEG_INIT);
-  if (t == 0) a[0] = pack2(0, NEG_INIT);                       // reference :201-208
+  for (int s = 0; s < 8; ++s) a[s] = AR::enc(pack2(NEG_INIT, NEG_INIT));
+  if (t == 0) a[0] = AR::enc(pack2(0, NEG_INIT));               // reference :201-208
   for (int c = 0; c * 4 < W; ++c) {
     uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sys + c * 16));
     uint4 p4 = __ldg(reinterpret_cast<const uint4*>(par + c * 16));
@@ -171,7 +257,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
       int k = c * 4 + q;
       if (k < W) {
         if (k % S == 0) ckpt_put(ck + (k / S) * 32, a);
-        alpha_step<AR>(a, gamma2<AR>(sv[q], pv[q]));
+        astep(a, gamma2<AR>(sv[q], pv[q]));
       }
     }
   }
@@ -181,7 +267,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     u32 prev = __shfl_sync(gmask, a[s], (t + 3) & 3, 4);      // thread t-1 (lanes 2t-2, 2t-1)
-    if (t == 0) prev = pack2(0, (s == 0) ? 0 : NEG_INIT);      // hi half is what gets used
+    if (t == 0) prev = AR::enc(pack2(0, (s == 0) ? 0 : NEG_INIT));   // hi half is what gets used
     seed[s] = __byte_perm(prev, a[s], 0x5432);                 // lo <- prev.hi, hi <- mine.lo
   }
   ckpt_put(ck + nseg * 32, seed);
@@ -189,16 +275,16 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     // the re-run covers the whole lane, so alpha[W] itself is the re-run value (K=40)
 #pragma unroll
     for (int s = 0; s < 8; ++s) a[s] = seed[s];
-    for (int k = 0; k < W; ++k)
-      alpha_step<AR>(a, gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+    for (int k = 0; k < W; ++k) astep(a, gam(k));
   }
 
-  // ---- beta start: lanes 0..6 <- own alpha[W], lane 7 <- tail metrics ---------------
+  // ---- beta start: lanes 0..6 <- own alpha[W], lane 7 <- tail metrics (signed form, see bstep) ----
   u32 b[8];
+  bool b_signed = true;
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
-    b[s] = a[s];
-    if (t == 3) b[s] = (a[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
+    b[s] = AR::dec(a[s]);
+    if (t == 3) b[s] = (b[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
   }
 
   // ---- backward sweep, pass 1 -----------------------------------------------------
@@ -207,54 +293,56 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     ckpt_get(ck + seg * 32, a);
     for (int k = k0; k < k1; ++k) {
       abuf_put(abuf, k - k0, tid, a);
-      if (k + 1 < k1) alpha_step<AR>(a, gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+      if (k + 1 < k1) astep(a, gam(k));
     }
     if (seg == 0) {          // alpha[0..5] come from the re-run chain
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
       for (int k = 0; k <= RERUN_STEPS && k < k1; ++k) {
         abuf_put(abuf, k, tid, a);
-        if (k < RERUN_STEPS) alpha_step<AR>(a, gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+        if (k < RERUN_STEPS) astep(a, gam(k));
       }
     }
     for (int k = k1 - 1; k >= k0; --k) {
-      Gam<AR> g = gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
+      const Gam<AR> g = gam(k);
       if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
         abuf_get(abuf, k - k0, tid, a);
-        ext[c4_word(k, 0)] = fb(ext_step<AR>(a, b, g), k);
+        ext[c4_word(k, 0)] = fb(extv(a, b, b_signed, g), k);
       }
-      beta_step<AR>(b, g);
+      bstep(b, b_signed, g);
     }
   }
 
   // ---- beta re-run: lane l <- beta[0] of lane l+1, lane 7 <- tail metrics ------------
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
-    u32 next = __shfl_sync(gmask, b[s], (t + 1) & 3, 4);      // thread t+1 (lanes 2t+2, 2t+3)
+    const u32 mine = b_signed ? b[s] : AR::dec(b[s]);           // back to signed form: lane 7 takes the tail metrics again
+    u32 next = __shfl_sync(gmask, mine, (t + 1) & 3, 4);      // thread t+1 (lanes 2t+2, 2t+3)
     if (t == 3) next = (u32)(uint16_t)Tv[s];
-    b[s] = __byte_perm(b[s], next, 0x5432);                    // lo <- mine.hi, hi <- next.lo
+    b[s] = __byte_perm(mine, next, 0x5432);                    // lo <- mine.hi, hi <- next.lo
   }
+  b_signed = true;
   {
     const int kk0 = max(W - 6, 0);
     const int sa = kk0 / S;
     ckpt_get(ck + sa * 32, a);
     for (int k = sa * S; k < W; ++k) {
       if (k >= kk0) abuf_put(abuf, k - kk0, tid, a);
-      if (k + 1 < W) alpha_step<AR>(a, gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+      if (k + 1 < W) astep(a, gam(k));
     }
     if (kk0 <= RERUN_STEPS) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
       for (int k = 0; k <= RERUN_STEPS && k < W; ++k) {
         if (k >= kk0) abuf_put(abuf, k - kk0, tid, a);
-        if (k < RERUN_STEPS) alpha_step<AR>(a, gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0))));
+        if (k < RERUN_STEPS) astep(a, gam(k));
       }
     }
     for (int k = W - 1; k >= kk0; --k) {
-      Gam<AR> g = gamma2<AR>(__ldg(sys + c4_word(k, 0)), __ldg(par + c4_word(k, 0)));
+      const Gam<AR> g = gam(k);
       abuf_get(abuf, k - kk0, tid, a);
-      ext[c4_word(k, 0)] = fb(ext_step<AR>(a, b, g), k);
-      if (k >= W - RERUN_STEPS) beta_step<AR>(b, g);             // loopval=(n-40)>>3, reference :585
+      ext[c4_word(k, 0)] = fb(extv(a, b, b_signed, g), k);
+      if (k >= W - RERUN_STEPS) bstep(b, b_signed, g);           // loopval=(n-40)>>3, reference :585
     }
   }
 }
@@ -704,7 +792,7 @@ __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>(abuf);
   const u32* s0 = reinterpret_cast<const u32*>(slot + (long)ARR_S0 * p.A) + t * 4;
   if (P == 0) {                                 // exact saturating policy, int16 arrays, 8-step segments
-    map_pass<SatArith, MAP_ABUF_ENTRIES>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
+    map_pass<InvArith, MAP_ABUF_ENTRIES>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
     return;
   }
   // int8 copies of parity / s0 when the whole batch has |y| <= 127 (warp-uniform: one flag per batch)

@@ -56,8 +56,26 @@ __host__ __device__ inline int c4_hw(int k, int lane) { return (c4_word(k, lane 
 // identical results whenever no intermediate leaves the int16 range, which the
 // per-pass guard (see DESIGN.md "fast-path guard") proves before this policy is chosen.
 struct SatArith {
+  static constexpr bool kInv = false;
+  static __device__ __forceinline__ u32 enc(u32 v) { return v; }
+  static __device__ __forceinline__ u32 dec(u32 r) { return r; }
   static __device__ __forceinline__ u32 add(u32 a, u32 b) { return __vaddss2(a, b); }
   static __device__ __forceinline__ u32 sub(u32 a, u32 b) { return __vsubss2(a, b); }
+};
+// InvArith: the exact policy of the MAP recursions in an order-reversing unsigned representation R(v) = 16383 - v.
+// Normalised metrics are <= 0 and |branch metric| <= 16384, so every candidate a +- g lies in [-49152, 16383], i.e.
+// R in [0, 65535] (the single exception, 0 + 16384, is detected per step and handled in signed arithmetic): the add
+// never wraps, the reference's saturation at -32768 is a min with 49151, and max becomes min:
+//     max(sat(ax + gx), sat(ay + gy))  ->  VIMNMX3.U16x2(ax' - gx, ay' - gy, 49151)      (2 VIADD + 1 ALU-pipe instruction)
+//     sat(n - max_s n)                 ->  VIADDMNMX.U16x2(n', 16383 - min_s n', 49151)
+// against 6 / 8 instructions for one emulated __vaddss2 / __vsubss2.  enc/dec convert from / to packed signed int16
+// (the same involution); add/sub are the signed saturating forms used where values are signed (gamma, ext, feedback).
+struct InvArith {
+  static constexpr bool kInv = true;
+  static __device__ __forceinline__ u32 add(u32 a, u32 b) { return __vaddss2(a, b); }
+  static __device__ __forceinline__ u32 sub(u32 a, u32 b) { return __vsubss2(a, b); }
+  static __device__ __forceinline__ u32 enc(u32 v) { return __vadd2(~v, 0x40004000u); }     // 16383 - v per halfword
+  static __device__ __forceinline__ u32 dec(u32 r) { return __vadd2(~r, 0x40004000u); }
 };
 struct WrapArith {
   static __device__ __forceinline__ u32 add(u32 a, u32 b) { return __vadd2(a, b); }
