@@ -216,7 +216,7 @@ struct Batch {
     CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
     CU(cudaMalloc(&d_batch_max, sizeof(int) * MAX_PARTS));
     CU(cudaMalloc(&d_active, sizeof(int) * ncb * 2));            // two lists (current / next)
-    CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 2));
+    CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 4));     // per part: two lists x two class counters
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     return 0;
@@ -248,7 +248,7 @@ struct Batch {
     u32* d_ckpt = this->d_ckpt + (long)lo * ckpt_words;
     int* d_batch_max = this->d_batch_max + part;
     int* act[2] = {this->d_active + lo, this->d_active + cap + lo};      // packed lists of running blocks
-    int* nact[2] = {this->d_nactive + 2 * part, this->d_nactive + 2 * part + 1};
+    int* nact[2] = {this->d_nactive + 4 * part, this->d_nactive + 4 * part + 2};
     int cur = 0;
     if (status_dev) status_dev += lo;
     XchgArgs x;
@@ -257,18 +257,18 @@ struct Batch {
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
     x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
     x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq;
-    cudaMemsetAsync(nact[0], 0, sizeof(int), st);
+    cudaMemsetAsync(nact[0], 0, 2 * sizeof(int), st);
     cudaMemsetAsync(d_batch_max, 0, sizeof(int), st);
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
     // packs the running blocks into list c (its counter is zero: memset above / k_x1_16) and makes it current
     auto compact_into = [&](int c) {
-      k_compact<<<(n + COMPACT_THREADS - 1) / COMPACT_THREADS, COMPACT_THREADS, 0, st>>>(d_state, n, act[c], nact[c]);
+      k_compact<<<(n + COMPACT_THREADS - 1) / COMPACT_THREADS, COMPACT_THREADS, 0, st>>>(d_state, n, act[c], nact[c], GUARD_B);
       ++launches;
       mp.active = act[c]; mp.nactive = nact[c]; x.active = act[c]; x.nactive = nact[c]; x.nactive_next = nact[1 - c];
     };
-    const int map_grid = (n * 4 + MAP_THREADS - 1) / MAP_THREADS;
+    const int map_grid = ((n + 7) * 4 + MAP_THREADS - 1) / MAP_THREADS;     // + the padding between the two classes of the list
     const size_t map_smem = MAP_SMEM_BYTES;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter; mp.upd = upd;

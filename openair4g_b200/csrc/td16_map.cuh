@@ -58,8 +58,8 @@ struct MapArgs {
   int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
   const int* batch_max;  // max |y| over the batch: <= 127 selects the int8 parity / s0 copies
   int upd;               // 1: write ext = (ext (-) sys) (+) s0 (the feedback step, reference :1354-1375)
-  const int* active;     // compacted list of running blocks (k_compact) or nullptr = all nblk blocks
-  const int* nactive;
+  const int* active;     // compacted two-ended list of running blocks (k_compact) or nullptr = all nblk blocks
+  const int* nactive;    // its two counters
 };
 
 template <class AR>
@@ -755,7 +755,12 @@ __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   const int t = gt & 3;
   int blk = gt >> 2;
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
-  if (p.active) blk = (blk < *p.nactive) ? p.active[blk] : p.nblk;
+  if (p.active) {              // two-ended list: fast-policy blocks first (padded to whole warps), exact-policy blocks after
+    const int nf = p.nactive[0], nx = p.nactive[1], nfp = (nf + 7) & ~7;
+    if (blk < nf) blk = p.active[blk];
+    else if (blk >= nfp && blk - nfp < nx) blk = p.active[p.nblk - 1 - (blk - nfp)];
+    else blk = p.nblk;
+  }
 
   bool active = false;
   int W = 0, P = 64;           // P: largest renormalisation period this block's guard allows (0: exact path)

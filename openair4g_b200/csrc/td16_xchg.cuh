@@ -36,8 +36,8 @@ struct XchgArgs {
   int guard_b;                  // MAP fast-path guard (same value as MapArgs::guard_b)
   int* batch_max;               // max |y| over the whole batch (atomicMax by k_demux16)
   const int* active;            // packed list of the blocks still being decoded, or nullptr = all nblk blocks
-  const int* nactive;
-  int* nactive_next;            // k_x1_16 zeroes the counter of the list that k_compact builds after k_x2_16
+  const int* nactive;           // two counters: fast-policy blocks (front of the list), exact-policy blocks (back)
+  int* nactive_next;            // k_x1_16 zeroes the counters of the list that k_compact builds after k_x2_16
   // fused front end (k_demux16<true>): block i of the batch is rm block i; its decoder input is read straight out of
   // the rate-dematched circular buffer w (sub-block deinterleaving on the fly) instead of a materialised y
   const RmBlock* rm;
@@ -51,22 +51,42 @@ struct XchgArgs {
 // packs its 1024 blocks (ascending) and reserves its range with one atomicAdd, so neighbouring list entries stay
 // neighbours in memory; k_x1_16 zeroes the counter of the list that is built next.
 constexpr int COMPACT_THREADS = 1024;
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count) {
-  __shared__ int wsum[COMPACT_THREADS / 32];
-  __shared__ int base;
+// Two classes are kept apart so that a warp of the MAP kernel (8 blocks, one arithmetic policy per warp) does not mix
+// them: blocks whose guard allows the fast policy are packed from the FRONT of the list (count[0]), blocks that need the
+// exact saturating policy from the BACK (list[nblk-1-j], count[1]).  The class is taken from the maxima known when the
+// list is built (k_map16 re-derives the policy from the current ones, so this is grouping only, never correctness).
+__device__ __forceinline__ bool needs_exact_policy(const CbState& st, int guard_b) {
+  const int B = max(st.max_sys, st.max_in) + st.max_in;
+  return B > guard_b || ((32491 / (B + 1) - 11) >> 1) < 1;
+}
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count, int guard_b) {
+  __shared__ int wsum[2][COMPACT_THREADS / 32];
+  __shared__ int base[2];
   const int i = blockIdx.x * COMPACT_THREADS + threadIdx.x;
   const bool on = (i < nblk) && (state[i].status == 0);
-  const unsigned bal = __ballot_sync(0xffffffffu, on);
+  const bool ex = on && needs_exact_policy(state[i], guard_b);
+  const unsigned balf = __ballot_sync(0xffffffffu, on && !ex), balx = __ballot_sync(0xffffffffu, ex);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) wsum[wid] = __popc(bal);
+  if (lane == 0) { wsum[0][wid] = __popc(balf); wsum[1][wid] = __popc(balx); }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 2) {
     int t = 0;
-    for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int c = wsum[w]; wsum[w] = t; t += c; }
-    base = t ? atomicAdd(count, t) : 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int c = wsum[threadIdx.x][w]; wsum[threadIdx.x][w] = t; t += c; }
+    base[threadIdx.x] = t ? atomicAdd(count + threadIdx.x, t) : 0;
   }
   __syncthreads();
-  if (on) list[base + wsum[wid] + __popc(bal & ((1u << lane) - 1u))] = i;
+  const unsigned lt = (1u << lane) - 1u;
+  if (on && !ex) list[base[0] + wsum[0][wid] + __popc(balf & lt)] = i;
+  if (ex) list[nblk - 1 - (base[1] + wsum[1][wid] + __popc(balx & lt))] = i;
+}
+
+// entry `gi` of the two-ended list: the fast class occupies [0, nf), padded to a multiple of 8 (one warp of k_map16),
+// the exact class follows; -1: no block
+__device__ __forceinline__ int active_block(const int* list, const int* count, int nblk, int gi) {
+  const int nf = count[0], nx = count[1], nfp = (nf + 7) & ~7;
+  if (gi < nf) return list[gi];
+  if (gi >= nfp && gi - nfp < nx) return list[nblk - 1 - (gi - nfp)];
+  return -1;
 }
 
 // block handled by this CTA of an exchange kernel (-1: none)
@@ -78,7 +98,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* stat
 __device__ __forceinline__ int xchg_block(const XchgArgs& p, bool use_list = true) {
   const int bi = blockIdx.x;
   if (!use_list) return (bi < p.nblk) ? bi : -1;
-  if (p.active) return (bi < *p.nactive) ? p.active[bi] : -1;
+  if (p.active) return active_block(p.active, p.nactive, p.nblk, bi);
   return (bi < p.nblk) ? bi : -1;
 }
 
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
 __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p.nactive_next) *p.nactive_next = 0;    // the list k_compact fills next
+  if (blockIdx.x == 0 && threadIdx.x < 2 && p.nactive_next) p.nactive_next[threadIdx.x] = 0;   // the list k_compact fills next
   const int blk = xchg_block(p, (XCHG_LIST_MODE & 1) != 0);
   if (blk < 0) return;
   const CbMeta m = p.meta[blk];
