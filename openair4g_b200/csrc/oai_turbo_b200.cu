@@ -219,6 +219,9 @@ struct Batch {
     CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 4));     // per part: two lists x two class counters
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
+    // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which does not order with the
+    // non-blocking streams the decodes use: without this wait the zeroing could land AFTER the first kernels' writes
+    CU(cudaDeviceSynchronize());
     return 0;
   }
   void release() {
@@ -329,6 +332,7 @@ struct Batch8 {
     CU(cudaMalloc(&d_ck, sizeof(u32) * ck_words * ncb));
     CU(cudaMemset(d_ws, 0, slot_b * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
+    CU(cudaDeviceSynchronize());                       // see Batch::alloc
     return 0;
   }
   void release() {
@@ -988,7 +992,7 @@ int oai_turbo_harq_pool_create(int gpu, uint32_t n_slots, uint16_t max_K, oai_tu
   p->slot_hw = 3u * 32u * (((uint32_t)max_K + 4 + 31) / 32);
   if ((unsigned long long)p->slot_hw * n_slots > 0xffffffffull) { delete p; cudaSetDevice(prev); return fail(-1, "pool too large for 32-bit offsets"); }
   const size_t bytes = sizeof(int16_t) * (size_t)p->slot_hw * n_slots;
-  if (cudaMalloc(&p->d, bytes) != cudaSuccess || cudaMemset(p->d, 0, bytes) != cudaSuccess) {
+  if (cudaMalloc(&p->d, bytes) != cudaSuccess || cudaMemset(p->d, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     cudaGetLastError(); delete p; cudaSetDevice(prev);
     return fail(-100, "HARQ pool: cudaMalloc of %zu bytes failed", bytes);
   }

@@ -62,6 +62,8 @@ struct MapArgs {
   const int* nactive;    // its two counters
 };
 
+__device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
+
 template <class AR>
 struct Gam { u32 g1, g0, n1, n0; };
 
@@ -147,6 +149,39 @@ __device__ __forceinline__ void beta_step_inv(u32 (&b)[8], const G& g) {
   norm_inv(b, n);
 }
 
+// a-posteriori LLR of one step (reference :757-818) from alpha, beta in the inverted representation; returns the SIGNED
+// packed LLR.  The 16 sums a + b of two metrics in [-32768, 0] saturate at -32768; with magnitudes ua = -a, ub = -b in
+// [0, 32768] that is min(ua + ub, 32768), and ua + ub fits 16 bits except for 32768 + 32768: with ua~ = min(ua, 32767),
+// max(ua~ + ub, ua + ub~) equals ua + ub except in that case, where it is 65535 -- still above the cap.  The cap commutes
+// with the max over the four sums of a group.  Adding +-gamma needs 16383 - x >= 0 for the added metric x, i.e. no
+// metric of +16384: the caller routes such steps (hazard) to the signed form.
+template <class G>
+__device__ __forceinline__ u32 ext_step_inv(const u32 (&al)[8], const u32 (&be)[8], const G& g) {
+  constexpr u32 K16383 = 0x3fff3fffu, K32767 = 0x7fff7fffu, K32768 = 0x80008000u;
+  u32 ua[8], ub[8], uat[8], ubt[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    ua[s] = __vsub2(al[s], K16383); ub[s] = __vsub2(be[s], K16383);
+    uat[s] = __vminu2(ua[s], K32767); ubt[s] = __vminu2(ub[s], K32767);
+  }
+  auto sum = [&](int i, int j) -> u32 { return __vmaxu2(__vadd2(uat[i], ub[j]), __vadd2(ua[i], ubt[j])); };
+  auto grp = [&](int i0, int j0, int i1, int j1, int i2, int j2, int i3, int j3) -> u32 {   // magnitude of the saturated max
+    return __vimin3_u16x2(__vimin3_u16x2(sum(i0, j0), sum(i1, j1), K32768), sum(i2, j2), sum(i3, j3));
+  };
+  const u32 u00 = grp(0, 0, 1, 4, 6, 7, 7, 3);
+  const u32 u11 = grp(0, 4, 1, 0, 6, 3, 7, 7);
+  const u32 u01 = grp(2, 5, 3, 1, 4, 2, 5, 6);
+  const u32 u10 = grp(2, 1, 3, 5, 4, 6, 5, 2);
+  // R(m + x) = um + (16383 - x), capped at R(-32768)
+  const u32 eg1 = __vadd2(~g.g1, 0x40004000u), eg0 = __vadd2(~g.g0, 0x40004000u);          // 16383 - g
+  const u32 r01 = __viaddmin_u16x2(u01, __vadd2(g.g0, K16383), KINV_CAP);                   // m01 + n0, n0 = -g0
+  const u32 r00 = __viaddmin_u16x2(u00, __vadd2(g.g1, K16383), KINV_CAP);                   // m00 + n1
+  const u32 r10 = __viaddmin_u16x2(u10, eg0, KINV_CAP);                                     // m10 + g0
+  const u32 r11 = __viaddmin_u16x2(u11, eg1, KINV_CAP);                                     // m11 + g1
+  const u32 ru = __vminu2(r10, r11), rv = __vminu2(r01, r00);                               // R of the two maxima
+  return __vsubss2(__vadd2(~ru, 0x40004000u), __vadd2(~rv, 0x40004000u));
+}
+
 // a-posteriori LLR of one step, reference :757-818
 template <class AR>
 __device__ __forceinline__ u32 ext_step(const u32 (&a)[8], const u32 (&b)[8], const Gam<AR>& g) {
@@ -218,6 +253,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   // ext of one step from alpha (stored representation) and beta; b_signed: beta is still in signed form
   auto extv = [&](const u32 (&al)[8], const u32 (&be)[8], bool b_signed, const Gam<AR>& g) -> u32 {
     if (!INV) return ext_step<AR>(al, be, g);
+    if (!b_signed && !hazard(g)) return ext_step_inv(al, be, g);
     u32 as[8], bs[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) { as[s] = AR::dec(al[s]); bs[s] = b_signed ? be[s] : AR::dec(be[s]); }
@@ -248,9 +284,13 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = AR::enc(pack2(NEG_INIT, NEG_INIT));
   if (t == 0) a[0] = AR::enc(pack2(0, NEG_INIT));               // reference :201-208
+  const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c (4 steps) of this thread at [c*4]
+  const uint4* par4 = reinterpret_cast<const uint4*>(par);
+  const uint4* s04 = reinterpret_cast<const uint4*>(s0);
+  uint4 s4n = __ldg(sys4), p4n = __ldg(par4);
   for (int c = 0; c * 4 < W; ++c) {
-    uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sys + c * 16));
-    uint4 p4 = __ldg(reinterpret_cast<const uint4*>(par + c * 16));
+    const uint4 s4 = s4n, p4 = p4n;
+    if ((c + 1) * 4 < W) { s4n = __ldg(sys4 + (c + 1) * 4); p4n = __ldg(par4 + (c + 1) * 4); }   // one chunk ahead
     const u32 sv[4] = {s4.x, s4.y, s4.z, s4.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -288,29 +328,70 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   }
 
   // ---- backward sweep, pass 1 -----------------------------------------------------
+  // A segment is two 4-step chunks per stream; its inputs are loaded once into registers (the next segment's are
+  // requested at the segment start, a whole segment ahead of their use) and its 8 branch-metric pairs are computed once
+  // and shared by the alpha recomputation, the LLR and the beta step.
+  static_assert(S == 8, "exact-path segment = two chunks");
+  const int nchunk = (W + 3) >> 2;
+  uint4 sc[2], pc[2], zc[2], sn[2], pn[2], zn[2];
+  auto load_seg = [&](int seg, uint4 (&sv)[2], uint4 (&pv)[2], uint4 (&zv)[2]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = seg * 2 + j;
+      if (c < nchunk) { sv[j] = __ldg(sys4 + c * 4); pv[j] = __ldg(par4 + c * 4); if (upd) zv[j] = __ldg(s04 + c * 4); }
+    }
+  };
+  load_seg(nseg - 1, sc, pc, zc);
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
+    if (seg > 0) load_seg(seg - 1, sn, pn, zn);
     ckpt_get(ck + seg * 32, a);
-    for (int k = k0; k < k1; ++k) {
-      abuf_put(abuf, k - k0, tid, a);
-      if (k + 1 < k1) astep(a, gam(k));
+    Gam<AR> g8[S];
+#pragma unroll
+    for (int e = 0; e < S; ++e) {
+      if (k0 + e < k1) {
+        g8[e] = gamma2<AR>(pick4(sc[e >> 2], e & 3), pick4(pc[e >> 2], e & 3));
+        abuf_put(abuf, e, tid, a);
+        if (k0 + e + 1 < k1) astep(a, g8[e]);
+      }
     }
     if (seg == 0) {          // alpha[0..5] come from the re-run chain
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
-      for (int k = 0; k <= RERUN_STEPS && k < k1; ++k) {
-        abuf_put(abuf, k, tid, a);
-        if (k < RERUN_STEPS) astep(a, gam(k));
+#pragma unroll
+      for (int k = 0; k <= RERUN_STEPS; ++k) {
+        if (k < k1) {
+          abuf_put(abuf, k, tid, a);
+          if (k < RERUN_STEPS) astep(a, g8[k]);
+        }
       }
     }
-    for (int k = k1 - 1; k >= k0; --k) {
-      const Gam<AR> g = gam(k);
-      if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
-        abuf_get(abuf, k - k0, tid, a);
-        ext[c4_word(k, 0)] = fb(extv(a, b, b_signed, g), k);
+#pragma unroll
+    for (int j = 1; j >= 0; --j) {
+      u32 e4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int q = 3; q >= 0; --q) {
+        const int e = j * 4 + q, k = k0 + e;
+        if (k < k1) {
+          if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
+            abuf_get(abuf, e, tid, a);
+            u32 x = extv(a, b, b_signed, g8[e]);
+            if (upd) x = __vaddss2(__vsubss2(x, pick4(sc[j], q)), pick4(zc[j], q));     // feedback, reference :1354-1375
+            e4[q] = x;
+          }
+          bstep(b, b_signed, g8[e]);
+        }
       }
-      bstep(b, b_signed, g);
+      const int kc = k0 + j * 4;
+      if (kc + 3 <= W - 7) *reinterpret_cast<uint4*>(ext + ((kc >> 2) << 4)) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (kc + q < k1 && kc + q <= W - 7) ext[c4_word(kc + q, 0)] = e4[q];
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { sc[j] = sn[j]; pc[j] = pn[j]; zc[j] = zn[j]; }
   }
 
   // ---- beta re-run: lane l <- beta[0] of lane l+1, lane 7 <- tail metrics ------------
@@ -447,7 +528,6 @@ struct FastSmem {
   }
 };
 
-__device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
 
 // Fast MAP pass.  PM = P-1 with P the renormalisation period (1, 4 or 16 steps; compile time so
 // that the unrolled steady-state code has no data-dependent branches).
