@@ -198,6 +198,51 @@ void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t *plan);
 int oai_turbo_dev_plan_profile(oai_turbo_dev_plan_t *plan, int enable, double *ms4, long *count4);
 
 /* ------------------------------------------------------------------------------------
+ * Section 3b.  Transmit-side mirror: test-vector generation on the GPU.
+ * The three reference entry points with their exact signatures, and one batched call.
+ * ---------------------------------------------------------------------------------- */
+
+/* openair1/PHY/CODING/defs.h:315-320 ; impl 3gpplte_sse.c:380-476.  output = 3*8*input_length_bytes + 12
+ * bytes holding one bit each: (systematic, parity 1, parity 2) per input bit, then the 12 termination
+ * bits.  F, f1 and f2 are accepted and ignored like in the reference (the interleaver follows from the
+ * length; filler bits are ordinary zeros of the input).  Illegal lengths print "Illegal frame length!"
+ * and leave output untouched.  For odd byte counts the reference's byte-pair interleaver leaves its last
+ * interleaved byte unwritten (3gpplte_sse.c:321), i.e. encodes stack garbage; this call encodes the
+ * 36.212 5.1.3.2 code for every length. */
+void threegpplte_turbo_encoder(uint8_t *input, uint16_t input_length_bytes, uint8_t *output, uint8_t F,
+                               uint16_t interleaver_f1, uint16_t interleaver_f2);
+
+/* openair1/PHY/CODING/defs.h:112 ; impl lte_rate_matching.c:51-130.  Like the reference it READS the
+ * 3*ND bytes in front of d (the callers keep LTE_NULL there, dlsch_coding.c:205) and WRITES
+ * d[3*D+2] = d[2].  Returns RTC. */
+uint32_t sub_block_interleaving_turbo(uint32_t D, uint8_t *d, uint8_t *w);
+
+/* openair1/PHY/CODING/defs.h:191-204 ; impl lte_rate_matching.c:464-634.  Returns E, or 0 (and prints
+ * the reference's message) when the soft buffer is smaller than the circular buffer. */
+uint32_t lte_rate_matching_turbo(uint32_t RTC, uint32_t G, uint8_t *w, uint8_t *e, uint8_t C,
+                                 uint32_t Nsoft, uint8_t Mdlharq, uint8_t Kmimo, uint8_t rvidx, uint8_t Qm,
+                                 uint8_t Nl, uint8_t r, uint8_t nb_rb, uint8_t m);
+
+/* One code block of the batched TX call = the body of the per-segment loops of dlsch_encoding /
+ * ulsch_encoding (dlsch_coding.c:356-404, ulsch_coding.c:400-550): encoder -> sub-block interleaver ->
+ * rate matching, without storing d or w. */
+typedef struct {
+  const uint8_t *c;     /* K/8 info bytes incl. CRC and leading filler zeros, MSB first (harq->c[r]) */
+  uint8_t *e;           /* out: E bits, one per byte (harq->e + r_offset) */
+  uint32_t G, Nsoft;
+  uint32_t E;           /* out: bits written (0: soft buffer smaller than the circular buffer) */
+  uint16_t K;
+  uint8_t F;            /* filler bits of this block (first block of a transport block only) */
+  uint8_t filler_null;  /* 0: the reference's TX, which transmits the filler bits; 1: 36.212 5.1.4.1.1, filler bits
+                           of streams 0/1 are <NULL> -- what generate_dummy_w assumes on the receive side */
+  uint8_t C, Mdlharq, Kmimo, rvidx, Qm, Nl, r, reserved;
+} oai_tx_desc_t;
+
+#define OAI_TX_DEVICE_POINTERS 1u   /* c and e are device pointers on `gpu` */
+/* Synchronous.  Returns 0, or < 0 with oai_turbo_b200_last_error(). */
+int oai_turbo_tx_batch(oai_tx_desc_t *blocks, int n, unsigned flags, int gpu);
+
+/* ------------------------------------------------------------------------------------
  * 4. Introspection
  * ---------------------------------------------------------------------------------- */
 const char *oai_turbo_b200_version(void);

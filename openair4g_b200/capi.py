@@ -31,7 +31,8 @@ EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_tu
            "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
            "oai_turbo_harq_pool_create", "oai_turbo_harq_pool_read", "oai_turbo_harq_pool_destroy",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
-           "oai_turbo_debug_map16"]
+           "oai_turbo_debug_map16", "threegpplte_turbo_encoder", "sub_block_interleaving_turbo",
+           "lte_rate_matching_turbo", "oai_turbo_tx_batch"]
 
 
 class CbDesc(C.Structure):
@@ -46,6 +47,16 @@ class CbDesc(C.Structure):
                 ("scr_c_init", C.c_uint32), ("scr_offset", C.c_uint32), ("scr_enable", C.c_uint8)]
 
 
+class TxDesc(C.Structure):
+    """oai_tx_desc_t"""
+    _fields_ = [("c", C.c_void_p), ("e", C.c_void_p), ("G", C.c_uint32), ("Nsoft", C.c_uint32), ("E", C.c_uint32),
+                ("K", C.c_uint16), ("F", C.c_uint8), ("filler_null", C.c_uint8), ("C", C.c_uint8),
+                ("Mdlharq", C.c_uint8), ("Kmimo", C.c_uint8), ("rvidx", C.c_uint8), ("Qm", C.c_uint8),
+                ("Nl", C.c_uint8), ("r", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+TX_DEVICE_POINTERS = 1
+
 _stats7 = [C.c_void_p] * 7
 for _f in ("phy_threegpplte_turbo_decoder16", "phy_threegpplte_turbo_decoder8"):
     getattr(lib, _f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint8,
@@ -58,6 +69,14 @@ lib.lte_rate_matching_turbo_rx.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C
 lib.lte_rate_matching_turbo_rx.restype = C.c_int
 lib.sub_block_deinterleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
 lib.sub_block_deinterleaving_turbo.restype = None
+lib.threegpplte_turbo_encoder.argtypes = [C.c_void_p, C.c_uint16, C.c_void_p, C.c_uint8, C.c_uint16, C.c_uint16]
+lib.threegpplte_turbo_encoder.restype = None
+lib.sub_block_interleaving_turbo.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+lib.sub_block_interleaving_turbo.restype = C.c_uint32
+lib.lte_rate_matching_turbo.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint8, C.c_uint32] + [C.c_uint8] * 8
+lib.lte_rate_matching_turbo.restype = C.c_uint32
+lib.oai_turbo_tx_batch.argtypes = [C.POINTER(TxDesc), C.c_int, C.c_uint, C.c_int]
+lib.oai_turbo_tx_batch.restype = C.c_int
 lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
 lib.oai_lte_segmentation_params.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 6
@@ -135,6 +154,51 @@ def sub_block_deinterleaving_turbo(D, d_buf, d_offset, w):
     """Writes into d_buf (int16) around element d_offset exactly what the reference writes around its `d`."""
     assert d_buf.dtype == np.int16 and w.dtype == np.int16
     lib.sub_block_deinterleaving_turbo(D, d_buf.ctypes.data + 2 * d_offset, w.ctypes.data)
+
+
+def threegpplte_turbo_encoder(input_bytes, F=0, f1=0, f2=0):
+    """Reference call shape: K/8 info bytes -> uint8[3K+12] coded bits (one per byte)."""
+    inp = np.ascontiguousarray(input_bytes, dtype=np.uint8)
+    out = np.full(3 * 8 * inp.size + 12, 255, dtype=np.uint8)
+    lib.threegpplte_turbo_encoder(inp.ctypes.data, inp.size, out.ctypes.data, F, f1, f2)
+    return out
+
+
+def sub_block_interleaving_turbo(D, d_buf, d_offset, w):
+    """d_buf (uint8) holds the reference's d at element d_offset (>= 3*ND bytes in front of it are read, element
+    3*D+2 behind it is written); w (uint8[3*Kpi]) receives the three interleaved sub-blocks.  Returns RTC."""
+    assert d_buf.dtype == np.uint8 and w.dtype == np.uint8
+    return int(lib.sub_block_interleaving_turbo(D, d_buf.ctypes.data + d_offset, w.ctypes.data))
+
+
+def lte_rate_matching_turbo(RTC, G, w, e, C_, Nsoft, Mdlharq, Kmimo, rvidx, Qm, Nl, r, nb_rb=0, m=0):
+    """Reference call shape; writes e (uint8) and returns E."""
+    assert w.dtype == np.uint8 and e.dtype == np.uint8
+    return int(lib.lte_rate_matching_turbo(RTC, G, w.ctypes.data, e.ctypes.data, C_, Nsoft, Mdlharq, Kmimo, rvidx, Qm, Nl,
+                                           r, nb_rb, m))
+
+
+def tx_batch(blocks, gpu=-1):
+    """blocks: list of dicts with c (uint8[K/8]), K, G, C, r, rvidx, Qm and optionally F, filler_null, Nsoft, Mdlharq,
+    Kmimo, Nl.  Returns the list of e arrays (uint8, one bit per byte) produced by oai_turbo_tx_batch."""
+    n = len(blocks)
+    descs = (TxDesc * n)()
+    keep, outs = [], []
+    for i, b in enumerate(blocks):
+        c = np.ascontiguousarray(b["c"], dtype=np.uint8)
+        e = np.full(int(b.get("e_cap", b["G"])) + 8, 255, dtype=np.uint8)
+        keep.append(c)
+        outs.append(e)
+        d = descs[i]
+        d.c = c.ctypes.data; d.e = e.ctypes.data
+        d.K = b["K"]; d.F = b.get("F", 0); d.filler_null = b.get("filler_null", 0)
+        d.G = b["G"]; d.Nsoft = b.get("Nsoft", 1827072); d.C = b.get("C", 1); d.Mdlharq = b.get("Mdlharq", 8)
+        d.Kmimo = b.get("Kmimo", 1); d.rvidx = b.get("rvidx", 0); d.Qm = b.get("Qm", 2); d.Nl = b.get("Nl", 1)
+        d.r = b.get("r", 0)
+    rc = lib.oai_turbo_tx_batch(descs, n, 0, gpu)
+    if rc:
+        raise RuntimeError("oai_turbo_tx_batch failed (%d): %s" % (rc, last_error()))
+    return [outs[i][:descs[i].E].copy() for i in range(n)]
 
 
 def decode_batch(blocks, flags=0, gpu=-1):

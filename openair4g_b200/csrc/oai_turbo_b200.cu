@@ -18,6 +18,7 @@
 #include "td16_xchg.cuh"
 #include "rm_kernels.cuh"
 #include "td8_kernels.cuh"
+#include "tx_kernels.cuh"
 
 namespace oai {
 
@@ -1187,6 +1188,157 @@ void sub_block_deinterleaving_turbo(uint32_t D, int16_t* dd, int16_t* w) {
   d1[0] = y[0]; d1[1] = y[1];
   memcpy(d1 + 3, y + 3, ((size_t)3 * Kpi - 3) * 2);
   d1[3 * Kpi + 2] = y[3 * Kpi + 2];
+}
+
+// ---- transmit-side mirror -------------------------------------------------------------------
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+void threegpplte_turbo_encoder(uint8_t* input, uint16_t input_length_bytes, uint8_t* output, uint8_t F,
+                               uint16_t interleaver_f1, uint16_t interleaver_f2) {
+  (void)F; (void)interleaver_f1; (void)interleaver_f2;
+  const int K = (int)input_length_bytes * 8, idx = qpp_index(K);
+  if (idx < 0) { printf("Illegal frame length!\n"); return; }                            // 3gpplte_sse.c:399-402
+  Scratch& sc = t_scratch;
+  const size_t o_c = 256, o_d = o_c + up256(input_length_bytes), total = o_d + up256(3 * (size_t)K + 12);
+  DevCtx* c;
+  if (sc.ensure(total) || ctx_get(-1, &c)) { fprintf(stderr, "[oai_turbo_b200] threegpplte_turbo_encoder: GPU path failed (%s)\n", g_err); return; }
+  TxBlock b;
+  memset(&b, 0, sizeof(b));
+  b.K = K; b.qpp_off = c->qpp_off[idx]; b.c_off_lo = (uint32_t)o_c; b.d_off_lo = (uint32_t)o_d;
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  memcpy(h, &b, sizeof(b));
+  memcpy(h + o_c, input, input_length_bytes);
+  cudaMemcpyAsync(d, h, o_d, cudaMemcpyHostToDevice, sc.st);
+  k_turbo_enc<<<1, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, 1, (const uint8_t*)d, (uint8_t*)d, c->qpp_pool);
+  ++g_launches;
+  cudaMemcpyAsync(h + o_d, d + o_d, 3 * (size_t)K + 12, cudaMemcpyDeviceToHost, sc.st);
+  if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "threegpplte_turbo_encoder: CUDA failure"); return; }
+  memcpy(output, h + o_d, 3 * (size_t)K + 12);
+}
+
+uint32_t sub_block_interleaving_turbo(uint32_t D, uint8_t* dd, uint8_t* w) {
+  const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
+  dd[3 * D + 2] = dd[2];                                                                  // lte_rate_matching.c:76
+  Scratch& sc = t_scratch;
+  const size_t nin = 3 * (size_t)Kpi + 3, o_w = up256(nin), total = o_w + up256(3 * (size_t)Kpi);
+  if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] sub_block_interleaving_turbo: GPU path failed (%s)\n", g_err); return RTC; }
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  memcpy(h, dd - 3 * (long)ND, nin);
+  cudaMemcpyAsync(d, h, nin, cudaMemcpyHostToDevice, sc.st);
+  k_sbi_tx<<<(Kpi + 255) / 256, 256, 0, sc.st>>>((const uint8_t*)d, (uint8_t*)(d + o_w), RTC, Kpi, ND);
+  ++g_launches;
+  cudaMemcpyAsync(h + o_w, d + o_w, 3 * (size_t)Kpi, cudaMemcpyDeviceToHost, sc.st);
+  if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "sub_block_interleaving_turbo: CUDA failure"); return RTC; }
+  memcpy(w, h + o_w, 3 * (size_t)Kpi);
+  return RTC;
+}
+
+uint32_t lte_rate_matching_turbo(uint32_t RTC, uint32_t G, uint8_t* w, uint8_t* e, uint8_t C, uint32_t Nsoft,
+                                 uint8_t Mdlharq, uint8_t Kmimo, uint8_t rvidx, uint8_t Qm, uint8_t Nl, uint8_t r,
+                                 uint8_t nb_rb, uint8_t m) {
+  (void)nb_rb; (void)m;
+  RmParams q;
+  if (rm_params(32 * RTC - 4, G, C, Nsoft, Mdlharq, Kmimo, rvidx, Qm, Nl, r, RTC, &q)) {
+    fprintf(stderr, "[oai_turbo_b200] lte_rate_matching_turbo: invalid parameters (Kmimo %d, Mdlharq %d, C %d, Qm %d, Nl %d)\n",
+            Kmimo, Mdlharq, C, Qm, Nl);                                                   // the reference divides by zero here
+    return 0;
+  }
+  if (q.Ncb < 3 * q.Kpi) {                                                                // :508-511
+    printf("Exiting, RM condition (Nir %d, Nsoft %d, Kw %d\n", (int)(Nsoft / Kmimo / (Mdlharq < 8 ? Mdlharq : 8)), (int)Nsoft, (int)(3 * q.Kpi));
+    return 0;
+  }
+  Scratch& sc = t_scratch;
+  const size_t o_w = 256, o_e = o_w + up256(q.Ncb), total = o_e + up256(q.E);
+  if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] lte_rate_matching_turbo: GPU path failed (%s)\n", g_err); return 0; }
+  TxBlock b;
+  memset(&b, 0, sizeof(b));
+  b.K = 32 * RTC - 4; b.RTC = RTC; b.Kpi = q.Kpi; b.Ncb = q.Ncb; b.k0 = q.k0; b.E = q.E;
+  b.w_from_d = 0; b.w_off_lo = (uint32_t)o_w; b.e_off_lo = (uint32_t)o_e;
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  memcpy(h, &b, sizeof(b));
+  memcpy(h + o_w, w, q.Ncb);
+  cudaMemcpyAsync(d, h, o_e, cudaMemcpyHostToDevice, sc.st);
+  k_rm_tx<<<1, RM_THREADS, q.Ncb + 16, sc.st>>>((const TxBlock*)d, 1, nullptr, (const uint8_t*)d, (uint8_t*)d);
+  ++g_launches;
+  cudaMemcpyAsync(h + o_e, d + o_e, q.E, cudaMemcpyDeviceToHost, sc.st);
+  if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "lte_rate_matching_turbo: CUDA failure"); return 0; }
+  memcpy(e, h + o_e, q.E);
+  return q.E;
+}
+
+int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
+  g_err[0] = 0;
+  if (n <= 0) return 0;
+  if (!blocks) return fail(-1, "oai_turbo_tx_batch: null descriptor array");
+  const bool devp = (flags & OAI_TX_DEVICE_POINTERS) != 0;
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  if (gpu >= 0 && gpu != prev) CU(cudaSetDevice(gpu));
+  struct Restore { int p; ~Restore() { cudaSetDevice(p); } } restore{prev};
+  DevCtx* c;
+  int rc = ctx_get(gpu, &c);
+  if (rc) return rc;
+  // scratch layout: [TxBlock x n][c bytes][e bytes][d bytes (device only)]
+  std::vector<TxBlock> tb(n);
+  const size_t o_c = up256(sizeof(TxBlock) * (size_t)n);
+  size_t cur_c = o_c, tot_e = 0, tot_d = 0;
+  uint32_t max_ncb = 0;
+  for (int i = 0; i < n; ++i) {
+    oai_tx_desc_t& t = blocks[i];
+    const int idx = qpp_index(t.K);
+    if (idx < 0) return fail(-3, "oai_turbo_tx_batch: block %d: illegal block size %d", i, (int)t.K);
+    if (!t.c || !t.e) return fail(-1, "oai_turbo_tx_batch: block %d: null pointer", i);
+    RmParams q;
+    if (rm_params(t.K, t.G, t.C, t.Nsoft, t.Mdlharq, t.Kmimo, t.rvidx, t.Qm, t.Nl, t.r, 0, &q))
+      return fail(-3, "oai_turbo_tx_batch: block %d: invalid rate-matching parameters", i);
+    TxBlock& b = tb[i];
+    memset(&b, 0, sizeof(b));
+    b.K = t.K; b.F = t.filler_null ? t.F : 0; b.RTC = q.RTC; b.Kpi = q.Kpi; b.ND = q.ND; b.Ncb = q.Ncb; b.k0 = q.k0;
+    b.E = (q.Ncb < 3 * q.Kpi) ? 0 : q.E;
+    b.qpp_off = c->qpp_off[idx]; b.w_from_d = 1;
+    t.E = b.E;
+    max_ncb = std::max(max_ncb, q.Ncb);
+    if (devp) {
+      const unsigned long long pc = (unsigned long long)(uintptr_t)t.c, pe = (unsigned long long)(uintptr_t)t.e;
+      b.c_off_lo = (uint32_t)pc; b.c_off_hi = (uint32_t)(pc >> 32); b.e_off_lo = (uint32_t)pe; b.e_off_hi = (uint32_t)(pe >> 32);
+    } else {
+      b.c_off_lo = (uint32_t)cur_c; b.c_off_hi = (uint32_t)((unsigned long long)cur_c >> 32);
+      cur_c += ((size_t)t.K / 8 + 3) & ~(size_t)3;
+      b.e_off_lo = (uint32_t)tot_e; b.e_off_hi = (uint32_t)((unsigned long long)tot_e >> 32);     // relative, fixed below
+      tot_e += b.E;
+    }
+    b.d_off_lo = (uint32_t)tot_d; b.d_off_hi = (uint32_t)((unsigned long long)tot_d >> 32);
+    tot_d += (3 * (size_t)t.K + 12 + 3) & ~(size_t)3;
+  }
+  const size_t o_e = up256(cur_c), o_d = o_e + up256(tot_e), total = o_d + up256(tot_d);
+  Scratch& sc = t_scratch;
+  if (sc.ensure(total)) return fail(-100, "oai_turbo_tx_batch: GPU path failed (%s)", g_err);
+  char* h = (char*)sc.h; char* d = (char*)sc.d;
+  for (int i = 0; i < n; ++i) {
+    TxBlock& b = tb[i];
+    const unsigned long long od = (unsigned long long)o_d + (((unsigned long long)b.d_off_hi << 32) | b.d_off_lo);
+    b.d_off_lo = (uint32_t)od; b.d_off_hi = (uint32_t)(od >> 32);
+    if (!devp) {
+      const unsigned long long oe = (unsigned long long)o_e + (((unsigned long long)b.e_off_hi << 32) | b.e_off_lo);
+      b.e_off_lo = (uint32_t)oe; b.e_off_hi = (uint32_t)(oe >> 32);
+      memcpy(h + (((unsigned long long)b.c_off_hi << 32) | b.c_off_lo), blocks[i].c, blocks[i].K / 8);
+    }
+  }
+  memcpy(h, tb.data(), sizeof(TxBlock) * (size_t)n);
+  CU(cudaMemcpyAsync(d, h, devp ? o_c : o_e, cudaMemcpyHostToDevice, sc.st));
+  const uint8_t* cbase = devp ? nullptr : (const uint8_t*)d;
+  uint8_t* ebase = devp ? nullptr : (uint8_t*)d;
+  k_turbo_enc<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, n, cbase, (uint8_t*)d, c->qpp_pool);
+  k_rm_tx<<<n, RM_THREADS, max_ncb + 16, sc.st>>>((const TxBlock*)d, n, (const uint8_t*)d, nullptr, ebase);
+  g_launches += 2;
+  if (!devp && tot_e) CU(cudaMemcpyAsync(h + o_e, d + o_e, tot_e, cudaMemcpyDeviceToHost, sc.st));
+  CU(cudaStreamSynchronize(sc.st));
+  CU(cudaGetLastError());
+  if (!devp) {
+    size_t off = o_e;
+    for (int i = 0; i < n; ++i) { memcpy(blocks[i].e, h + off, tb[i].E); off += tb[i].E; }
+  }
+  return 0;
 }
 
 // Kernel-level test hook: one MAP pass (demux + k_map16) on a single block; the systematic

@@ -78,8 +78,9 @@ def demap_maxlog(sym, Qm, n0, llr_scale):
 
 
 class LinkSim:
-    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1):
-        self.cfg, self.max_it, self.llr8, self.scale = cfg, max_iterations, llr8, llr_scale
+    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1, gpu_tx=False):
+        """gpu_tx: encode / interleave / rate-match on the GPU (oai_turbo_tx_batch) instead of the numpy TX chain."""
+        self.cfg, self.max_it, self.llr8, self.scale, self.gpu_tx = cfg, max_iterations, llr8, llr_scale, gpu_tx
         self.rng = np.random.default_rng(seed)
         B = cfg.tbs + 24
         self.C, self.Cp, self.Cm, self.Kp, self.Km, self.F = tx.segmentation(B)
@@ -104,6 +105,8 @@ class LinkSim:
         if C > 1:
             flat = cb.reshape(n * C, K)
             flat[:, per:] = tx.crc24b(flat[:, :per])
+        if self.gpu_tx:
+            return cb, cb                                                      # the GPU chain starts from the code blocks
         d = tx.turbo_encode(cb.reshape(n * C, K))
         return cb, d.reshape(n, C, 3 * K + 12)
 
@@ -116,9 +119,20 @@ class LinkSim:
         n0 = 10.0 ** (-snr_db / 10.0)
         es, offs, off = [], [], 0
         c = tx.gold_sequence(cfg.c_init, cfg.G) if cfg.downlink else None
+        if self.gpu_tx:
+            from .. import capi
+            packed = np.packbits(d, axis=2)
+            sent = capi.tx_batch([{"c": packed[i, r], "K": self.K, "F": self.F if r == 0 else 0, "filler_null": 1,
+                                   "G": cfg.G, "C": self.C, "r": r, "rvidx": rv, "Qm": cfg.Qm, "Nl": cfg.Nl,
+                                   "Mdlharq": cfg.Mdlharq, "Kmimo": cfg.Kmimo}
+                                  for r in range(self.C) for i in range(d.shape[0])])
         for r in range(self.C):
-            bits, E = tx.rate_match(d[:, r], self.K, self.F if r == 0 else 0, cfg.G, self.C, cfg.Qm, cfg.Nl, r, rv,
-                                    cfg.Mdlharq, cfg.Kmimo)
+            if self.gpu_tx:
+                bits = np.stack(sent[r * d.shape[0]:(r + 1) * d.shape[0]])
+                E = bits.shape[1]
+            else:
+                bits, E = tx.rate_match(d[:, r], self.K, self.F if r == 0 else 0, cfg.G, self.C, cfg.Qm, cfg.Nl, r, rv,
+                                        cfg.Mdlharq, cfg.Kmimo)
             if cfg.downlink:
                 bits = bits ^ c[None, off:off + E]
             s = modulate(bits, cfg.Qm)

@@ -119,6 +119,7 @@ uint32_t orc_lte_rate_matching_turbo(uint32_t RTC, uint32_t G, const uint8_t *w,
 {
   uint32_t Ncb, ind, E, k = 0;
   rm_params(RTC, C, Nsoft, Mdlharq, Kmimo, rvidx, &Ncb, &ind);
+  if (Ncb < 3 * (RTC << 5)) return 0;      /* the TX side gives up on a limited soft buffer (RM:508-511) */
   E = e_for_block(G, C, Qm, Nl, r);
   while (k < E) {
     if (ind >= Ncb) ind = 0;

@@ -33,12 +33,17 @@ def test_cbdesc_layout_matches_header():
     import subprocess
     import tempfile
     from openair4g_b200 import capi
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "oai_turbo_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "oai_turbo_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(oai_tx_desc_t),offsetof(oai_tx_desc_t,E),offsetof(oai_tx_desc_t,K),offsetof(oai_tx_desc_t,C),offsetof(oai_tx_desc_t,r));' \
+          'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(oai_cb_desc_t),offsetof(oai_cb_desc_t,K),offsetof(oai_cb_desc_t,w),offsetof(oai_cb_desc_t,C),offsetof(oai_cb_desc_t,tb_id),offsetof(oai_cb_desc_t,harq_pool),offsetof(oai_cb_desc_t,harq_slot),offsetof(oai_cb_desc_t,scr_c_init),offsetof(oai_cb_desc_t,scr_enable));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "p"), os.path.join(d, "p.c")], check=True)
         out = subprocess.run([os.path.join(d, "p")], capture_output=True, text=True, check=True).stdout.split()
+    T = capi.TxDesc
+    assert [int(v) for v in out[:5]] == [ctypes.sizeof(T), T.E.offset, T.K.offset, T.C.offset, T.r.offset]
+    out = out[5:]
     D = capi.CbDesc
     assert [int(v) for v in out] == [ctypes.sizeof(D), D.K.offset, D.w.offset, D.C.offset, D.tb_id.offset, D.harq_pool.offset, D.harq_slot.offset, D.scr_c_init.offset, D.scr_enable.offset]
 

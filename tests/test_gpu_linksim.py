@@ -107,3 +107,24 @@ def test_ulsim_8bit_decoder_switch(capi):
     r = sim.run(8.0, 6, capi=rec)
     assert r["mismatch_vs_tx"] == 0
     assert oracle_check(rec, llr8=1) >= 5
+
+
+def test_gpu_tx_switch_gives_identical_runs(capi):
+    """gpu_tx=True (oai_turbo_tx_batch instead of the numpy TX chain): same seeds -> the same transmitted bits, hence the
+    same soft bits, HARQ buffers, return values and decoded bytes, on a DL (scrambled, C=13) and an UL (2 rounds) shape."""
+    from openair4g_b200.sim import linksim
+    for cfg, snr, n, rounds in ((linksim.DLSIM_100PRB_MCS28, 21.0, 4, 1), (linksim.ULSIM_25PRB_MCS16, 6.5, 12, 2)):
+        runs = []
+        for gpu_tx in (False, True):
+            rec = Recorder(capi)
+            sim = linksim.LinkSim(cfg, max_iterations=4, seed=11, gpu_tx=gpu_tx)
+            r = sim.run(snr, n, max_rounds=rounds, capi=rec)
+            runs.append((r, rec))
+        (ra, reca), (rb, recb) = runs
+        assert ra["tb_err"] == rb["tb_err"] and ra["cb_err"] == rb["cb_err"] and np.array_equal(ra["iters"], rb["iters"])
+        assert len(reca.calls) == len(recb.calls)
+        for ca, cb in zip(reca.calls, recb.calls):
+            assert ca[4] == cb[4]
+            assert all(np.array_equal(x["y"], y["y"]) for x, y in zip(ca[0], cb[0]))
+            assert all(np.array_equal(x, y) for x, y in zip(ca[2], cb[2]))
+            assert all(np.array_equal(x, y) for x, y in zip(ca[3], cb[3]))

@@ -118,6 +118,11 @@ def test_tx_chain_port_matches_reference(port, ref):
             E1 = ref.ref_lte_rate_matching_turbo(RTC, G, w1, e1, Cc, 1827072, 8, 1, rv, Qm, 1, r, 25, 0)
             E2 = port.orc_lte_rate_matching_turbo(RTC, G, w2, e2, Cc, 1827072, 8, 1, rv, Qm, 1, r)
             assert E1 == E2 and np.array_equal(e1, e2)
+        if K >= 5824:                                 # limited soft buffer (Nir/C < 3*Kpi): the TX side gives up, RM:508-511
+            for Cc in (13, 14):
+                E1 = ref.ref_lte_rate_matching_turbo(RTC, 20 * K, w1, e1, Cc, 1827072, 8, 1, 0, 2, 1, 0, 25, 0)
+                E2 = port.orc_lte_rate_matching_turbo(RTC, 20 * K, w2, e2, Cc, 1827072, 8, 1, 0, 2, 1, 0)
+                assert E1 == E2 and (E1 == 0) == (1827072 // 8 // Cc < 3 * 32 * RTC)
 
 
 def _cmp16(K, blk, regime, crc, max_it, A=8, F=0):
