@@ -26,6 +26,7 @@
 //          lane (:541-549,585-587).  ext(k) reads alpha[k] and beta[k+1] of the final
 //          arrays, i.e. re-run values for k<=5 (alpha) and k>=W-6 (beta).
 #pragma once
+#include <type_traits>
 #include "td_common.cuh"
 
 namespace oai {
@@ -182,6 +183,85 @@ __device__ __forceinline__ u32 ext_step_inv(const u32 (&al)[8], const u32 (&be)[
   return __vsubss2(__vadd2(~ru, 0x40004000u), __vadd2(~rv, 0x40004000u));
 }
 
+// ---- hazard steps: a branch metric of exactly -16384 in some halfword ----------------------------------------
+// With the NEGATED metric +16384 the candidate 0 + 16384 = 16384 lies one above what R can hold.  In the halfwords
+// concerned the whole step is shifted by one (R_o(v) = 16383 + o - v, o = 1): the low end of the candidate range moves to
+// 0, the high end, -32768 - 16384 -> 65536, would wrap -- but only for the operand -32768 in the add of -16384, whose
+// result is capped to -32768 anyway, so that operand is clamped to -32767 first (R <= 49150) and still lands above the
+// cap.  The max-normalisation subtracts two values of the same offset, so its result is back in the plain representation.
+struct HzOff { u32 o, k1, k0; };     // o: offset per halfword; k1 / k0: clamp of the operands that take -g1 / -g0 negated, i.e. +16384
+template <class G>
+__device__ __forceinline__ HzOff hz_offsets(const G& g) {
+  HzOff h;
+  const u32 o1 = __vcmpeq2(g.g1, 0xC000C000u) & 0x00010001u, o0 = __vcmpeq2(g.g0, 0xC000C000u) & 0x00010001u;
+  h.o = o1 | o0; h.k1 = KINV_CAP - o1; h.k0 = KINV_CAP - o0;
+  return h;
+}
+// min(min(xc, kc) + mc, y + my, cap): xc is the operand added to the negated metric
+__device__ __forceinline__ u32 acs_inv_hz(u32 xc, u32 kc, u32 mc, u32 y, u32 my, u32 cap) {
+  return __vimin3_u16x2(__vadd2(__vminu2(xc, kc), mc), __vadd2(y, my), cap);
+}
+template <class G>
+__device__ __forceinline__ void alpha_step_inv_hz(u32 (&a)[8], const G& g) {
+  const HzOff h = hz_offsets(g);
+  const u32 cap = KINV_CAP + h.o;
+  const u32 n1 = __vadd2(g.n1, h.o), g1 = __vadd2(g.g1, h.o), n0 = __vadd2(g.n0, h.o), g0 = __vadd2(g.g0, h.o);
+  u32 n[8];
+  n[0] = acs_inv_hz(a[1], h.k1, n1, a[0], g1, cap);
+  n[1] = acs_inv_hz(a[2], h.k0, n0, a[3], g0, cap);
+  n[2] = acs_inv_hz(a[5], h.k0, n0, a[4], g0, cap);
+  n[3] = acs_inv_hz(a[6], h.k1, n1, a[7], g1, cap);
+  n[4] = acs_inv_hz(a[0], h.k1, n1, a[1], g1, cap);
+  n[5] = acs_inv_hz(a[3], h.k0, n0, a[2], g0, cap);
+  n[6] = acs_inv_hz(a[4], h.k0, n0, a[5], g0, cap);
+  n[7] = acs_inv_hz(a[7], h.k1, n1, a[6], g1, cap);
+  norm_inv(a, n);
+}
+template <class G>
+__device__ __forceinline__ void beta_step_inv_hz(u32 (&b)[8], const G& g) {
+  const HzOff h = hz_offsets(g);
+  const u32 cap = KINV_CAP + h.o;
+  const u32 n1 = __vadd2(g.n1, h.o), g1 = __vadd2(g.g1, h.o), n0 = __vadd2(g.n0, h.o), g0 = __vadd2(g.g0, h.o);
+  u32 n[8];
+  n[0] = acs_inv_hz(b[4], h.k1, n1, b[0], g1, cap);
+  n[1] = acs_inv_hz(b[0], h.k1, n1, b[4], g1, cap);
+  n[2] = acs_inv_hz(b[1], h.k0, n0, b[5], g0, cap);
+  n[3] = acs_inv_hz(b[5], h.k0, n0, b[1], g0, cap);
+  n[4] = acs_inv_hz(b[6], h.k0, n0, b[2], g0, cap);
+  n[5] = acs_inv_hz(b[2], h.k0, n0, b[6], g0, cap);
+  n[6] = acs_inv_hz(b[3], h.k1, n1, b[7], g1, cap);
+  n[7] = acs_inv_hz(b[7], h.k1, n1, b[3], g1, cap);
+  norm_inv(b, n);
+}
+// LLR of a hazard step: the four sums m + x get the same offset; m10 + g0 and m11 + g1 add -16384 to a magnitude that
+// may be 32768 -- clamped to 32767 like above.  16383 + o - r turns the two minima back into exact signed values.
+template <class G>
+__device__ __forceinline__ u32 ext_step_inv_hz(const u32 (&al)[8], const u32 (&be)[8], const G& g) {
+  constexpr u32 K16383 = 0x3fff3fffu, K32767 = 0x7fff7fffu, K32768 = 0x80008000u;
+  u32 ua[8], ub[8], uat[8], ubt[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    ua[s] = __vsub2(al[s], K16383); ub[s] = __vsub2(be[s], K16383);
+    uat[s] = __vminu2(ua[s], K32767); ubt[s] = __vminu2(ub[s], K32767);
+  }
+  auto sum = [&](int i, int j) -> u32 { return __vmaxu2(__vadd2(uat[i], ub[j]), __vadd2(ua[i], ubt[j])); };
+  auto grp = [&](int i0, int j0, int i1, int j1, int i2, int j2, int i3, int j3) -> u32 {
+    return __vimin3_u16x2(__vimin3_u16x2(sum(i0, j0), sum(i1, j1), K32768), sum(i2, j2), sum(i3, j3));
+  };
+  const u32 u00 = grp(0, 0, 1, 4, 6, 7, 7, 3);
+  const u32 u11 = grp(0, 4, 1, 0, 6, 3, 7, 7);
+  const u32 u01 = grp(2, 5, 3, 1, 4, 2, 5, 6);
+  const u32 u10 = grp(2, 1, 3, 5, 4, 6, 5, 2);
+  const u32 o1 = __vcmpeq2(g.g1, 0xC000C000u) & 0x00010001u, o0 = __vcmpeq2(g.g0, 0xC000C000u) & 0x00010001u, o = o1 | o0;
+  const u32 cap = KINV_CAP + o, ko = K16383 + o;
+  const u32 r01 = __viaddmin_u16x2(u01, __vadd2(g.g0, ko), cap);                                   // m01 - g0
+  const u32 r00 = __viaddmin_u16x2(u00, __vadd2(g.g1, ko), cap);                                   // m00 - g1
+  const u32 r10 = __viaddmin_u16x2(__vminu2(u10, K32768 - o0), __vadd2(~g.g0, 0x40004000u + o), cap);   // m10 + g0
+  const u32 r11 = __viaddmin_u16x2(__vminu2(u11, K32768 - o1), __vadd2(~g.g1, 0x40004000u + o), cap);   // m11 + g1
+  const u32 ru = __vminu2(r10, r11), rv = __vminu2(r01, r00);
+  return __vsubss2(__vadd2(~ru, 0x40004000u + o), __vadd2(~rv, 0x40004000u + o));
+}
+
 // a-posteriori LLR of one step, reference :757-818
 template <class AR>
 __device__ __forceinline__ u32 ext_step(const u32 (&a)[8], const u32 (&b)[8], const Gam<AR>& g) {
@@ -238,67 +318,86 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     auto zh = [](u32 x) -> u32 { return (x - 0x00010001u) & ~x & 0x80008000u; };     // some halfword of x is zero
     return (zh(g.g1 ^ 0xC000C000u) | zh(g.g0 ^ 0xC000C000u)) != 0;
   };
-  auto astep = [&](u32 (&x)[8], const Gam<AR>& g) {
-    if (!INV) { alpha_step<AR>(x, g); return; }
-    if (hazard(g)) {
-#pragma unroll
-      for (int s = 0; s < 8; ++s) x[s] = AR::dec(x[s]);
-      alpha_step<AR>(x, g);
-#pragma unroll
-      for (int s = 0; s < 8; ++s) x[s] = AR::enc(x[s]);
-    } else {
-      alpha_step_inv(x, g);
-    }
+  // Every step picks its form from its own branch metrics; both forms stay in the inverted representation.  Only the first
+  // beta step of a sweep (b still signed, see below) runs in signed saturating arithmetic.
+  auto astep = [&](u32 (&x)[8], const Gam<AR>& g) { if (hazard(g)) alpha_step_inv_hz(x, g); else alpha_step_inv(x, g); };
+  auto bstep = [&](u32 (&be)[8], const Gam<AR>& g) { if (hazard(g)) beta_step_inv_hz(be, g); else beta_step_inv(be, g); };
+  auto extv = [&](const u32 (&al)[8], const u32 (&be)[8], const Gam<AR>& g) -> u32 {
+    return hazard(g) ? ext_step_inv_hz(al, be, g) : ext_step_inv(al, be, g);
   };
-  // ext of one step from alpha (stored representation) and beta; b_signed: beta is still in signed form
-  auto extv = [&](const u32 (&al)[8], const u32 (&be)[8], bool b_signed, const Gam<AR>& g) -> u32 {
-    if (!INV) return ext_step<AR>(al, be, g);
-    if (!b_signed && !hazard(g)) return ext_step_inv(al, be, g);
-    u32 as[8], bs[8];
+  // The beta vector that enters the FIRST step of a sweep contains the tail metrics of lane 7, which are computed in
+  // wrapping int16 and may be positive (TD16:474-520): that step (and the LLR that reads this vector) runs in signed
+  // saturating arithmetic; its max-normalised result is <= 0 and goes on in the inverted representation.
+  auto ext_first = [&](const u32 (&al)[8], const u32 (&bs)[8], const Gam<AR>& g) -> u32 {
+    u32 as[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) { as[s] = AR::dec(al[s]); bs[s] = b_signed ? be[s] : AR::dec(be[s]); }
+    for (int s = 0; s < 8; ++s) as[s] = AR::dec(al[s]);
     return ext_step<AR>(as, bs, g);
   };
-  // one backward step.  The beta vector that enters the FIRST step of a sweep contains the tail metrics of lane 7,
-  // which are computed in wrapping int16 and may be positive (TD16:474-520): that step runs in signed saturating
-  // arithmetic; its max-normalised result is <= 0 and goes on in the inverted representation.
-  auto bstep = [&](u32 (&be)[8], bool& b_signed, const Gam<AR>& g) {
-    if (!INV) { beta_step<AR>(be, g); return; }
-    if (b_signed || hazard(g)) {
-      if (!b_signed) {
+  auto bstep_first = [&](u32 (&be)[8], const Gam<AR>& g) {
+    beta_step<AR>(be, g);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) be[s] = AR::dec(be[s]);
-      }
-      beta_step<AR>(be, g);
-#pragma unroll
-      for (int s = 0; s < 8; ++s) be[s] = AR::enc(be[s]);
-      b_signed = false;
-    } else {
-      beta_step_inv(be, g);
-    }
+    for (int s = 0; s < 8; ++s) be[s] = AR::enc(be[s]);
   };
   const int nseg = (W + S - 1) / S;
   u32 a[8];
+  static_assert(S == 8 && INV, "exact policy: 8-step segments (two 4-step chunks per stream) in the inverted representation");
+  const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c (4 steps) of this thread at [c*4]
+  const uint4* par4 = reinterpret_cast<const uint4*>(par);
+  const uint4* s04 = reinterpret_cast<const uint4*>(s0);
+  const int nchunk = (W + 3) >> 2;
+  // Branch metrics of a segment, computed once and shared by the alpha recomputation, the LLR and the beta step.
+  // Measured (tools/exact_path_probe.py, uniform noise +-3000 / +-12000, Gbit/s): every step testing for itself with a
+  // signed-arithmetic fallback 7.5 / 4.3; the same with the in-representation hazard form 7.5 / 6.3; a per-segment mask of
+  // hazard steps 8.0 / 4.3; the 4-thread group instead of the warp voting on the body 8.4 / 3.3; this version 9.1 / 2.6
+  // (coded signals of amplitude 256, where hazards are rare: 12.5 against 9.9 in the waterfall regime).
+  // Returns whether some thread of the warp has a hazard step in the segment (min over all metrics == -16384; they are
+  // >= -16384 by construction).  Segments without one run a branch-free body, the others test every step; the choice is
+  // warp-uniform (threads that disagree would make the warp run both bodies) and changes no result.
+  auto seg_gamma = [&](const uint4 (&sv)[2], const uint4 (&pv)[2], int k0, int k1, Gam<AR> (&g8)[S]) -> bool {
+    u32 m = 0;
+#pragma unroll
+    for (int e = 0; e < S; ++e) {
+      if (k0 + e < k1) {
+        g8[e] = gamma2<AR>(pick4(sv[e >> 2], e & 3), pick4(pv[e >> 2], e & 3));
+        m = __vimin3_s16x2(m, g8[e].g1, g8[e].g0);
+      }
+    }
+    const u32 x = m ^ 0xC000C000u;
+    return __any_sync(__activemask(), ((x - 0x00010001u) & ~x & 0x80008000u) != 0);
+  };
+  auto load_seg2 = [&](int seg, uint4 (&sv)[2], uint4 (&pv)[2]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = seg * 2 + j;
+      if (c < nchunk) { sv[j] = __ldg(sys4 + c * 4); pv[j] = __ldg(par4 + c * 4); }
+    }
+  };
 
   // ---- forward sweep (alpha pass 1), checkpoint every S steps ----------------------
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = AR::enc(pack2(NEG_INIT, NEG_INIT));
   if (t == 0) a[0] = AR::enc(pack2(0, NEG_INIT));               // reference :201-208
-  const uint4* sys4 = reinterpret_cast<const uint4*>(sys);     // chunk c (4 steps) of this thread at [c*4]
-  const uint4* par4 = reinterpret_cast<const uint4*>(par);
-  const uint4* s04 = reinterpret_cast<const uint4*>(s0);
-  uint4 s4n = __ldg(sys4), p4n = __ldg(par4);
-  for (int c = 0; c * 4 < W; ++c) {
-    const uint4 s4 = s4n, p4 = p4n;
-    if ((c + 1) * 4 < W) { s4n = __ldg(sys4 + (c + 1) * 4); p4n = __ldg(par4 + (c + 1) * 4); }   // one chunk ahead
-    const u32 sv[4] = {s4.x, s4.y, s4.z, s4.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
+  {
+    uint4 sf[2], pf[2], sfn[2], pfn[2];
+    load_seg2(0, sf, pf);
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int k0 = seg * S, k1 = min(W, k0 + S);
+      if (seg + 1 < nseg) load_seg2(seg + 1, sfn, pfn);         // one segment ahead
+      Gam<AR> g8[S];
+      const bool hz = seg_gamma(sf, pf, k0, k1, g8);
+      ckpt_put(ck + seg * 32, a);
+      if (!hz) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int k = c * 4 + q;
-      if (k < W) {
-        if (k % S == 0) ckpt_put(ck + (k / S) * 32, a);
-        astep(a, gamma2<AR>(sv[q], pv[q]));
+        for (int e = 0; e < S; ++e)
+          if (k0 + e < k1) alpha_step_inv(a, g8[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < S; ++e)
+          if (k0 + e < k1) astep(a, g8[e]);
       }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { sf[j] = sfn[j]; pf[j] = pfn[j]; }
     }
   }
 
@@ -318,21 +417,19 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     for (int k = 0; k < W; ++k) astep(a, gam(k));
   }
 
-  // ---- beta start: lanes 0..6 <- own alpha[W], lane 7 <- tail metrics (signed form, see bstep) ----
+  // ---- beta start: lanes 0..6 <- own alpha[W], lane 7 <- tail metrics (signed form, see bstep_first) ----
   u32 b[8];
-  bool b_signed = true;
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     b[s] = AR::dec(a[s]);
     if (t == 3) b[s] = (b[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
   }
+  bstep_first(b, gam(W - 1));        // step W-1 of the sweep; the segment loop below skips it
 
   // ---- backward sweep, pass 1 -----------------------------------------------------
   // A segment is two 4-step chunks per stream; its inputs are loaded once into registers (the next segment's are
   // requested at the segment start, a whole segment ahead of their use) and its 8 branch-metric pairs are computed once
   // and shared by the alpha recomputation, the LLR and the beta step.
-  static_assert(S == 8, "exact-path segment = two chunks");
-  const int nchunk = (W + 3) >> 2;
   uint4 sc[2], pc[2], zc[2], sn[2], pn[2], zn[2];
   auto load_seg = [&](int seg, uint4 (&sv)[2], uint4 (&pv)[2], uint4 (&zv)[2]) {
 #pragma unroll
@@ -347,49 +444,55 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     if (seg > 0) load_seg(seg - 1, sn, pn, zn);
     ckpt_get(ck + seg * 32, a);
     Gam<AR> g8[S];
+    const bool hz = seg_gamma(sc, pc, k0, k1, g8);
+    auto seg_body = [&](auto hz_tag) {
+      constexpr bool HZ = decltype(hz_tag)::value;
+      auto a_st = [&](const Gam<AR>& g) { if constexpr (HZ) astep(a, g); else alpha_step_inv(a, g); };
 #pragma unroll
-    for (int e = 0; e < S; ++e) {
-      if (k0 + e < k1) {
-        g8[e] = gamma2<AR>(pick4(sc[e >> 2], e & 3), pick4(pc[e >> 2], e & 3));
-        abuf_put(abuf, e, tid, a);
-        if (k0 + e + 1 < k1) astep(a, g8[e]);
-      }
-    }
-    if (seg == 0) {          // alpha[0..5] come from the re-run chain
-#pragma unroll
-      for (int s = 0; s < 8; ++s) a[s] = seed[s];
-#pragma unroll
-      for (int k = 0; k <= RERUN_STEPS; ++k) {
-        if (k < k1) {
-          abuf_put(abuf, k, tid, a);
-          if (k < RERUN_STEPS) astep(a, g8[k]);
+      for (int e = 0; e < S; ++e) {
+        if (k0 + e < k1) {
+          abuf_put(abuf, e, tid, a);
+          if (k0 + e + 1 < k1) a_st(g8[e]);
         }
       }
-    }
+      if (seg == 0) {          // alpha[0..5] come from the re-run chain
 #pragma unroll
-    for (int j = 1; j >= 0; --j) {
-      u32 e4[4] = {0u, 0u, 0u, 0u};
+        for (int s = 0; s < 8; ++s) a[s] = seed[s];
 #pragma unroll
-      for (int q = 3; q >= 0; --q) {
-        const int e = j * 4 + q, k = k0 + e;
-        if (k < k1) {
-          if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
-            abuf_get(abuf, e, tid, a);
-            u32 x = extv(a, b, b_signed, g8[e]);
-            if (upd) x = __vaddss2(__vsubss2(x, pick4(sc[j], q)), pick4(zc[j], q));     // feedback, reference :1354-1375
-            e4[q] = x;
+        for (int k = 0; k <= RERUN_STEPS; ++k) {
+          if (k < k1) {
+            abuf_put(abuf, k, tid, a);
+            if (k < RERUN_STEPS) a_st(g8[k]);
           }
-          bstep(b, b_signed, g8[e]);
         }
       }
-      const int kc = k0 + j * 4;
-      if (kc + 3 <= W - 7) *reinterpret_cast<uint4*>(ext + ((kc >> 2) << 4)) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
-      else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (kc + q < k1 && kc + q <= W - 7) ext[c4_word(kc + q, 0)] = e4[q];
+      for (int j = 1; j >= 0; --j) {
+        u32 e4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+          const int e = j * 4 + q, k = k0 + e;
+          if (k < k1) {
+            if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
+              abuf_get(abuf, e, tid, a);
+              u32 x;
+              if constexpr (HZ) x = extv(a, b, g8[e]); else x = ext_step_inv(a, b, g8[e]);
+              if (upd) x = __vaddss2(__vsubss2(x, pick4(sc[j], q)), pick4(zc[j], q));     // feedback, reference :1354-1375
+              e4[q] = x;
+            }
+            if (k != W - 1) { if constexpr (HZ) bstep(b, g8[e]); else beta_step_inv(b, g8[e]); }
+          }
+        }
+        const int kc = k0 + j * 4;
+        if (kc + 3 <= W - 7) *reinterpret_cast<uint4*>(ext + ((kc >> 2) << 4)) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (kc + q < k1 && kc + q <= W - 7) ext[c4_word(kc + q, 0)] = e4[q];
+        }
       }
-    }
+    };
+    if (hz) seg_body(std::true_type{}); else seg_body(std::false_type{});
 #pragma unroll
     for (int j = 0; j < 2; ++j) { sc[j] = sn[j]; pc[j] = pn[j]; zc[j] = zn[j]; }
   }
@@ -397,12 +500,11 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   // ---- beta re-run: lane l <- beta[0] of lane l+1, lane 7 <- tail metrics ------------
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
-    const u32 mine = b_signed ? b[s] : AR::dec(b[s]);           // back to signed form: lane 7 takes the tail metrics again
+    const u32 mine = AR::dec(b[s]);                            // back to signed form: lane 7 takes the tail metrics again
     u32 next = __shfl_sync(gmask, mine, (t + 1) & 3, 4);      // thread t+1 (lanes 2t+2, 2t+3)
     if (t == 3) next = (u32)(uint16_t)Tv[s];
     b[s] = __byte_perm(mine, next, 0x5432);                    // lo <- mine.hi, hi <- next.lo
   }
-  b_signed = true;
   {
     const int kk0 = max(W - 6, 0);
     const int sa = kk0 / S;
@@ -419,11 +521,17 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
         if (k < RERUN_STEPS) astep(a, gam(k));
       }
     }
-    for (int k = W - 1; k >= kk0; --k) {
+    {                                                          // step W-1: b is still signed
+      const Gam<AR> g = gam(W - 1);
+      abuf_get(abuf, W - 1 - kk0, tid, a);
+      ext[c4_word(W - 1, 0)] = fb(ext_first(a, b, g), W - 1);
+      bstep_first(b, g);
+    }
+    for (int k = W - 2; k >= kk0; --k) {
       const Gam<AR> g = gam(k);
       abuf_get(abuf, k - kk0, tid, a);
-      ext[c4_word(k, 0)] = fb(extv(a, b, b_signed, g), k);
-      if (k >= W - RERUN_STEPS) bstep(b, b_signed, g);           // loopval=(n-40)>>3, reference :585
+      ext[c4_word(k, 0)] = fb(extv(a, b, g), k);
+      if (k >= W - RERUN_STEPS) bstep(b, g);                   // loopval=(n-40)>>3, reference :585
     }
   }
 }
