@@ -330,6 +330,30 @@ def run_b200(args):
                              "distinct_blocks": nd}
             del y_r, out_r, st_r
 
+    # ---- side measurement: TX mirror (encoder + sub-block interleaver + rate matching), device pointers ----
+    tx_side = None
+    if world == 1 and not args.no_regimes:
+        G_tx = 11520                                            # 100 PRB MCS16 uplink share of one K=6144 block (configs[3])
+        c_dev = torch.randint(0, 256, (B, K // 8), dtype=torch.uint8, device="cuda")
+        e_dev = torch.zeros((B, G_tx), dtype=torch.uint8, device="cuda")
+        descs = (capi.TxDesc * B)()
+        for i in range(B):
+            d = descs[i]
+            d.c = c_dev.data_ptr() + i * (K // 8); d.e = e_dev.data_ptr() + i * G_tx
+            d.K = K; d.G = G_tx; d.Nsoft = 1827072; d.C = 1; d.Mdlharq = 8; d.Kmimo = 1; d.Qm = 2; d.Nl = 1
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(4):                                      # the call is synchronous: wall clock around it, best of 4
+            tx0 = time.perf_counter()
+            rc = capi.lib.oai_turbo_tx_batch(descs, B, capi.TX_DEVICE_POINTERS, -1)
+            tx_dt = time.perf_counter() - tx0
+            if rc:
+                raise SystemExit("bench.py: oai_turbo_tx_batch failed: " + capi.last_error())
+            best = tx_dt if best is None else min(best, tx_dt)
+        tx_side = {"value": B * K / best / 1e6, "unit": "Mbit/s", "blocks": B, "E": G_tx, "ms": best * 1e3,
+                   "api": "oai_turbo_tx_batch, device pointers (descriptor staging inside the call)"}
+        del c_dev, e_dev
+
     # final result gather (outside every timed region): per-rank block / bit / status counts
     from openair4g_b200 import sharding
     recs = sharding.gather_results(st_dev, B * K, dist)
@@ -405,7 +429,7 @@ def run_b200(args):
                              % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6),
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
                        "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
-            "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes,
+            "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes, "tx_mirror": tx_side,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
                     "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
                     "in_flight": 1 if args.e2e_serial else 2,

@@ -434,17 +434,28 @@ namespace oai {
 // per-thread scratch for the single-call reference entry points of the front end
 struct Scratch {
   cudaStream_t st = nullptr;
-  void* h = nullptr; void* d = nullptr; size_t cap = 0;
-  int ensure(size_t bytes) {
+  void* h = nullptr; void* d = nullptr; size_t cap = 0, dcap = 0;
+  // host_bytes: size of the page-locked mirror (defaults to the device size; smaller when part of the device area is
+  // never copied, e.g. the intermediate d of the TX batch)
+  int ensure(size_t bytes, size_t host_bytes = (size_t)-1) {
     DevCtx* c;
     int rc = ctx_get(-1, &c);
     if (rc) return rc;
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    if (bytes > cap) {
-      if (h) { cudaFreeHost(h); cudaFree(d); }
-      cap = bytes + (bytes >> 2) + 4096;
-      CU(cudaMallocHost(&h, cap));
-      CU(cudaMalloc(&d, cap));
+    if (host_bytes == (size_t)-1) host_bytes = bytes;
+    if (host_bytes > cap) {
+      if (h) cudaFreeHost(h);
+      h = nullptr; cap = 0;
+      const size_t want = host_bytes + (host_bytes >> 2) + 4096;
+      CU(cudaMallocHost(&h, want));
+      cap = want;
+    }
+    if (bytes > dcap) {
+      if (d) cudaFree(d);
+      d = nullptr; dcap = 0;
+      const size_t want = bytes + (bytes >> 2) + 4096;
+      CU(cudaMalloc(&d, want));
+      dcap = want;
     }
     return 0;
   }
@@ -1312,7 +1323,7 @@ int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
   }
   const size_t o_e = up256(cur_c), o_d = o_e + up256(tot_e), total = o_d + up256(tot_d);
   Scratch& sc = t_scratch;
-  if (sc.ensure(total)) return fail(-100, "oai_turbo_tx_batch: GPU path failed (%s)", g_err);
+  if (sc.ensure(total, o_d)) return fail(-100, "oai_turbo_tx_batch: GPU path failed (%s)", g_err);   // d is device-only
   char* h = (char*)sc.h; char* d = (char*)sc.d;
   for (int i = 0; i < n; ++i) {
     TxBlock& b = tb[i];
