@@ -349,12 +349,14 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   // Branch metrics of a segment, computed once and shared by the alpha recomputation, the LLR and the beta step.
   // Measured (tools/exact_path_probe.py, uniform noise +-3000 / +-12000, Gbit/s): every step testing for itself with a
   // signed-arithmetic fallback 7.5 / 4.3; the same with the in-representation hazard form 7.5 / 6.3; a per-segment mask of
-  // hazard steps 8.0 / 4.3; the 4-thread group instead of the warp voting on the body 8.4 / 3.3; this version 9.1 / 2.6
-  // (coded signals of amplitude 256, where hazards are rare: 12.5 against 9.9 in the waterfall regime).
+  // hazard steps 8.0 / 4.3; two bodies, the hazard one testing every step 9.1 / 2.6; the 4-thread group instead of the
+  // warp voting on the body 8.4 / 3.3; two branch-free bodies chosen per segment 9.0 / 3.5; hazard body only 6.5 / 6.4;
+  // this version (per segment, but per pass once hazards are frequent) 9.0 / 6.3.
   // Returns whether some thread of the warp has a hazard step in the segment (min over all metrics == -16384; they are
-  // >= -16384 by construction).  Segments without one run a branch-free body, the others test every step; the choice is
-  // warp-uniform (threads that disagree would make the warp run both bodies) and changes no result.
-  auto seg_gamma = [&](const uint4 (&sv)[2], const uint4 (&pv)[2], int k0, int k1, Gam<AR> (&g8)[S]) -> bool {
+  // >= -16384 by construction).  Segments without one run the plain steps, the others the hazard form of every step
+  // (which equals the plain form where the offset is 0); both bodies are branch-free, the choice is warp-uniform
+  // (threads that disagree would make the warp run both bodies) and changes no result.
+  auto seg_gamma = [&](const uint4 (&sv)[2], const uint4 (&pv)[2], int k0, int k1, Gam<AR> (&g8)[S], bool force) -> bool {
     u32 m = 0;
 #pragma unroll
     for (int e = 0; e < S; ++e) {
@@ -364,7 +366,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
       }
     }
     const u32 x = m ^ 0xC000C000u;
-    return __any_sync(__activemask(), ((x - 0x00010001u) & ~x & 0x80008000u) != 0);
+    return __any_sync(__activemask(), force || ((x - 0x00010001u) & ~x & 0x80008000u) != 0);
   };
   auto load_seg2 = [&](int seg, uint4 (&sv)[2], uint4 (&pv)[2]) {
 #pragma unroll
@@ -375,17 +377,20 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   };
 
   // ---- forward sweep (alpha pass 1), checkpoint every S steps ----------------------
+  int nhz = 0;                                                  // hazard segments met by this warp
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = AR::enc(pack2(NEG_INIT, NEG_INIT));
   if (t == 0) a[0] = AR::enc(pack2(0, NEG_INIT));               // reference :201-208
   {
     uint4 sf[2], pf[2], sfn[2], pfn[2];
     load_seg2(0, sf, pf);
+    nhz = 0;
     for (int seg = 0; seg < nseg; ++seg) {
       const int k0 = seg * S, k1 = min(W, k0 + S);
       if (seg + 1 < nseg) load_seg2(seg + 1, sfn, pfn);         // one segment ahead
       Gam<AR> g8[S];
-      const bool hz = seg_gamma(sf, pf, k0, k1, g8);
+      const bool hz = seg_gamma(sf, pf, k0, k1, g8, false);
+      nhz += hz ? 1 : 0;
       ckpt_put(ck + seg * 32, a);
       if (!hz) {
 #pragma unroll
@@ -394,7 +399,7 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
       } else {
 #pragma unroll
         for (int e = 0; e < S; ++e)
-          if (k0 + e < k1) astep(a, g8[e]);
+          if (k0 + e < k1) alpha_step_inv_hz(a, g8[e]);
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) { sf[j] = sfn[j]; pf[j] = pfn[j]; }
@@ -430,6 +435,10 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
   // A segment is two 4-step chunks per stream; its inputs are loaded once into registers (the next segment's are
   // requested at the segment start, a whole segment ahead of their use) and its 8 branch-metric pairs are computed once
   // and shared by the alpha recomputation, the LLR and the beta step.
+  // The two unrolled bodies of the backward sweep do not fit the instruction cache together: a pass in which more than
+  // a quarter of the segments have a hazard step (uniform +-12000 noise: alternating bodies ran at 3.5 Gbit/s, the hazard
+  // body alone at 6.4) takes the hazard body for every segment.
+  const bool always_hz = nhz * 4 > nseg;
   uint4 sc[2], pc[2], zc[2], sn[2], pn[2], zn[2];
   auto load_seg = [&](int seg, uint4 (&sv)[2], uint4 (&pv)[2], uint4 (&zv)[2]) {
 #pragma unroll
@@ -444,10 +453,10 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
     if (seg > 0) load_seg(seg - 1, sn, pn, zn);
     ckpt_get(ck + seg * 32, a);
     Gam<AR> g8[S];
-    const bool hz = seg_gamma(sc, pc, k0, k1, g8);
+    const bool hz = seg_gamma(sc, pc, k0, k1, g8, always_hz);
     auto seg_body = [&](auto hz_tag) {
       constexpr bool HZ = decltype(hz_tag)::value;
-      auto a_st = [&](const Gam<AR>& g) { if constexpr (HZ) astep(a, g); else alpha_step_inv(a, g); };
+      auto a_st = [&](const Gam<AR>& g) { if constexpr (HZ) alpha_step_inv_hz(a, g); else alpha_step_inv(a, g); };
 #pragma unroll
       for (int e = 0; e < S; ++e) {
         if (k0 + e < k1) {
@@ -476,11 +485,11 @@ __device__ void map_pass(const u32* __restrict__ sys, const u32* __restrict__ pa
             if (k <= W - 7) {       // steps whose beta[k+1] is not replaced by the re-run
               abuf_get(abuf, e, tid, a);
               u32 x;
-              if constexpr (HZ) x = extv(a, b, g8[e]); else x = ext_step_inv(a, b, g8[e]);
+              if constexpr (HZ) x = ext_step_inv_hz(a, b, g8[e]); else x = ext_step_inv(a, b, g8[e]);
               if (upd) x = __vaddss2(__vsubss2(x, pick4(sc[j], q)), pick4(zc[j], q));     // feedback, reference :1354-1375
               e4[q] = x;
             }
-            if (k != W - 1) { if constexpr (HZ) bstep(b, g8[e]); else beta_step_inv(b, g8[e]); }
+            if (k != W - 1) { if constexpr (HZ) beta_step_inv_hz(b, g8[e]); else beta_step_inv(b, g8[e]); }
           }
         }
         const int kc = k0 + j * 4;
