@@ -218,6 +218,45 @@ def test_log_map16_internals_match_reference(port, ref):
                 assert np.array_equal(b1[:64 * (W + 1)], b2[:64 * (W + 1)])
 
 
+def test_log_map16_corner_inputs_match_reference(port, ref):
+    """The crafted corner inputs of tests/test_gpu_map_pass.py (branch metrics of exactly -16384, metrics saturated at
+    -32768, positive tail metrics) through the port's and the compiled reference's log_map16: LLRs, alpha and beta."""
+    from test_gpu_map_pass import craft
+    for kind in ("sparse_hazard", "dense_hazard", "edges", "saturated", "positive_tail"):
+        rng = np.random.default_rng(sum(map(ord, kind)))
+        for n in (40, 48, 512, 6144):
+            y = craft(n, kind, rng)
+            W = n // 8
+            pos = np.arange(n)
+            st = (pos % W) * 8 + pos // W
+            for term in (0, 1):
+                sys_ = loader.aligned(n + 64, np.int16)
+                par = loader.aligned(n + 64, np.int16)
+                sys_[:] = 0
+                par[:] = 0
+                sys_[st] = y[0:3 * n:3]
+                par[st] = y[(2 if term else 1):3 * n:3]
+                t = y[3 * n:]
+                for i in range(3):
+                    if term == 0:
+                        sys_[n + i] = t[2 * i]; par[n + i] = t[2 * i + 1]
+                    else:
+                        sys_[n + 8 + i] = t[6 + 2 * i]; par[n + i] = t[7 + 2 * i]
+                ab = 8 * (n + 16)
+                a1, b1 = loader.aligned(ab, np.int16), loader.aligned(ab, np.int16)
+                m11, m10 = loader.aligned(n + 64, np.int16), loader.aligned(n + 64, np.int16)
+                e1 = loader.aligned(n + 128, np.int16)
+                ref.log_map16(sys_.ctypes.data, par.ctypes.data, m11.ctypes.data, m10.ctypes.data,
+                              a1.ctypes.data, b1.ctypes.data, e1.ctypes.data, n, term, 0, 0, None, None, None, None)
+                a2, b2 = np.zeros(ab, np.int16), np.zeros(ab, np.int16)
+                e2 = np.zeros(n + 16, np.int16)
+                port.orc_log_map16(np.ascontiguousarray(sys_[:n + 16]), np.ascontiguousarray(par[:n + 16]), e2, n, term,
+                                   a2.ctypes.data, b2.ctypes.data)
+                assert np.array_equal(e1[:n], e2[:n]), (kind, n, term)
+                assert np.array_equal(a1[:64 * (W + 1)], a2[:64 * (W + 1)]), (kind, n, term)
+                assert np.array_equal(b1[:64 * (W + 1)], b2[:64 * (W + 1)]), (kind, n, term)
+
+
 def test_td8_all_sizes_of_its_domain(ref):
     """8-bit decoder: every K >= 256 with K % 16 == 0 (145 sizes), all input-scaling brackets
     (amplitudes 8..2000 and full-range int16), both hard-decision rules (K % 128 == 0 or not)."""
