@@ -819,7 +819,7 @@ struct HostBatch {
     const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
     auto front_end = [&](size_t jlo, size_t jhi) {            // dematch (+ deinterleave) of rm blocks [jlo, jhi) on st
       const int cnt = (int)(jhi - jlo);
-      k_rm_rx<<<cnt, RM_THREADS, deint_smem / 2, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);   // one flag byte per slot
+      k_rm_rx<<<cnt, RM_THREADS, 0, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);
       ++g_launches;
       if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
@@ -1223,7 +1223,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
   memcpy(h + o_dm, dummy_w, q.Ncb);
   memcpy(h + o_e, soft_input, (size_t)q.E * 2);
   CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, sc.st));
-  k_rm_rx<<<1, RM_THREADS, q.Ncb + 16, sc.st>>>((const RmBlock*)d, 1, (int16_t*)(d + o_w), (const int16_t*)(d + o_e), (const uint8_t*)(d + o_dm));
+  k_rm_rx<<<1, RM_THREADS, 0, sc.st>>>((const RmBlock*)d, 1, (int16_t*)(d + o_w), (const int16_t*)(d + o_e), (const uint8_t*)(d + o_dm));
   ++g_launches;
   CU(cudaMemcpyAsync(h + o_w, d + o_w, (size_t)q.Ncb * 2, cudaMemcpyDeviceToHost, sc.st));
   CU(cudaStreamSynchronize(sc.st));
@@ -1270,12 +1270,12 @@ void threegpplte_turbo_encoder(uint8_t* input, uint16_t input_length_bytes, uint
   if (sc.ensure(total) || ctx_get(-1, &c)) { fprintf(stderr, "[oai_turbo_b200] threegpplte_turbo_encoder: GPU path failed (%s)\n", g_err); return; }
   TxBlock b;
   memset(&b, 0, sizeof(b));
-  b.K = K; b.qpp_off = c->qpp_off[idx]; b.c_off_lo = (uint32_t)o_c; b.d_off_lo = (uint32_t)o_d;
+  b.K = K; b.f1 = kQpp[idx][0]; b.f2 = kQpp[idx][1]; b.c_off_lo = (uint32_t)o_c; b.d_off_lo = (uint32_t)o_d;
   char* h = (char*)sc.h; char* d = (char*)sc.d;
   memcpy(h, &b, sizeof(b));
   memcpy(h + o_c, input, input_length_bytes);
   cudaMemcpyAsync(d, h, o_d, cudaMemcpyHostToDevice, sc.st);
-  k_turbo_enc<<<1, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, 1, (const uint8_t*)d, (uint8_t*)d, c->qpp_pool);
+  k_turbo_enc<<<1, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, 1, (const uint8_t*)d, (uint8_t*)d);
   ++g_launches;
   cudaMemcpyAsync(h + o_d, d + o_d, 3 * (size_t)K + 12, cudaMemcpyDeviceToHost, sc.st);
   if (cudaStreamSynchronize(sc.st) != cudaSuccess) { fail(-100, "threegpplte_turbo_encoder: CUDA failure"); return; }
@@ -1361,7 +1361,7 @@ int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
     memset(&b, 0, sizeof(b));
     b.K = t.K; b.F = t.filler_null ? t.F : 0; b.RTC = q.RTC; b.Kpi = q.Kpi; b.ND = q.ND; b.Ncb = q.Ncb; b.k0 = q.k0;
     b.E = (q.Ncb < 3 * q.Kpi) ? 0 : q.E;
-    b.qpp_off = c->qpp_off[idx]; b.w_from_d = 1;
+    b.f1 = kQpp[idx][0]; b.f2 = kQpp[idx][1]; b.w_from_d = 1;
     t.E = b.E;
     max_ncb = std::max(max_ncb, q.Ncb);
     if (devp) {
@@ -1394,7 +1394,7 @@ int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
   CU(cudaMemcpyAsync(d, h, devp ? o_c : o_e, cudaMemcpyHostToDevice, sc.st));
   const uint8_t* cbase = devp ? nullptr : (const uint8_t*)d;
   uint8_t* ebase = devp ? nullptr : (uint8_t*)d;
-  k_turbo_enc<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, n, cbase, (uint8_t*)d, c->qpp_pool);
+  k_turbo_enc<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, sc.st>>>((const TxBlock*)d, n, cbase, (uint8_t*)d);
   k_rm_tx<<<n, RM_THREADS, max_ncb + 16, sc.st>>>((const TxBlock*)d, n, (const uint8_t*)d, nullptr, ebase);
   g_launches += 2;
   if (!devp && tot_e) CU(cudaMemcpyAsync(h + o_e, d + o_e, tot_e, cudaMemcpyDeviceToHost, sc.st));

@@ -76,10 +76,41 @@ __global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, u
     if (dummy_is_null(i, RTC, Kpi, ND, F, magic)) w[i] = 2;
 }
 
-// Dynamic shared memory: one flag byte per circular-buffer slot (Ncb <= 3*Kpi bytes).
-// Pass 1 marks the slots that carry soft bits and counts them (N in [0,Ncb), and those before the start index);
-// pass 2 walks the buffer in coalesced chunks of 256 slots with a running block-wide prefix count, so that every
-// thread knows the rank of its slot on the reference's walk and adds e[rank], e[rank+N], ... to it.
+// Ranks on the circular-buffer walk.  The slots are handled in groups of 32 (one warp ballot each, RM_GROUPS_MAX groups for
+// 3*Kpi = 18 528 slots); s_bal[g] holds the ballot of the slots that carry a bit, s_pre[g] the number of such slots in all
+// groups before g.  One block-wide scan replaces the running prefix that cost two barriers per 256 slots.
+constexpr int RM_GROUPS_MAX = 580;
+__device__ __forceinline__ uint32_t rm_scan_groups(const uint32_t* s_bal, uint32_t* s_pre, uint32_t ng, uint32_t* s_w) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  static_assert(RM_GROUPS_MAX <= 3 * RM_THREADS, "three groups per thread");
+  uint32_t loc[3], tsum = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint32_t g = threadIdx.x * 3 + j;
+    loc[j] = (g < ng) ? __popc(s_bal[g]) : 0u;
+    tsum += loc[j];
+  }
+  uint32_t x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < RM_THREADS / 32; ++k) { const uint32_t v = s_w[k]; total += v; wbase += (k < wid) ? v : 0u; }
+  uint32_t excl = wbase + x - tsum;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint32_t g = threadIdx.x * 3 + j;
+    if (g < ng) { s_pre[g] = excl; excl += loc[j]; }
+  }
+  __syncthreads();
+  return total;
+}
+
+// Pass 1 takes one ballot per 32 circular-buffer slots of the slots that carry soft bits; a block-wide scan gives every
+// group its prefix count (and N, and the count before the start index); pass 2 walks the buffer coalesced: every thread
+// knows the rank of its slot on the reference's walk and adds e[rank], e[rank+N], ... to it.
 // With gold != nullptr and b.gold_off set, the soft bits are descrambled on the fly (dlsch_unscrambling,
 // LTE_TRANSPORT/dlsch_scrambling.c:99-138): soft bit k is NEGATED where scrambling bit scr_off + k is 0.  (The reference
 // stores the product back as int16, so -32768 stays -32768; under the int16 wrap of the accumulation below, adding
@@ -87,8 +118,7 @@ __global__ void k_dummy_w(uint8_t* w, uint32_t RTC, uint32_t Kpi, uint32_t ND, u
 __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
                                                       const int16_t* e_pool, const uint8_t* dummy_pool,
                                                       int16_t* harq_pool = nullptr, const uint32_t* gold = nullptr) {
-  extern __shared__ uint8_t sflag[];
-  __shared__ uint32_t s_w[RM_THREADS / 32], s_a[RM_THREADS / 32], s_b[RM_THREADS / 32];
+  __shared__ uint32_t s_bal[RM_GROUPS_MAX], s_pre[RM_GROUPS_MAX], s_w[RM_THREADS / 32];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
   const RmBlock b = blocks[blk];
@@ -97,53 +127,37 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
   const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
   const uint32_t magic = 0xffffffffu / b.RTC + 1;
   const uint32_t* gs = (gold && b.gold_off != 0xffffffffu) ? gold + b.gold_off : nullptr;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   // the first reference loop runs only when k0 < Ncb (:747)
   const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
-  uint32_t cnt = 0, cntb = 0;
-  for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
-    const bool nul = dm ? (dm[i] == 2) : dummy_is_null(i, b.RTC, b.Kpi, b.ND, b.F, magic);
-    sflag[i] = nul ? 0 : 1;
-    cnt += nul ? 0u : 1u;
-    cntb += (!nul && i < start) ? 1u : 0u;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); cntb += __shfl_xor_sync(0xffffffffu, cntb, o); }
-  if (lane == 0) { s_a[wid] = cnt; s_b[wid] = cntb; }
-  __syncthreads();
-  uint32_t N = 0, before_start = 0;                     // non-NULL slots in [0,Ncb) / before `start`
-#pragma unroll
-  for (int i = 0; i < RM_THREADS / 32; ++i) { N += s_a[i]; before_start += s_b[i]; }
-  if (N == 0) return;                                   // (the reference would loop forever)
-  uint32_t base = 0;
+  const uint32_t ng = (b.Ncb + 31) >> 5;
   for (uint32_t c0 = 0; c0 < b.Ncb; c0 += RM_THREADS) {
     const uint32_t i = c0 + threadIdx.x;
-    const bool f = (i < b.Ncb) && sflag[i];
+    const bool f = (i < b.Ncb) && !(dm ? (dm[i] == 2) : dummy_is_null(i, b.RTC, b.Kpi, b.ND, b.F, magic));
     const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_w[wid] = __popc(bal);
-    __syncthreads();
-    uint32_t woff = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < RM_THREADS / 32; ++k) { const uint32_t v = s_w[k]; tot += v; woff += (k < wid) ? v : 0u; }
-    if (i < b.Ncb) {
-      int acc = (b.clear == 1) ? 0 : (int)w[i];          // memset(w,0,Ncb) when clear==1 (:741-742)
-      if (f) {
-        const uint32_t c = base + woff + __popc(bal & ((1u << lane) - 1u));
-        const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
-        if (gs) {
-          for (uint32_t k = rank; k < b.E; k += N) {
-            const uint32_t pos = b.scr_off + k;
-            const int v = e[k];
-            acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
-          }
-        } else {
-          for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+    if (lane == 0 && (i >> 5) < ng) s_bal[i >> 5] = bal;
+  }
+  __syncthreads();
+  const uint32_t N = rm_scan_groups(s_bal, s_pre, ng, s_w);         // non-NULL slots in [0,Ncb)
+  if (N == 0) return;                                   // (the reference would loop forever)
+  const uint32_t before_start = s_pre[start >> 5] + __popc(s_bal[start >> 5] & ((1u << (start & 31)) - 1u));
+  for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
+    const uint32_t bal = s_bal[i >> 5];
+    int acc = (b.clear == 1) ? 0 : (int)w[i];            // memset(w,0,Ncb) when clear==1 (:741-742)
+    if ((bal >> lane) & 1u) {
+      const uint32_t c = s_pre[i >> 5] + __popc(bal & ((1u << lane) - 1u));
+      const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
+      if (gs) {
+        for (uint32_t k = rank; k < b.E; k += N) {
+          const uint32_t pos = b.scr_off + k;
+          const int v = e[k];
+          acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
         }
+      } else {
+        for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
       }
-      w[i] = (int16_t)acc;                               // wraps like the reference's int16 +=
     }
-    base += tot;
-    __syncthreads();
+    w[i] = (int16_t)acc;                                 // wraps like the reference's int16 +=
   }
 }
 

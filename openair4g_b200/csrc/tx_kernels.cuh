@@ -22,7 +22,7 @@ struct TxBlock {
   uint32_t K, F;                 // block size; filler bits that are NULL in streams 0/1 of w (0: the reference's TX, which sends them)
   uint32_t RTC, Kpi, ND;
   uint32_t Ncb, k0, E;
-  uint32_t qpp_off;              // offset of pi[] of this K in the plain QPP pool
+  uint32_t f1, f2;               // QPP coefficients of this K: pi(i) = (f1 i + f2 i^2) mod K
   uint32_t w_from_d;             // 1: build w from d (fused interleaver), 0: w is given (w_off)
   uint32_t c_off_lo, c_off_hi;   // byte offset of the K/8 info bytes
   uint32_t d_off_lo, d_off_hi;   // byte offset of d (3K+12 bytes, multiple of 4)
@@ -43,25 +43,42 @@ __device__ __forceinline__ uint32_t lin3(uint32_t cols, uint32_t s) {       // (
 }
 
 __global__ void __launch_bounds__(ENC_WARPS * 32) k_turbo_enc(const TxBlock* blocks, int nblk, const uint8_t* c_pool,
-                                                               uint8_t* d_pool, const uint16_t* qpp_pool) {
+                                                               uint8_t* d_pool) {
   __shared__ uint8_t s_c[ENC_WARPS][768];
+  __shared__ uint32_t s_i[ENC_WARPS][6][32];     // interleaved input bits of each lane's run: word w of lane l at [w][l]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int blk = blockIdx.x * ENC_WARPS + wid;
   if (blk >= nblk) return;
   const TxBlock b = blocks[blk];
   const uint8_t* c = c_pool + off64(b.c_off_lo, b.c_off_hi);
   uint8_t* d = d_pool + off64(b.d_off_lo, b.d_off_hi);
-  const uint16_t* pi = qpp_pool + b.qpp_off;
-  const uint32_t KB = b.K >> 3;
+  const uint32_t K = b.K, KB = K >> 3;
   uint8_t* sc = s_c[wid];
   for (uint32_t i = lane; i < KB; i += 32) sc[i] = c[i];
   __syncwarp();
-  auto bit = [&](uint32_t k) -> uint32_t { return (sc[k >> 3] >> (7u - (k & 7u))) & 1u; };     // MSB first
-  const uint32_t nb = (KB + 31) / 32;
+  const uint32_t nb = (KB + 31) / 32;            // <= 24 bytes = 6 words of bits per lane
   const uint32_t k_lo = min(KB, lane * nb) * 8, k_hi = min(KB, (lane + 1) * nb) * 8;
-  // pass 1: zero-state response of this lane's run, both constituent encoders
-  uint32_t sa = 0, sb = 0;
-  for (uint32_t k = k_lo; k < k_hi; ++k) { rsc_step(sa, bit(k)); rsc_step(sb, bit(pi[k])); }
+  // QPP positions by recursion instead of a table read per step (the first version was bound by the shared / global
+  // load queues: ncu mio_throttle 65, lg_throttle 19 per issue): pi(k+1) = pi(k) + g(k), g(k+1) = g(k) + 2 f2 (mod K),
+  // g(k) = f1 + f2 (2k + 1)
+  uint32_t pi = (uint32_t)(((unsigned long long)b.f1 * k_lo + ((unsigned long long)b.f2 * k_lo % K) * k_lo) % K);
+  uint32_t g = (uint32_t)((b.f1 + (unsigned long long)b.f2 * (2 * k_lo + 1)) % K);
+  const uint32_t g2 = (2 * b.f2) % K;
+  // pass 1: zero-state response of this lane's run, both constituent encoders; the interleaved input bits are kept
+  uint32_t sa = 0, sb = 0, acc = 0;
+  for (uint32_t k = k_lo; k < k_hi; k += 8) {
+    const uint32_t byte = sc[k >> 3], sh = (k - k_lo) & 31u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      rsc_step(sa, (byte >> (7 - q)) & 1u);                                   // MSB first
+      const uint32_t ui = (sc[pi >> 3] >> (7u - (pi & 7u))) & 1u;
+      rsc_step(sb, ui);
+      acc |= ui << (sh + q);
+      pi += g; pi -= (pi >= K) ? K : 0u;
+      g += g2; g -= (g >= K) ? K : 0u;
+    }
+    if (sh == 24 || k + 8 >= k_hi) { s_i[wid][(k - k_lo) >> 5][lane] = acc; acc = 0; }
+  }
   // M^len: images of the three basis states under (k_hi - k_lo) zero-input steps (M^7 = 1)
   uint32_t c1 = 1, c2 = 2, c4 = 4;
   for (uint32_t i = 0; i < (k_hi - k_lo) % 7; ++i) { rsc_step(c1, 0); rsc_step(c2, 0); rsc_step(c4, 0); }
@@ -75,18 +92,24 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_turbo_enc(const TxBlock* blo
   }
   // pass 2: d[3k] = c_k, d[3k+1] = z_k, d[3k+2] = z'_k; four steps = three aligned words
   sa = mya; sb = myb;
-  for (uint32_t k = k_lo; k < k_hi; k += 4) {
-    uint32_t by[12];
+  for (uint32_t k = k_lo; k < k_hi; k += 8) {
+    const uint32_t byte = sc[k >> 3], sh = (k - k_lo) & 31u;
+    if (sh == 0) acc = s_i[wid][(k - k_lo) >> 5][lane];
+    const uint32_t ib = acc >> sh;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t u = bit(k + q);
-      by[3 * q] = u;
-      by[3 * q + 1] = rsc_step(sa, u);
-      by[3 * q + 2] = rsc_step(sb, bit(pi[k + q]));
+    for (int h = 0; h < 2; ++h) {
+      uint32_t by[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u = (byte >> (7 - 4 * h - q)) & 1u;
+        by[3 * q] = u;
+        by[3 * q + 1] = rsc_step(sa, u);
+        by[3 * q + 2] = rsc_step(sb, (ib >> (4 * h + q)) & 1u);
+      }
+      uint32_t* o = reinterpret_cast<uint32_t*>(d + 3 * (size_t)(k + 4 * h));
+#pragma unroll
+      for (int w = 0; w < 3; ++w) o[w] = by[4 * w] | (by[4 * w + 1] << 8) | (by[4 * w + 2] << 16) | (by[4 * w + 3] << 24);
     }
-    uint32_t* o = reinterpret_cast<uint32_t*>(d + 3 * (size_t)k);
-#pragma unroll
-    for (int w = 0; w < 3; ++w) o[w] = by[4 * w] | (by[4 * w + 1] << 8) | (by[4 * w + 2] << 16) | (by[4 * w + 3] << 24);
   }
   // termination: x = d2 ^ d3 drives the register to zero, z = d1 ^ d3; x z x z x z of encoder 1, then of encoder 2
   if (lane == 0) {
@@ -119,27 +142,30 @@ __global__ void k_sbi_tx(const uint8_t* dbuf, uint8_t* w, uint32_t RTC, uint32_t
 }
 
 // lte_rate_matching_turbo: e[k] = k-th non-NULL entry met on the walk of the circular buffer from k0, wrapping until
-// E bits are out.  Same parallel form as k_rm_rx: with N non-NULL slots, the slot of rank c on the walk supplies
-// e[c], e[c+N], ...  One CTA per block; w lives in shared memory.
+// E bits are out.  Same parallel form as k_rm_rx (one ballot per 32 slots, one block-wide scan): with N non-NULL slots,
+// the slot of rank c on the walk supplies e[c], e[c+N], ...  One CTA per block; w lives in shared memory.
 __global__ void __launch_bounds__(RM_THREADS) k_rm_tx(const TxBlock* blocks, int nblk, const uint8_t* d_pool,
                                                       const uint8_t* w_pool, uint8_t* e_pool) {
   extern __shared__ uint8_t swb[];
-  __shared__ uint32_t s_w[RM_THREADS / 32], s_a[RM_THREADS / 32], s_b[RM_THREADS / 32];
+  __shared__ uint32_t s_bal[RM_GROUPS_MAX], s_pre[RM_GROUPS_MAX], s_w[RM_THREADS / 32];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
   const TxBlock b = blocks[blk];
   if (b.E == 0 || b.Ncb < 3 * b.Kpi) return;            // "Exiting, RM condition" (:508-511): nothing written
   uint8_t* e = e_pool + off64(b.e_off_lo, b.e_off_hi);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const uint32_t magic = 0xffffffffu / b.RTC + 1;
   const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
-  uint32_t cnt = 0, cntb = 0;
-  if (b.w_from_d) {
-    const uint8_t* d = d_pool + off64(b.d_off_lo, b.d_off_hi);
-    const uint32_t D = b.K + 4;
-    for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
-      uint8_t v = 2;
-      if (!dummy_is_null(i, b.RTC, b.Kpi, b.ND, b.F, magic)) {
+  const uint32_t ng = (b.Ncb + 31) >> 5;
+  const uint8_t* d = d_pool + off64(b.d_off_lo, b.d_off_hi);
+  const uint8_t* w = w_pool + off64(b.w_off_lo, b.w_off_hi);
+  const uint32_t D = b.K + 4;
+  for (uint32_t c0 = 0; c0 < b.Ncb; c0 += RM_THREADS) {
+    const uint32_t i = c0 + threadIdx.x;
+    uint8_t v = 2;
+    if (i < b.Ncb) {
+      if (!b.w_from_d) v = w[i];
+      else if (!dummy_is_null(i, b.RTC, b.Kpi, b.ND, b.F, magic)) {
         const uint32_t k = (i < b.Kpi) ? i : ((i - b.Kpi) >> 1);
         const uint32_t col = __umulhi(k, magic), row = k - col * b.RTC;
         const uint32_t idx = brev5(col) + 32 * row;
@@ -148,44 +174,22 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_tx(const TxBlock* blocks, int
         else { uint32_t pos = idx + 1 - b.ND; if (pos == D) pos = 0; v = d[3 * pos + 2]; }     // stream 2 is shifted by one (:76,84)
       }
       swb[i] = v;
-      cnt += (v != 2) ? 1u : 0u;
-      cntb += (v != 2 && i < start) ? 1u : 0u;
     }
-  } else {
-    const uint8_t* w = w_pool + off64(b.w_off_lo, b.w_off_hi);
-    for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
-      const uint8_t v = w[i];
-      swb[i] = v;
-      cnt += (v != 2) ? 1u : 0u;
-      cntb += (v != 2 && i < start) ? 1u : 0u;
-    }
+    const unsigned bal = __ballot_sync(0xffffffffu, v != 2);
+    if (lane == 0 && (i >> 5) < ng) s_bal[i >> 5] = bal;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); cntb += __shfl_xor_sync(0xffffffffu, cntb, o); }
-  if (lane == 0) { s_a[wid] = cnt; s_b[wid] = cntb; }
   __syncthreads();
-  uint32_t N = 0, before_start = 0;
-#pragma unroll
-  for (int i = 0; i < RM_THREADS / 32; ++i) { N += s_a[i]; before_start += s_b[i]; }
+  const uint32_t N = rm_scan_groups(s_bal, s_pre, ng, s_w);
   if (N == 0) return;                                   // (the reference would loop forever)
-  uint32_t base = 0;
-  for (uint32_t c0 = 0; c0 < b.Ncb; c0 += RM_THREADS) {
-    const uint32_t i = c0 + threadIdx.x;
-    const uint8_t v = (i < b.Ncb) ? swb[i] : (uint8_t)2;
-    const bool f = v != 2;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_w[wid] = __popc(bal);
-    __syncthreads();
-    uint32_t woff = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < RM_THREADS / 32; ++k) { const uint32_t x = s_w[k]; tot += x; woff += (k < wid) ? x : 0u; }
-    if (f) {
-      const uint32_t c = base + woff + __popc(bal & ((1u << lane) - 1u));
+  const uint32_t before_start = s_pre[start >> 5] + __popc(s_bal[start >> 5] & ((1u << (start & 31)) - 1u));
+  for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
+    const uint32_t bal = s_bal[i >> 5];
+    if ((bal >> lane) & 1u) {
+      const uint8_t v = swb[i];
+      const uint32_t c = s_pre[i >> 5] + __popc(bal & ((1u << lane) - 1u));
       const uint32_t rank = (c >= before_start) ? (c - before_start) : (c + N - before_start);
       for (uint32_t k = rank; k < b.E; k += N) e[k] = v;
     }
-    base += tot;
-    __syncthreads();
   }
 }
 
