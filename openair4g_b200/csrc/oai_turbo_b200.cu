@@ -10,6 +10,8 @@
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+#include <tuple>
+#include <utility>
 #include <algorithm>
 
 #include "../../include/oai_turbo_b200.h"
@@ -190,6 +192,40 @@ struct Profiler {
   ~Profiler() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
+// Either launches on a stream or appends nodes to a CUDA graph (a linear chain).  The graph is built explicitly, not by
+// stream capture: a capture in progress makes device-wide calls of OTHER threads fail (cudaDeviceSynchronize returns
+// "operation not permitted when stream is capturing"), which a library with concurrent callers cannot impose.
+struct Launcher {
+  cudaStream_t st = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphNode_t last = nullptr;
+  bool ok = true;
+  template <class... P, class... A>
+  void run(void (*k)(P...), dim3 grid, dim3 block, size_t smem, A&&... a) {
+    if (!graph) { k<<<grid, block, smem, st>>>(std::forward<A>(a)...); return; }
+    std::tuple<typename std::decay<P>::type...> vals(std::forward<A>(a)...);
+    void* ptrs[sizeof...(P)];
+    fill(ptrs, vals, std::index_sequence_for<P...>{});
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)k; kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = ptrs;
+    cudaGraphNode_t node;
+    if (cudaGraphAddKernelNode(&node, graph, last ? &last : nullptr, last ? 1 : 0, &kp) != cudaSuccess) { ok = false; return; }
+    last = node;
+  }
+  template <class T, size_t... I>
+  static void fill(void** ptrs, T& vals, std::index_sequence<I...>) { ((ptrs[I] = (void*)&std::get<I>(vals)), ...); }
+  void zero_ints(int* dst, int count) {
+    if (!graph) { cudaMemsetAsync(dst, 0, count * sizeof(int), st); return; }
+    cudaMemsetParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.dst = dst; mp.value = 0; mp.elementSize = 4; mp.width = count; mp.height = 1; mp.pitch = 0;
+    cudaGraphNode_t node;
+    if (cudaGraphAddMemsetNode(&node, graph, last ? &last : nullptr, last ? 1 : 0, &mp) != cudaSuccess) { ok = false; return; }
+    last = node;
+  }
+};
+
 struct Batch {
   Profiler prof;
   DevCtx* ctx = nullptr;
@@ -215,7 +251,6 @@ struct Batch {
   };
   struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; };
   std::vector<GraphEntry> graphs;
-  cudaStream_t cap_st = nullptr;
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     graphs.clear();
@@ -245,7 +280,6 @@ struct Batch {
   }
   void release() {
     drop_graphs();
-    if (cap_st) { cudaStreamDestroy(cap_st); cap_st = nullptr; }
     cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt); cudaFree(d_batch_max); cudaFree(d_active); cudaFree(d_nactive);
     d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr; d_batch_max = nullptr; d_active = nullptr; d_nactive = nullptr;
   }
@@ -266,23 +300,23 @@ struct Batch {
     const int n = (cnt < 0) ? this->n : cnt;
     if (n <= 0) return 0;
     // Small batches are launch-latency bound (one K=40 block: 31 launches, 0.24 ms): their launch sequence -- static for a
-    // given block count, iteration limit and set of pointers, early exits are decided on the device -- is captured once
-    // into a CUDA graph and replayed.
+    // given block count, iteration limit and set of pointers, early exits are decided on the device -- is built once
+    // as a CUDA graph and replayed.
     if (n <= GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
       const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K};
       GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
-        if (!cap_st && cudaStreamCreateWithFlags(&cap_st, cudaStreamNonBlocking) != cudaSuccess) cap_st = nullptr;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         int l = -1;
-        if (cap_st && cudaStreamBeginCapture(cap_st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-          l = enqueue16(in_dev, out_dev, status_dev, cap_st, lo, n, part, fe_rm, fe_w, fe_harq, false);
-          if (cudaStreamEndCapture(cap_st, &graph) != cudaSuccess || l < 0) { l = -1; graph = nullptr; }
+        if (cudaGraphCreate(&graph, 0) == cudaSuccess) {
+          Launcher rec;
+          rec.graph = graph;
+          l = enqueue16(in_dev, out_dev, status_dev, rec, lo, n, part, fe_rm, fe_w, fe_harq, false);
+          if (!rec.ok || l < 0 || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+          cudaGraphDestroy(graph);
         }
-        if (graph && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
-        if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         if (exec) {
           if (graphs.size() >= 16) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
@@ -296,10 +330,13 @@ struct Batch {
         return ge->launches;
       }
     }
-    return enqueue16(in_dev, out_dev, status_dev, st, lo, n, part, fe_rm, fe_w, fe_harq, true);
+    Launcher direct;
+    direct.st = st;
+    return enqueue16(in_dev, out_dev, status_dev, direct, lo, n, part, fe_rm, fe_w, fe_harq, true);
   }
-  int enqueue16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st, int lo, int n, int part,
+  int enqueue16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, Launcher& L, int lo, int n, int part,
                 const RmBlock* fe_rm, const int16_t* fe_w, const int16_t* fe_harq, bool count) {
+    cudaStream_t st = L.st;                             // profiler events (never recorded into a graph: prof.on excludes graphs)
     int launches = 0;
     CbMeta* d_meta = this->d_meta + lo;
     CbState* d_state = this->d_state + lo;
@@ -316,14 +353,14 @@ struct Batch {
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
     x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
     x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq;
-    cudaMemsetAsync(nact[0], 0, 2 * sizeof(int), st);
-    cudaMemsetAsync(d_batch_max, 0, sizeof(int), st);
+    L.zero_ints(nact[0], 2);
+    L.zero_ints(d_batch_max, 1);
     MapArgs mp;
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
     // packs the running blocks into list c (its counter is zero: memset above / k_x1_16) and makes it current
     auto compact_into = [&](int c) {
-      k_compact<<<(n + COMPACT_THREADS - 1) / COMPACT_THREADS, COMPACT_THREADS, 0, st>>>(d_state, n, act[c], nact[c], GUARD_B);
+      L.run(k_compact, dim3((n + COMPACT_THREADS - 1) / COMPACT_THREADS), dim3(COMPACT_THREADS), 0, (const CbState*)d_state, n, act[c], nact[c], (int)GUARD_B);
       ++launches;
       mp.active = act[c]; mp.nactive = nact[c]; x.active = act[c]; x.nactive = nact[c]; x.nactive_next = nact[1 - c];
     };
@@ -332,13 +369,13 @@ struct Batch {
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter; mp.upd = upd;
       prof.begin(1, st);
-      k_map16<MAP_SEG><<<map_grid, MAP_THREADS, map_smem, st>>>(mp);
+      L.run(k_map16<MAP_SEG>, dim3(map_grid), dim3(MAP_THREADS), map_smem, mp);
       prof.end(st);
       ++launches;
     };
     prof.begin(0, st);
-    if (fe_rm) k_demux16_t<true><<<n, XCHG_THREADS, (3 * A + 3 * 32 * ((max_K + 4 + 31) / 32)) * sizeof(int16_t), st>>>(x);
-    else k_demux16<<<n, XCHG_THREADS, 3 * A * sizeof(int16_t), st>>>(x);
+    if (fe_rm) L.run(k_demux16_t<true>, dim3(n), dim3(XCHG_THREADS), (3 * A + 3 * 32 * ((max_K + 4 + 31) / 32)) * sizeof(int16_t), x);
+    else L.run(k_demux16_t<false>, dim3(n), dim3(XCHG_THREADS), 3 * A * sizeof(int16_t), x);
     prof.end(st);
     ++launches;
     compact_into(cur);
@@ -346,11 +383,11 @@ struct Batch {
     for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
       x.iter = it;
       prof.begin(2, st);
-      k_x1_16<<<n, XCHG_THREADS, A * sizeof(int16_t), st>>>(x);
+      L.run(k_x1_16, dim3(n), dim3(XCHG_THREADS), A * sizeof(int16_t), x);
       prof.end(st);
       map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it, 0);                  // :1236
       prof.begin(3, st);
-      k_x2_16<<<n, XCHG_THREADS, A * sizeof(int16_t), st>>>(x);
+      L.run(k_x2_16, dim3(n), dim3(XCHG_THREADS), A * sizeof(int16_t), x);
       prof.end(st);
       launches += 2;
       if (it < max_iter) {
@@ -359,6 +396,7 @@ struct Batch {
       }
     }
     if (count) g_launches += launches;
+    if (!L.ok) return -101;                               // graph construction failed: the caller launches directly instead
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-101, "kernel launch failed: %s", cudaGetErrorString(e));
     return launches;
