@@ -174,3 +174,30 @@ def test_concurrent_callers(capi):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_small_batch_graph_replay_follows_new_inputs(capi):
+    """Batches of <= 1024 blocks replay a cached CUDA graph of their launch sequence (keyed by block count, iteration limit
+    and buffers).  Successive batches of the same shape but different contents, block sizes, CRC types and early-exit
+    behaviour must each match the oracle; a different iteration limit or block count must not reuse a stale graph."""
+    from oracle import loader, vectors
+    plans = [
+        [(6144, "clean", 6, 1), (512, "noise", 6, 1), (40, "clean", 6, 0), (1056, "waterfall", 6, 1)],
+        [(512, "noise", 6, 1), (6144, "waterfall", 6, 1), (6144, "noise", 6, 0), (48, "clean", 6, 1)],      # same count and limit
+        [(6144, "clean", 6, 1), (512, "noise", 6, 1), (40, "clean", 6, 0), (1056, "waterfall", 6, 1)],      # first shape again
+        [(6144, "waterfall", 3, 1), (512, "noise", 3, 1), (40, "clean", 3, 0), (1056, "clean", 3, 1)],      # other iteration limit
+        [(6144, "noise", 6, 1), (512, "clean", 6, 1), (104, "full", 6, 1)],                                 # other block count
+        [(6144, "full", 6, 1), (2048, "full", 6, 1), (40, "full", 6, 0), (1056, "full", 6, 1)],             # exact policy
+    ]
+    for rnd in range(2):
+        for pi, plan in enumerate(plans):
+            blocks, want = [], []
+            for j, (K, regime, max_it, crc) in enumerate(plan):
+                y, _ = vectors.llr_block(K, 100 * rnd + 10 * pi + j, regime, crc_type=crc)
+                blocks.append({"y": y, "K": K, "max_iterations": max_it, "crc_type": crc})
+                want.append(loader.port_decode16(y, K, max_it, crc))
+            outs, status = capi.decode_batch(blocks)
+            for (wb, wr), ob, st, b in zip(want, outs, status, blocks):
+                assert st == wr, (rnd, pi, b["K"], st, wr)
+                if b["max_iterations"] > 1:
+                    assert np.array_equal(ob, wb), (rnd, pi, b["K"])
