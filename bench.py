@@ -263,8 +263,9 @@ def run_b200(args):
     # Every step is one oai_turbo_submit_batch (copies the step's inputs from page-locked host memory, decodes, copies the
     # decoded bytes and status back) and one oai_turbo_wait.  Inside a call the batch is pipelined in parts (input copy of
     # part i+1 overlaps the decode of part i).  One call at a time by default; --e2e-in-flight 2 keeps two batches in flight
-    # (submit of step i+1 before the wait of step i) -- measured SLOWER on this box (7.2 vs 8.2 Gbit/s): two concurrent
-    # host->device copy streams share the link and kernels run slower while copies are in flight.
+    # (submit of step i+1 before the wait of step i) -- measured 8.5-8.9 Gbit/s against 8.0-8.1 in most runs but 3.4 in one
+    # of six (the small metadata copies of one batch queue behind the large input copies of the other on the shared copy
+    # engine), so it is not the default.
     args.e2e_serial = args.e2e_in_flight < 2
     calls = [capi.HostBatchCall(y_pin.numpy(), K, MAX_ITER, CRC_TYPE) for _ in range(1 if args.e2e_serial else 2)]
     for c in calls:
