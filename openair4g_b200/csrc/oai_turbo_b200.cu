@@ -430,6 +430,7 @@ struct Batch8 {
     return 0;
   }
   void release() {
+    drop_graphs();
     cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ck);
     d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ck = nullptr; cap = 0;
   }
@@ -441,7 +442,47 @@ struct Batch8 {
     CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
+  std::vector<Batch::GraphEntry> graphs;                      // small batches: cached launch graphs, see Batch::decode16
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   int decode8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n <= Batch::GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
+      const Batch::GraphKey key{in_dev, out_dev, status_dev, nullptr, nullptr, nullptr, 0, n, 0, max_iter, 0};
+      Batch::GraphEntry* ge = nullptr;
+      for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
+      if (!ge) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int l = -1;
+        if (cudaGraphCreate(&graph, 0) == cudaSuccess) {
+          Launcher rec;
+          rec.graph = graph;
+          l = enqueue8(in_dev, out_dev, status_dev, rec, false);
+          if (!rec.ok || l < 0 || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+          cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+        if (exec) {
+          if (graphs.size() >= 16) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
+          graphs.push_back(Batch::GraphEntry{key, exec, l});
+          ge = &graphs.back();
+        }
+      }
+      if (ge) {
+        if (cudaGraphLaunch(ge->exec, st) != cudaSuccess) return fail(-101, "graph launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        g_launches += ge->launches;
+        return ge->launches;
+      }
+    }
+    Launcher direct;
+    direct.st = st;
+    return enqueue8(in_dev, out_dev, status_dev, direct, true);
+  }
+  int enqueue8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, Launcher& L, bool count) {
+    cudaStream_t st = L.st;
     int launches = 0;
     Td8Args a;
     a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ck = d_ck; a.ck_words = ck_words;
@@ -451,28 +492,29 @@ struct Batch8 {
     auto map = [&](int sys_arr, int par_arr, int out_arr, int iter) {
       a.sys_arr = sys_arr; a.par_arr = par_arr; a.out_arr = out_arr; a.iter = iter;
       prof.begin(1, st);
-      k_map8<<<map_grid, MAP8_THREADS, MAP8_SMEM_BYTES, st>>>(a);
+      L.run(k_map8, dim3(map_grid), dim3(MAP8_THREADS), MAP8_SMEM_BYTES, a);
       prof.end(st);
       ++launches;
     };
     prof.begin(0, st);
-    k_demux8<<<n, XCHG_THREADS, 3 * A, st>>>(a);
+    L.run(k_demux8, dim3(n), dim3(XCHG_THREADS), 3 * A, a);
     prof.end(st);
     ++launches;
     map(A8_S0, A8_P1, A8_EXT, 1);                                // TD8:1325
     for (int it = 1; it <= max_iter; ++it) {                    // TD8:1327
       a.iter = it;
       prof.begin(2, st);
-      k_x1_8<<<n, XCHG_THREADS, A, st>>>(a);
+      L.run(k_x1_8, dim3(n), dim3(XCHG_THREADS), A, a);
       prof.end(st);
       map(A8_SYS, A8_P2, A8_EXT2, it);                           // TD8:1386
       prof.begin(3, st);
-      k_x2_8<<<n, XCHG_THREADS, 2 * A, st>>>(a);
+      L.run(k_x2_8, dim3(n), dim3(XCHG_THREADS), 2 * A, a);
       prof.end(st);
       launches += 2;
       if (it < max_iter) map(A8_SYS, A8_P1, A8_EXT, it + 1);     // TD8:1634
     }
-    g_launches += launches;
+    if (count) g_launches += launches;
+    if (!L.ok) return -101;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(-101, "kernel launch failed: %s", cudaGetErrorString(e));
     return launches;
