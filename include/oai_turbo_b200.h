@@ -24,10 +24,24 @@
 extern "C" {
 #endif
 
-/* Same layout as the reference's x86 time_stats_t (openair1/PHY/TOOLS/time_meas.h:43-52).
- * Callers pass seven of them to the decoder; this library never dereferences them
- * (the reference only touches them when its global opp_enabled != 0). */
-#ifndef OAI_TIME_STATS_T_DEFINED
+/* The seven statistics arguments of the decoder calls.
+ *
+ * Inside the reference tree (a translation unit that also sees openair1/PHY/CODING/defs.h, e.g. ulsch_decoding.c or
+ * dlsch_decoding.c): compile with -DOAI_TURBO_B200_WITH_REFERENCE_HEADERS (the CMake target in
+ * cmake_targets/oai_turbo_b200 sets it) or simply include PHY/CODING/defs.h first.  This header then pulls in the
+ * reference's own header, oai_time_stats_t IS its time_stats_t (openair1/PHY/TOOLS/time_meas.h:43-52), and the
+ * prototypes of section 1 below are compatible re-declarations of defs.h:112,132,152,191-204,239-253,315-320,362,367,
+ * 470-484,499-513 -- the compiler checks the two sets against each other.
+ *
+ * Stand-alone (no reference headers): a struct of the same layout.  Either way this library never dereferences the
+ * pointers (the reference only touches them when its global opp_enabled != 0). */
+#if defined(OAI_TURBO_B200_WITH_REFERENCE_HEADERS) || defined(__CODING_DEFS__H__)
+#ifndef __CODING_DEFS__H__
+#include "PHY/CODING/defs.h"
+#endif
+typedef time_stats_t oai_time_stats_t;
+#define OAI_TIME_STATS_T_DEFINED
+#elif !defined(OAI_TIME_STATS_T_DEFINED)
 #define OAI_TIME_STATS_T_DEFINED
 typedef struct {
   long long in, diff, diff_now, p_time, diff_square, max;

@@ -74,6 +74,7 @@ struct DevCtx {
   uint32_t t8_off[188];
   u32* crc_xp = nullptr;              // [4][32][CRC_NM] powers of x mod the CRC polynomials
   bool ok = false;
+  unsigned gen = 0;                   // bumped when the tables are (re)built: cached launch graphs hold table pointers
 };
 static DevCtx g_ctx[16];
 static std::mutex g_ctx_mu;
@@ -84,15 +85,27 @@ static u32 gf_xtimes(u32 r, u32 poly, int w) {
   return top ? (r ^ poly) : r;
 }
 
+// sets the current device for the lifetime of the object and puts the caller's device back afterwards: no entry point
+// of the library changes the calling thread's current device
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev != prev) { if (cudaSetDevice(dev) != cudaSuccess) return -1; switched = true; }
+    return 0;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 static int ctx_get(int dev, DevCtx** out) {
   if (dev < 0) CU(cudaGetDevice(&dev));
   if (dev >= 16) return fail(-2, "device index %d out of range", dev);
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   DevCtx& c = g_ctx[dev];
   if (!c.ok) {
-    int prev = 0;
-    CU(cudaGetDevice(&prev));
-    CU(cudaSetDevice(dev));
+    DevGuard guard;
+    if (guard.enter(dev)) return fail(-100, "cannot select CUDA device %d", dev);
     std::vector<uint16_t> pool, tpool, qpool, t8pool;
     for (int i = 0; i < 188; ++i) {
       const int K = qpp_K(i), W = K / 8, A = c4_words(W) * 2;
@@ -150,10 +163,22 @@ static int ctx_get(int dev, DevCtx** out) {
     CU(cudaFuncSetAttribute(k_demux16_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 6208 * (int)sizeof(int16_t)));
     c.dev = dev;
     c.ok = true;
-    CU(cudaSetDevice(prev));
+    ++c.gen;
   }
   *out = &c;
   return 0;
+}
+
+// free_td16 / free_td8: releases the tables of every device (the next call rebuilds them)
+static void ctx_release_all() {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (DevCtx& c : g_ctx) {
+    if (!c.ok) continue;
+    cudaFree(c.pi_pool); cudaFree(c.t_pool); cudaFree(c.qpp_pool); cudaFree(c.t8_pool); cudaFree(c.crc_xp);
+    c.pi_pool = c.t_pool = c.qpp_pool = c.t8_pool = nullptr; c.crc_xp = nullptr;
+    c.ok = false;
+  }
+  cudaGetLastError();
 }
 
 // ---- a batch of code blocks resident on one GPU ---------------------------------------
@@ -244,9 +269,10 @@ struct Batch {
   struct GraphKey {
     const void *in, *out, *status, *fe_rm, *fe_w, *fe_harq;
     int lo, n, part, max_iter, max_K;
+    unsigned gen;                      // DevCtx::gen the graph was built against
     bool operator==(const GraphKey& o) const {
       return in == o.in && out == o.out && status == o.status && fe_rm == o.fe_rm && fe_w == o.fe_w && fe_harq == o.fe_harq &&
-             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K;
+             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen;
     }
   };
   struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; };
@@ -303,7 +329,7 @@ struct Batch {
     // given block count, iteration limit and set of pointers, early exits are decided on the device -- is built once
     // as a CUDA graph and replayed.
     if (n <= GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
-      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K};
+      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen};
       GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
@@ -450,7 +476,7 @@ struct Batch8 {
   int decode8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n <= Batch::GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
-      const Batch::GraphKey key{in_dev, out_dev, status_dev, nullptr, nullptr, nullptr, 0, n, 0, max_iter, 0};
+      const Batch::GraphKey key{in_dev, out_dev, status_dev, nullptr, nullptr, nullptr, 0, n, 0, max_iter, 0, ctx->gen};
       Batch::GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
@@ -566,12 +592,14 @@ struct oai_turbo_harq_pool {
 };
 namespace oai {
 
-// per-thread scratch for the single-call reference entry points of the front end
+// per-thread, per-device scratch for the single-call reference entry points of the front end: the stream and both
+// buffers belong to the device that was current when they were created, so a thread that drives several GPUs gets
+// one set per device; everything is released when the thread exits
 struct Scratch {
   cudaStream_t st = nullptr;
   void* h = nullptr; void* d = nullptr; size_t cap = 0, dcap = 0;
   // host_bytes: size of the page-locked mirror (defaults to the device size; smaller when part of the device area is
-  // never copied, e.g. the intermediate d of the TX batch)
+  // never copied, e.g. the intermediate d of the TX batch).  The current device must be the scratch's device.
   int ensure(size_t bytes, size_t host_bytes = (size_t)-1) {
     DevCtx* c;
     int rc = ctx_get(-1, &c);
@@ -594,8 +622,24 @@ struct Scratch {
     }
     return 0;
   }
+  void release() {
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    if (st) cudaStreamDestroy(st);
+    h = d = nullptr; st = nullptr; cap = dcap = 0;
+  }
 };
-static thread_local Scratch t_scratch;
+struct ScratchSet {
+  Scratch per_dev[16];
+  ~ScratchSet() { for (Scratch& s : per_dev) s.release(); cudaGetLastError(); }
+};
+static thread_local ScratchSet t_scratch_set;
+// scratch of the calling thread on the CURRENT device
+static Scratch& scratch_here() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = 0;
+  return t_scratch_set.per_dev[dev];
+}
 
 // ---- host-buffer batches: pinned staging + one stream per batch object ---------------
 struct HostBatch {
@@ -628,41 +672,53 @@ struct HostBatch {
   std::vector<uint32_t> out_off;
   unsigned flags = 0;
 
-  int ensure(int gpu, int nblk, int Kmax, size_t in_hw, size_t out_bytes, int nblk8 = 0, int Kmax8 = 0) {
-    DevCtx* c;
-    int rc = ctx_get(gpu, &c);
-    if (rc) return rc;
+  // The caller holds a DevGuard on the batch's device.  Capacities are raised only after the matching allocation
+  // succeeded; a failed allocation releases the whole object (nothing half-allocated survives into the next call).
+  int ensure(DevCtx* c, int nblk, int Kmax, size_t in_hw, size_t out_bytes, int nblk8 = 0, int Kmax8 = 0) {
     if (dev != c->dev) { release(); dev = c->dev; }
-    CU(cudaSetDevice(dev));
+    int rc = ensure_inner(c, nblk, Kmax, in_hw, out_bytes, nblk8, Kmax8);
+    if (rc) { release(); cudaGetLastError(); }
+    return rc;
+  }
+  int ensure_inner(DevCtx* c, int nblk, int Kmax, size_t in_hw, size_t out_bytes, int nblk8, int Kmax8) {
+    int rc;
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (nblk > cap_blocks || Kmax > cap_K) {
       b.release();
-      cap_blocks = std::max(nblk, cap_blocks); cap_K = std::max(Kmax, cap_K);
-      rc = b.alloc(c, cap_blocks, cap_K);
+      const int nb = std::max(nblk, cap_blocks), nk = std::max(Kmax, cap_K);
+      cap_blocks = cap_K = 0;
+      rc = b.alloc(c, nb, nk);
       if (rc) return rc;
+      cap_blocks = nb; cap_K = nk;
     }
     if (nblk8 > cap8_blocks || (nblk8 > 0 && Kmax8 > cap8_K)) {
       b8.release();
-      cap8_blocks = std::max(nblk8, cap8_blocks); cap8_K = std::max(Kmax8, cap8_K);
-      rc = b8.alloc(c, cap8_blocks, cap8_K);
+      const int nb = std::max(nblk8, cap8_blocks), nk = std::max(Kmax8, cap8_K);
+      cap8_blocks = cap8_K = 0;
+      rc = b8.alloc(c, nb, nk);
       if (rc) return rc;
+      cap8_blocks = nb; cap8_K = nk;
     }
     if (nblk + nblk8 > cap_status) {
-      if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); }
+      if (h_status) cudaFreeHost(h_status);
+      if (d_status) cudaFree(d_status);
+      h_status = nullptr; d_status = nullptr; cap_status = 0;
+      CU(cudaMallocHost(&h_status, nblk + nblk8));
+      CU(cudaMalloc(&d_status, nblk + nblk8));
       cap_status = nblk + nblk8;
-      CU(cudaMallocHost(&h_status, cap_status));
-      CU(cudaMalloc(&d_status, cap_status));
     }
     b.ctx = c; b8.ctx = c;
     if (in_hw > cap_in) {
       if (d_in) cudaFree(d_in);
+      d_in = nullptr; cap_in = 0;
+      CU(cudaMalloc(&d_in, in_hw * sizeof(int16_t)));
       cap_in = in_hw;
-      CU(cudaMalloc(&d_in, cap_in * sizeof(int16_t)));
     }
     if (out_bytes > cap_out) {
       if (d_out) cudaFree(d_out);
+      d_out = nullptr; cap_out = 0;
+      CU(cudaMalloc(&d_out, out_bytes));
       cap_out = out_bytes;
-      CU(cudaMalloc(&d_out, cap_out));
     }
     return 0;
   }
@@ -670,44 +726,54 @@ struct HostBatch {
   int ensure_stage_in() {
     if (cap_h_in < cap_in) {
       if (h_in) cudaFreeHost(h_in);
+      h_in = nullptr; cap_h_in = 0;
+      CU(cudaMallocHost(&h_in, cap_in * sizeof(int16_t)));
       cap_h_in = cap_in;
-      CU(cudaMallocHost(&h_in, cap_h_in * sizeof(int16_t)));
     }
     return 0;
   }
   int ensure_stage_out() {
     if (cap_h_out < cap_out) {
       if (h_out) cudaFreeHost(h_out);
+      h_out = nullptr; cap_h_out = 0;
+      CU(cudaMallocHost(&h_out, cap_out));
       cap_h_out = cap_out;
-      CU(cudaMallocHost(&h_out, cap_h_out));
     }
     return 0;
   }
   int ensure_rm(size_t e_hw, size_t w_hw, int nrm) {
     if (e_hw > cap_e) {
-      if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); }
+      if (h_e) cudaFreeHost(h_e);
+      if (d_e) cudaFree(d_e);
+      h_e = nullptr; d_e = nullptr; cap_e = 0;
+      CU(cudaMallocHost(&h_e, e_hw * sizeof(int16_t)));
+      CU(cudaMalloc(&d_e, e_hw * sizeof(int16_t)));
       cap_e = e_hw;
-      CU(cudaMallocHost(&h_e, cap_e * sizeof(int16_t)));
-      CU(cudaMalloc(&d_e, cap_e * sizeof(int16_t)));
     }
     if (w_hw > cap_w) {
-      if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); }
+      if (h_w) cudaFreeHost(h_w);
+      if (d_w) cudaFree(d_w);
+      h_w = nullptr; d_w = nullptr; cap_w = 0;
+      CU(cudaMallocHost(&h_w, w_hw * sizeof(int16_t)));
+      CU(cudaMalloc(&d_w, w_hw * sizeof(int16_t)));
       cap_w = w_hw;
-      CU(cudaMallocHost(&h_w, cap_w * sizeof(int16_t)));
-      CU(cudaMalloc(&d_w, cap_w * sizeof(int16_t)));
     }
     if (nrm > cap_rm) {
       if (d_rm) cudaFree(d_rm);
+      d_rm = nullptr; cap_rm = 0;
+      CU(cudaMalloc(&d_rm, sizeof(RmBlock) * nrm));
       cap_rm = nrm;
-      CU(cudaMalloc(&d_rm, sizeof(RmBlock) * cap_rm));
     }
     return 0;
   }
   void release() {
     b.release();
     b8.release(); cap8_blocks = cap8_K = 0; cap_status = 0;
-    if (h_e) { cudaFreeHost(h_e); cudaFree(d_e); h_e = nullptr; d_e = nullptr; }
-    if (h_w) { cudaFreeHost(h_w); cudaFree(d_w); h_w = nullptr; d_w = nullptr; }
+    if (h_e) cudaFreeHost(h_e);
+    if (d_e) cudaFree(d_e);
+    if (h_w) cudaFreeHost(h_w);
+    if (d_w) cudaFree(d_w);
+    h_e = nullptr; d_e = nullptr; h_w = nullptr; d_w = nullptr;
     if (d_rm) { cudaFree(d_rm); d_rm = nullptr; }
     if (d_gseq) { cudaFree(d_gseq); d_gseq = nullptr; }
     if (d_gold) { cudaFree(d_gold); d_gold = nullptr; }
@@ -718,7 +784,10 @@ struct HostBatch {
     if (h_out) { cudaFreeHost(h_out); h_out = nullptr; }
     if (d_out) { cudaFree(d_out); d_out = nullptr; }
     cap_h_in = cap_h_out = 0;
-    if (h_status) { cudaFreeHost(h_status); cudaFree(d_status); h_status = nullptr; d_status = nullptr; }
+    if (h_status) cudaFreeHost(h_status);
+    if (d_status) cudaFree(d_status);
+    h_status = nullptr; d_status = nullptr;
+    for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (st_copy) {
       cudaStreamDestroy(st_copy); st_copy = nullptr; cudaStreamDestroy(st_out); st_out = nullptr;
@@ -733,7 +802,8 @@ struct HostBatch {
     descs.assign(cbs, cbs + ncb);
     flags = fl;
     static const bool trace = getenv("OAI_TURBO_TRACE") != nullptr;
-    order.clear();
+    // handles are recycled: nothing of the previous batch may survive an early return below (wait() walks these)
+    order.clear(); rm.clear(); rm_desc.clear(); gseq.clear(); direct_out = false;
     int Kmax = 40;
     for (int i = 0; i < ncb; ++i) {
       const oai_cb_desc_t& d = descs[i];
@@ -768,7 +838,12 @@ struct HostBatch {
       in_off[i] = in_hw;  in_hw += (size_t)3 * d.K + 12;
       out_off[i] = (uint32_t)out_b; out_b += ((size_t)(d.K >> 3) + 15) & ~(size_t)15;
     }
-    int rc = ensure(gpu, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
+    DevCtx* dctx;
+    int rc = ctx_get(gpu, &dctx);
+    if (rc) return rc;
+    DevGuard guard;                                          // the caller's current device is restored on every return path
+    if (guard.enter(dctx->dev)) return fail(-100, "cannot select CUDA device %d", dctx->dev);
+    rc = ensure(dctx, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
     if (rc) return rc;
     if (trace) { for (auto& e : ev) if (!e) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
     // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
@@ -824,11 +899,9 @@ struct HostBatch {
       }
     }
     std::vector<CbMeta> meta(n);
-    rm.clear(); rm_desc.clear();
     size_t e_hw = 0, w_hw = 0;
     oai_turbo_harq_pool* pool = nullptr;
     const int16_t* prev_e_end = nullptr;
-    gseq.clear();
     std::unordered_map<uint32_t, int> seq_of;                // c_init -> index in gseq
     std::vector<int> rm_seq;                                 // per rm block: its sequence or -1
     for (int i = 0; i < n; ++i) {
@@ -1007,12 +1080,10 @@ struct HostBatch {
   int wait() {
     const int n = (int)order.size();
     if (n) CU(cudaStreamSynchronize(st));
-    if (ev[0] && getenv("OAI_TURBO_TRACE")) {
-      static cudaEvent_t origin = nullptr;
-      if (!origin) origin = ev[0];
-      float t[4];
-      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], origin, ev[i]);
-      fprintf(stderr, "[trace %p] submit %.2f  h2d_done %.2f  kernels_done %.2f  d2h_done %.2f ms\n", (void*)this, t[0], t[1], t[2], t[3]);
+    if (n && ev[0] && getenv("OAI_TURBO_TRACE")) {               // times relative to this batch's own submit event
+      float t[4] = {0, 0, 0, 0};
+      for (int i = 1; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[0], ev[i]);
+      fprintf(stderr, "[trace %p gpu %d] h2d_done %.2f  kernels_done %.2f  d2h_done %.2f ms after submit\n", (void*)this, dev, t[1], t[2], t[3]);
     }
     for (int i = 0; i < n; ++i) {
       const oai_cb_desc_t& d = descs[order[i]];
@@ -1131,30 +1202,26 @@ int oai_turbo_harq_pool_create(int gpu, uint32_t n_slots, uint16_t max_K, oai_tu
   DevCtx* c;
   int rc = ctx_get(gpu, &c);
   if (rc) return rc;
-  int prev = 0;
-  CU(cudaGetDevice(&prev));
-  CU(cudaSetDevice(c->dev));
+  DevGuard guard;
+  if (guard.enter(c->dev)) return fail(-100, "cannot select CUDA device %d", c->dev);
   oai_turbo_harq_pool* p = new oai_turbo_harq_pool();
   p->dev = c->dev; p->n_slots = n_slots;
   p->slot_hw = 3u * 32u * (((uint32_t)max_K + 4 + 31) / 32);
-  if ((unsigned long long)p->slot_hw * n_slots > 0xffffffffull) { delete p; cudaSetDevice(prev); return fail(-1, "pool too large for 32-bit offsets"); }
+  if ((unsigned long long)p->slot_hw * n_slots > 0xffffffffull) { delete p; return fail(-1, "pool too large for 32-bit offsets"); }
   const size_t bytes = sizeof(int16_t) * (size_t)p->slot_hw * n_slots;
   if (cudaMalloc(&p->d, bytes) != cudaSuccess || cudaMemset(p->d, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
-    cudaGetLastError(); delete p; cudaSetDevice(prev);
+    cudaGetLastError(); delete p;
     return fail(-100, "HARQ pool: cudaMalloc of %zu bytes failed", bytes);
   }
-  CU(cudaSetDevice(prev));
   *pool = p;
   return 0;
 }
 int oai_turbo_harq_pool_read(oai_turbo_harq_pool_t* p, uint32_t slot, int16_t* w_host, uint32_t n) {
   if (!p || !w_host || slot >= p->n_slots || n > p->slot_hw) return fail(-1, "bad arguments");
-  int prev = 0;
-  CU(cudaGetDevice(&prev));
-  CU(cudaSetDevice(p->dev));
+  DevGuard guard;
+  if (guard.enter(p->dev)) return fail(-100, "cannot select CUDA device %d", p->dev);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(w_host, p->d + (size_t)slot * p->slot_hw, sizeof(int16_t) * n, cudaMemcpyDeviceToHost));
-  CU(cudaSetDevice(prev));
   return 0;
 }
 void oai_turbo_harq_pool_destroy(oai_turbo_harq_pool_t* p) {
@@ -1203,17 +1270,50 @@ void* oai_turbo_host_alloc(size_t bytes) {
 }
 void oai_turbo_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// one cached single-block batch per calling thread: the call is re-entrant like the reference
+// (all scratch is per call there, TD16:967-979) and pays no allocation after the first use
+struct SingleHolder {
+  HostBatch* hb = nullptr;
+  HostBatch* get() { if (!hb) hb = new HostBatch(); return hb; }
+  void drop() { if (hb) { hb->release(); delete hb; hb = nullptr; cudaGetLastError(); } }
+  ~SingleHolder() { drop(); }                        // thread exit: stream, device workspace and pinned memory go back
+};
+static thread_local SingleHolder t_single;
+
+static unsigned char decode_one(short* y, unsigned char* decoded_bytes, unsigned short n, unsigned char max_iterations,
+                                unsigned char crc_type, unsigned char F, int llr8, const char* who) {
+  HostBatch* hb = t_single.get();
+  oai_cb_desc_t d;
+  memset(&d, 0, sizeof(d));
+  uint8_t status = 255;
+  d.in = y; d.decoded_bytes = decoded_bytes; d.status = &status; d.K = n; d.max_iterations = max_iterations;
+  d.crc_type = crc_type; d.F = F; d.decode_enable = 1; d.llr8 = (uint8_t)llr8;
+  if (hb->submit(&d, 1, 0, -1) || hb->wait()) {
+    fprintf(stderr, "[oai_turbo_b200] %s: GPU path failed (%s); there is no CPU fallback\n", who, g_err);
+    t_single.drop();                                  // a half-built workspace must not serve the next call
+    return 255;
+  }
+  return status;
+}
+
 void init_td16(void) {
   DevCtx* c;
   if (ctx_get(-1, &c)) fprintf(stderr, "[oai_turbo_b200] init_td16: no usable CUDA device -- decoder calls will fail\n");
 }
-void free_td16(void) {}
+// 3gpplte_turbo_decoder_sse_16bit.c:886 / _8bit.c:834 free the interleaver tables; here: the recycled batch objects
+// (streams, device workspace, pinned staging) and the per-device tables.  Like the reference's, not to be called while
+// other threads decode; the next init/decode call rebuilds what it needs.
+void free_td16(void) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (oai_turbo_batch* h : g_pool) { h->hb.release(); delete h; }
+    g_pool.clear();
+  }
+  t_single.drop();
+  ctx_release_all();
+}
 void init_td8(void) { init_td16(); }
-void free_td8(void) {}
-
-// one cached single-block batch per calling thread: the call is re-entrant like the reference
-// (all scratch is per call there, TD16:967-979) and pays no allocation after the first use
-static thread_local HostBatch* t_single = nullptr;
+void free_td8(void) { free_td16(); }
 
 unsigned char phy_threegpplte_turbo_decoder16(short* y, unsigned char* decoded_bytes, unsigned short n,
     unsigned short f1, unsigned short f2, unsigned char max_iterations, unsigned char crc_type, unsigned char F,
@@ -1222,32 +1322,7 @@ unsigned char phy_threegpplte_turbo_decoder16(short* y, unsigned char* decoded_b
   (void)f1; (void)f2;
   if (crc_type > 3) { fprintf(stderr, "Illegal crc length!\n"); return 255; }          // TD16:1003-1006
   if (qpp_index(n) < 0) { fprintf(stderr, "Illegal frame length!\n"); return 255; }    // TD16:1015-1018
-  if (!t_single) t_single = new HostBatch();
-  oai_cb_desc_t d;
-  memset(&d, 0, sizeof(d));
-  uint8_t status = 255;
-  d.in = y; d.decoded_bytes = decoded_bytes; d.status = &status; d.K = n; d.max_iterations = max_iterations;
-  d.crc_type = crc_type; d.F = F; d.decode_enable = 1;
-  if (t_single->submit(&d, 1, 0, -1) || t_single->wait()) {
-    fprintf(stderr, "[oai_turbo_b200] phy_threegpplte_turbo_decoder16: GPU path failed (%s); there is no CPU fallback\n", g_err);
-    return 255;
-  }
-  return status;
-}
-
-static unsigned char decode_one(short* y, unsigned char* decoded_bytes, unsigned short n, unsigned char max_iterations,
-                                unsigned char crc_type, unsigned char F, int llr8, const char* who) {
-  if (!t_single) t_single = new HostBatch();
-  oai_cb_desc_t d;
-  memset(&d, 0, sizeof(d));
-  uint8_t status = 255;
-  d.in = y; d.decoded_bytes = decoded_bytes; d.status = &status; d.K = n; d.max_iterations = max_iterations;
-  d.crc_type = crc_type; d.F = F; d.decode_enable = 1; d.llr8 = (uint8_t)llr8;
-  if (t_single->submit(&d, 1, 0, -1) || t_single->wait()) {
-    fprintf(stderr, "[oai_turbo_b200] %s: GPU path failed (%s); there is no CPU fallback\n", who, g_err);
-    return 255;
-  }
-  return status;
+  return decode_one(y, decoded_bytes, n, max_iterations, crc_type, F, 0, "phy_threegpplte_turbo_decoder16");
 }
 
 unsigned char phy_threegpplte_turbo_decoder8(short* y, unsigned char* decoded_bytes, unsigned short n, unsigned short f1,
@@ -1266,7 +1341,7 @@ unsigned char phy_threegpplte_turbo_decoder8(short* y, unsigned char* decoded_by
 
 uint32_t generate_dummy_w(uint32_t D, uint8_t* w, uint8_t F) {
   const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   if (sc.ensure(3 * (size_t)Kpi)) { fprintf(stderr, "[oai_turbo_b200] generate_dummy_w: GPU path failed (%s)\n", g_err); return RTC; }
   memcpy(sc.h, w, 3 * (size_t)Kpi);
   cudaMemcpyAsync(sc.d, sc.h, 3 * (size_t)Kpi, cudaMemcpyHostToDevice, sc.st);
@@ -1288,7 +1363,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
   }
   // K is not an argument of the reference call; everything it needs follows from RTC
   rm_params(32 * RTC - 4, G, C, Nsoft, Mdlharq, Kmimo, rvidx, Qm, Nl, r, RTC, &q);
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   // layout of the scratch buffer: [RmBlock][w: Ncb int16][dummy: Ncb bytes][e: E int16]
   const size_t o_w = 256, o_dm = o_w + (((size_t)q.Ncb * 2 + 255) & ~(size_t)255), o_e = o_dm + (((size_t)q.Ncb + 255) & ~(size_t)255);
   const size_t total = o_e + (size_t)q.E * 2 + 256;
@@ -1314,7 +1389,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
 
 void sub_block_deinterleaving_turbo(uint32_t D, int16_t* dd, int16_t* w) {
   const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   const size_t o_w = 256, o_y = o_w + (((size_t)3 * Kpi * 2 + 255) & ~(size_t)255), total = o_y + ((size_t)3 * Kpi + 3) * 2 + 256;
   if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] sub_block_deinterleaving_turbo: GPU path failed (%s)\n", g_err); return; }
   RmBlock b;
@@ -1344,7 +1419,7 @@ void threegpplte_turbo_encoder(uint8_t* input, uint16_t input_length_bytes, uint
   (void)F; (void)interleaver_f1; (void)interleaver_f2;
   const int K = (int)input_length_bytes * 8, idx = qpp_index(K);
   if (idx < 0) { printf("Illegal frame length!\n"); return; }                            // 3gpplte_sse.c:399-402
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   const size_t o_c = 256, o_d = o_c + up256(input_length_bytes), total = o_d + up256(3 * (size_t)K + 12);
   DevCtx* c;
   if (sc.ensure(total) || ctx_get(-1, &c)) { fprintf(stderr, "[oai_turbo_b200] threegpplte_turbo_encoder: GPU path failed (%s)\n", g_err); return; }
@@ -1365,7 +1440,7 @@ void threegpplte_turbo_encoder(uint8_t* input, uint16_t input_length_bytes, uint
 uint32_t sub_block_interleaving_turbo(uint32_t D, uint8_t* dd, uint8_t* w) {
   const uint32_t RTC = (D >> 5) + ((D & 31) ? 1 : 0), Kpi = RTC << 5, ND = Kpi - D;
   dd[3 * D + 2] = dd[2];                                                                  // lte_rate_matching.c:76
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   const size_t nin = 3 * (size_t)Kpi + 3, o_w = up256(nin), total = o_w + up256(3 * (size_t)Kpi);
   if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] sub_block_interleaving_turbo: GPU path failed (%s)\n", g_err); return RTC; }
   char* h = (char*)sc.h; char* d = (char*)sc.d;
@@ -1393,7 +1468,7 @@ uint32_t lte_rate_matching_turbo(uint32_t RTC, uint32_t G, uint8_t* w, uint8_t* 
     printf("Exiting, RM condition (Nir %d, Nsoft %d, Kw %d\n", (int)(Nsoft / Kmimo / (Mdlharq < 8 ? Mdlharq : 8)), (int)Nsoft, (int)(3 * q.Kpi));
     return 0;
   }
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   const size_t o_w = 256, o_e = o_w + up256(q.Ncb), total = o_e + up256(q.E);
   if (sc.ensure(total)) { fprintf(stderr, "[oai_turbo_b200] lte_rate_matching_turbo: GPU path failed (%s)\n", g_err); return 0; }
   TxBlock b;
@@ -1417,13 +1492,11 @@ int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
   if (n <= 0) return 0;
   if (!blocks) return fail(-1, "oai_turbo_tx_batch: null descriptor array");
   const bool devp = (flags & OAI_TX_DEVICE_POINTERS) != 0;
-  int prev = 0;
-  CU(cudaGetDevice(&prev));
-  if (gpu >= 0 && gpu != prev) CU(cudaSetDevice(gpu));
-  struct Restore { int p; ~Restore() { cudaSetDevice(p); } } restore{prev};
   DevCtx* c;
   int rc = ctx_get(gpu, &c);
   if (rc) return rc;
+  DevGuard guard;
+  if (guard.enter(c->dev)) return fail(-100, "cannot select CUDA device %d", c->dev);
   // scratch layout: [TxBlock x n][c bytes][e bytes][d bytes (device only)]
   std::vector<TxBlock> tb(n);
   const size_t o_c = up256(sizeof(TxBlock) * (size_t)n);
@@ -1457,7 +1530,7 @@ int oai_turbo_tx_batch(oai_tx_desc_t* blocks, int n, unsigned flags, int gpu) {
     tot_d += (3 * (size_t)t.K + 12 + 3) & ~(size_t)3;
   }
   const size_t o_e = up256(cur_c), o_d = o_e + up256(tot_e), total = o_d + up256(tot_d);
-  Scratch& sc = t_scratch;
+  Scratch& sc = scratch_here();
   if (sc.ensure(total, o_d)) return fail(-100, "oai_turbo_tx_batch: GPU path failed (%s)", g_err);   // d is device-only
   char* h = (char*)sc.h; char* d = (char*)sc.d;
   for (int i = 0; i < n; ++i) {
@@ -1495,7 +1568,10 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   if (qpp_index(K) < 0) return fail(-1, "illegal K");
   HostBatch hb;
   size_t in_hw = ((size_t)3 * K + 12 + 7) & ~(size_t)7;
-  int rc = hb.ensure(-1, 1, K, in_hw, 1024);
+  DevCtx* dctx;
+  int rc = ctx_get(-1, &dctx);
+  if (rc) return rc;
+  rc = hb.ensure(dctx, 1, K, in_hw, 1024);
   if (rc) return rc;
   rc = hb.ensure_stage_in();
   if (rc) return rc;
