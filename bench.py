@@ -167,9 +167,9 @@ def run_reference(args):
     rng = np.random.default_rng(1234)
     nd = 64
     y = rng.integers(-16, 17, size=(nd, 3 * K_BITS + 12)).astype(np.int16)
-    per_step = max(threads * 256, 1024)     # ~0.1 s per step on 16 threads
+    per_step = args.blocks                  # the repo arm's batch (42624 blocks: ~0.6 s per step on 16 host threads)
     for _ in range(args.warmup):
-        cpu_decode_rate(y, max(threads, 64), threads)
+        cpu_decode_rate(y, max(threads * 16, 64), threads)      # warm-up steps are short (tables, thread pool, caches)
     t_tot, kind = 0.0, "port"
     for _ in range(args.steps):
         _, kind, dt, _ = cpu_decode_rate(y, per_step, threads)
@@ -179,7 +179,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mbit/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "blocks_per_step": per_step},
+            "config": {"workload": WORKLOAD, "blocks_per_gpu_per_step": per_step, "e2e_blocks_per_gpu_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -296,6 +296,13 @@ def run_b200(args):
     same = bool((out_h == out_dev[:Be].cpu().numpy()).all() and (st_h == st[:Be]).all())
     if not same:
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
+    e2e_h2d, e2e_d2h = call.h2d_bytes, call.d2h_bytes
+    call_keep = None
+    del out_h, st_h, call
+
+    # ---- BASELINE configs[3]: multi-cell uplink through the front end, all ranks (strong scaling over 64 cells) ----
+    del y_pin, calls, call_keep
+    multicell = None if args.no_multicell else run_multicell_ul(args, capi, rank, world, dist, local_rank)
 
     # ---- side measurement: early-exit regimes of config 3 (device-resident, same plan, same timing rules) ----
     regimes = None
@@ -330,6 +337,28 @@ def run_b200(args):
                              "crc_passing_blocks_equal_transmitted_bytes": good,
                              "distinct_blocks": nd}
             del y_r, out_r, st_r
+
+    # ---- BASELINE configs[0] / [1]: one subframe through the drop-in call (latency), configs[4]: the 8-bit decoder ----
+    subframes = llr8_side = None
+    if world == 1 and not args.no_regimes:
+        def guarded(fn, *a, **kw):                               # a side measurement never takes the headline line down
+            try:
+                return fn(*a, **kw)
+            except Exception as ex:
+                return {"error": str(ex)}
+        subframes = {"ulsim_subframe_latency_ms": guarded(subframe_latency, capi, 7736, 14400, 4, 6),     # 25 PRB MCS16: 2 x K=3904
+                     "dlsim_subframe_latency_ms": guarded(subframe_latency, capi, 75376, 90000, 6, 4),    # 100 PRB MCS28: 13 x K=5824
+                     "dlsim_subframe_latency_ms_8bit": guarded(subframe_latency, capi, 75376, 90000, 6, 4, llr8=1)}
+        llr8_side = {}
+        B8 = 21312
+        for K8 in (5824, 6144):
+            r8, r16 = guarded(device_rate, capi, B8, K8, 1, args.steps), guarded(device_rate, capi, B8, K8, 0, args.steps)
+            if "value" in r8 and "value" in r16:
+                r8["ratio_to_16bit"] = r8["value"] / r16["value"]
+                r8["value_16bit"] = r16["value"]
+            llr8_side["K%d" % K8] = r8
+        llr8_side["note"] = ("device-resident, %d blocks, noise regime, 6 iterations; ratio = 8-bit / 16-bit decoder at the same K and "
+                             "batch (on the reference CPU the 8-bit decoder is ~1.4x the 16-bit one, SURVEY 6)" % B8)
 
     # ---- side measurement: TX mirror (encoder + sub-block interleaver + rate matching), device pointers ----
     tx_side = None
@@ -371,42 +400,52 @@ def run_b200(args):
     bytes_per_launch = B * algorithmic_bytes_per_block(K) / (2.0 * MAX_ITER)
     achieved = bytes_per_launch / (map_ms * 1e-3) / 1e9 if n_map else 0.0
     kernel_ms_total = sum(prof_ms)
-    # dram__bytes_read.sum + dram__bytes_write.sum per k_map16 launch of 23680 blocks, ncu --set full capture
-    # profiles/r1o_ncu_full_all_summary.txt (mean of the three captured launches; unchanged since r1h), scaled to this batch size
-    traffic = 1.444e9 * B / 23680.0 if K == K_BITS else None
+    # measured figures of the kernel from the committed ncu --set full capture of this bench command
+    # (profiles/ncu_kmap16.json, written by tools/ncu_summary.py from the .ncu-rep): DRAM bytes, executed warp instructions
+    # and pipe utilisations per launch, keyed by the block count of the captured launch and scaled linearly to this batch
+    nk = {}
+    try:
+        nk = json.load(open(os.path.join(ROOT, "profiles", "ncu_kmap16.json")))
+    except Exception:
+        pass
+    cap_blocks = float(nk.get("blocks_per_launch") or 0)
+    traffic = (nk["dram_bytes_per_launch"] * B / cap_blocks) if (cap_blocks and K == nk.get("K")) else None
+    ratio = (traffic / bytes_per_launch) if traffic else None
+    actual_gbs = (traffic / (map_ms * 1e-3) / 1e9) if (traffic and n_map) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_map16", "avg_launch_ms": map_ms, "launches_timed": n_map,
                 "share_of_step": prof_ms[1] / kernel_ms_total if kernel_ms_total else None,
                 "kernel_ms": {"demux": prof_ms[0], "map": prof_ms[1], "x1": prof_ms[2], "x2": prof_ms[3]},
                 "peak_source": peak_src,
-                "actual_dram_gbs": (traffic / (map_ms * 1e-3) / 1e9) if (traffic and n_map) else None,
-                "note": "algorithmic bytes per launch = blocks x (2(3K+12)+K/8+1)/12 (SURVEY 8d: y read once, bytes + "
-                        "status written once, spread over the 12 MAP passes); the decoder streams its per-block state "
-                        "through HBM on every pass, so the traffic actually moved per launch (`traffic`, ncu) is ~11x "
-                        "the algorithmic figure; `actual_dram_gbs` = traffic / launch time.  The kernel is co-limited "
-                        "by the ALU pipe (VIADDMNMX issues every 2nd clock), the L1/shared-memory data pipe and HBM "
-                        "latency (ncu: 62 % / 60 % / 50 % of peak), see DESIGN.md and int_simd"}
-    # integer-SIMD view: SURVEY 8(d) counts 123 int16 ops / info bit / MAP pass; the peak is the MEASURED issue rate of
-    # the k_map16 instruction mix (tools/int16_peak.cu, profiles/int16_peak.json), scaled by the sampled SM clock
-    ops = B * K * 123.0
-    try:
-        ipk = json.load(open(os.path.join(ROOT, "profiles", "int16_peak.json")))
-        int_peak = ipk["int16_ops_peak_gops_kmap16_mix"] * 1e9 * ((clocks and clocks["sm_mhz"]) or 1965.0) / 1965.0
-        int_note = "peak = measured issue rate of the 2 VIADDMNMX + VIADD + IMAD mix (tools/int16_peak.cu) at the sampled SM clock"
-    except Exception:
-        int_peak = 148 * 128 * 2 * 1965.0e6
-        int_note = "paper peak = 148 SM x 128 lanes x 2 halfwords x 1965 MHz (profiles/int16_peak.json missing)"
-    int_simd = {"achieved_int16_gops": ops / (map_ms * 1e-3) / 1e9 if n_map else None,
-                "measured_peak_int16_gops": int_peak / 1e9, "note": int_note}
-    if int_simd["achieved_int16_gops"]:
-        int_simd["frac"] = int_simd["achieved_int16_gops"] / int_simd["measured_peak_int16_gops"]
-    # issue-slot view from executed instructions: ncu (profiles/r1h) counts 207.8 M warp instructions per k_map16
-    # launch of 23680 blocks at K=6144 = 8776 per block (the fast path needs 44 thread instructions per bit and pass,
-    # not SURVEY's nominal 123 ops); the SM issues at most 4 warp instructions per clock
-    if K == K_BITS and n_map:
+                "traffic_source": nk.get("source"),
+                "traffic_over_algorithmic": ratio,
+                "actual_dram_gbs": actual_gbs, "actual_dram_frac": (actual_gbs / peak) if actual_gbs else None,
+                "ncu_utilisation_pct": nk.get("utilisation_pct"),
+                "timing_note": "per-launch CUDA events are recorded around every kernel INSIDE the timed region (they are what "
+                               "`avg_launch_ms` and `kernel_ms` come from), so `value` includes their small overhead",
+                "note": "algorithmic bytes per launch = blocks x (2(3K+12)+K/8+1)/12 (SURVEY 8d: y read once, bytes + status "
+                        "written once, spread over the 12 MAP passes).  The decoder streams its per-block state through HBM "
+                        "on every pass, so the bytes really moved per launch (`traffic`, ncu dram__bytes of the committed "
+                        "capture) are `traffic_over_algorithmic` x that figure; `actual_dram_gbs` = traffic / launch time.  "
+                        "Of the kernel's resources HBM is the one closest to its measured peak (`actual_dram_frac`), ahead of "
+                        "the ALU pipe and the issue slots (`ncu_utilisation_pct`, `int_simd.issue_frac`): `bound` = hbm on "
+                        "the traffic the design moves, not on the algorithmic bytes"}
+    # integer-SIMD view from EXECUTED instructions (ncu smsp__inst_executed of the same capture): the SM issues at most
+    # 4 warp instructions per clock; the measured peak of the kernel's own instruction mix is in profiles/int16_peak.json
+    int_simd = {}
+    if K == nk.get("K") and n_map and cap_blocks:
         sm_hz = ((clocks and clocks["sm_mhz"]) or 1965.0) * 1e6
-        int_simd["executed_warp_instr_per_block_pass"] = 8776
-        int_simd["issue_frac"] = B * 8776.0 / (map_ms * 1e-3) / (148 * 4 * sm_hz)
+        wi = nk["warp_instructions_per_launch"] / cap_blocks
+        int_simd["executed_warp_instr_per_block_pass"] = wi
+        int_simd["issue_frac"] = B * wi / (map_ms * 1e-3) / (148 * 4 * sm_hz)
+        try:
+            ipk = json.load(open(os.path.join(ROOT, "profiles", "int16_peak.json")))
+            mix = ipk["warp_instr_per_clk_per_sm"]["2 VIADDMNMX+VIADD+IMAD (k_map16 mix)"]
+            int_simd["issue_frac_of_measured_mix_peak"] = B * wi / (map_ms * 1e-3) / (148 * mix * sm_hz)
+            int_simd["note"] = ("executed warp instructions per second / (148 SMs x 4 issue slots x SM clock); the measured peak of "
+                                "the kernel's instruction mix is %.2f of 4 slots (tools/int16_peak.cu)" % mix)
+        except Exception:
+            pass
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -431,8 +470,9 @@ def run_b200(args):
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
                        "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes, "tx_mirror": tx_side,
-            "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": call.h2d_bytes,
-                    "d2h_bytes_per_step": call.d2h_bytes, "ms_per_step": 1e3 * dt / args.steps,
+            "multicell_ul": multicell, "subframe_latency": subframes, "llr8": llr8_side,
+            "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h, "ms_per_step": 1e3 * dt / args.steps,
                     "in_flight": 1 if args.e2e_serial else 2,
                     "api": "oai_turbo_submit_batch + oai_turbo_wait per step, page-locked host input and output buffers; "
                            "bound by the PCIe copy of 36.9 KB of int16 LLRs per 6144 decoded bits"},
@@ -440,6 +480,180 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def device_rate(capi, B, K, llr8, steps):
+    """device-resident decoder throughput (noise regime, 6 iterations) of B blocks of size K; CUDA events"""
+    import torch
+    row = 3 * K + 12 + (4 if llr8 else 0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4321)
+    y = torch.randint(-16, 17, (B, row), dtype=torch.int16, device="cuda", generator=g)
+    out = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
+    st = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE, llr8=llr8)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        plan.decode(y.data_ptr(), row, out.data_ptr(), K // 8, st.data_ptr(), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.decode(y.data_ptr(), row, out.data_ptr(), K // 8, st.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if not (st == MAX_ITER + 1).all():
+        raise RuntimeError("bench.py: device_rate: noise-regime blocks must report status 7")
+    plan.close()
+    return {"value": B * K * steps / (ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": ms / steps}
+
+
+def subframe_latency(capi, tbs, G, Qm, max_it, llr8=0, reps=30):
+    """BASELINE configs[0]/[1]: wall-clock latency of ONE subframe's transport block through the host-buffer call
+    (page-locked soft bits e in -> fused front end + decoder -> bytes out), the drop-in replacement of the per-code-block
+    loops of ulsch_decoding.c:1222-1369 / dlsch_decoding.c:303-453.  Inputs come from the product's own TX chain
+    (openair4g_b200/sim/txchain.py): `clean` (sigma/A = 0.25: every block leaves at iteration 2) and `full_iterations`
+    (pure noise: max_it iterations).  Returns medians in ms."""
+    import ctypes as C
+    import numpy as np
+    from openair4g_b200.sim import txchain as tx
+    rc, seg = capi.lte_segmentation_params(tbs + 24)
+    assert rc == 0
+    Cn, F = seg["C"], seg["F"]
+    Ks = [seg["Kminus"] if r < seg["Cminus"] else seg["Kplus"] for r in range(Cn)]
+    rng = np.random.default_rng(tbs)
+    a = rng.integers(0, 2, size=(1, tbs)).astype(np.uint8)
+    b = np.concatenate([a, tx.crc24a(a)], axis=1)
+    L = 24 if Cn > 1 else 0
+    es, pos = [], 0
+    for r, K in enumerate(Ks):
+        cb = np.zeros((1, K), dtype=np.uint8)
+        f = F if r == 0 else 0
+        cb[:, f:K - L] = b[:, pos:pos + K - L - f]
+        pos += K - L - f
+        if Cn > 1:
+            cb[:, K - 24:] = tx.crc24b(cb[:, :K - 24])
+        bits, E = tx.rate_match(tx.turbo_encode(cb), K, f, G, Cn, Qm, 1, r, 0)
+        es.append(bits[0].astype(np.int64))
+    tx_bits = np.concatenate(es)
+    out = {"code_blocks": Cn, "K": Ks[-1], "max_iterations": max_it, "decoder": "8-bit" if llr8 else "16-bit"}
+    pin = capi.PinnedArray((G,), np.int16)
+    obuf = capi.PinnedArray((Cn, 768), np.uint8)
+    status = np.zeros(Cn, dtype=np.uint8)
+    pool = capi.HarqPool(Cn, max(Ks))
+    descs = (capi.CbDesc * Cn)()
+    off = 0
+    for r, K in enumerate(Ks):
+        d = descs[r]
+        d.in_ = pin.array.ctypes.data + 2 * off
+        off += es[r].size
+        d.decoded_bytes = obuf.array.ctypes.data + r * 768
+        d.status = status.ctypes.data + r
+        d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable, d.dematch_enable = K, max_it, (0 if Cn == 1 else 1), (F if r == 0 else 0), 1, 1
+        d.G, d.C, d.r, d.rvidx, d.clear, d.Qm, d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = G, Cn, r, 0, 1, Qm, 1, 8, 1, 1827072
+        d.llr8 = llr8
+        d.harq_pool = pool.handle
+        d.harq_slot = r
+    for name, sig in (("clean", 0.25), ("full_iterations", None)):
+        if sig is None:
+            pin.array[...] = rng.integers(-16, 17, size=G).astype(np.int16)
+        else:
+            pin.array[...] = np.clip(8 * (2 * tx_bits - 1) + np.rint(sig * 8 * rng.standard_normal(G)), -32768, 32767).astype(np.int16)
+        ts = []
+        for i in range(reps + 5):
+            h = C.c_void_p()
+            t0 = time.perf_counter()
+            if capi.lib.oai_turbo_submit_batch(descs, Cn, capi.BATCH_DL_STOP_AFTER_FAILURE if sig is not None else 0, -1, C.byref(h)) \
+                    or capi.lib.oai_turbo_wait(h):
+                raise RuntimeError("bench.py: subframe batch failed: " + capi.last_error())
+            if i >= 5:
+                ts.append(time.perf_counter() - t0)
+        want = 2 if sig is not None else max_it + 1
+        if not (status == want).all():
+            raise RuntimeError("bench.py: subframe latency (%s): unexpected status %s" % (name, status))
+        out[name] = 1e3 * statistics.median(ts)
+    pool.close()
+    return out
+
+
+def run_multicell_ul(args, capi, rank, world, dist, gpu):
+    """BASELINE configs[3] through the product path: 64 cells, every cell-subframe one 100 PRB MCS16 allocation
+    (ulsch_decoding.c:1222-1369 shape: C = 5 code blocks of K = 6144, G = 57600, Qm = 4, E = 11520 soft bits per block),
+    cells assigned to GPUs with sharding.assign_by_cell, one device-resident HARQ pool per GPU, rate-matched soft bits e
+    in page-locked host memory -> fused front end + decoder -> decoded bytes in page-locked host memory.  Fixed total work
+    (strong scaling over the 64 cells); timed on the host around submit + wait like `e2e`, max over ranks.
+    Two feeds: the reference's int16 soft bits and the narrow int8 feed (oai_cb_desc_t.in_fmt = 1)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from openair4g_b200 import sharding
+    K, G, Cb, Qm, cells = K_BITS, 57600, 5, 4, 64
+    E = G // Cb
+    S = args.mc_subframes
+    owner = sharding.assign_by_cell([c for c in range(cells) for _ in range(S)], world)     # one entry per cell-subframe
+    mine = [i for i, r in enumerate(owner) if r == rank]
+    n_ue = len(mine)
+    n = n_ue * Cb
+    out = capi.PinnedArray((max(n, 1), K // 8), np.uint8)
+    status = np.zeros(max(n, 1), dtype=np.uint8)
+    pool = capi.HarqPool(max(n, 1), K, gpu=gpu)
+    res = {}
+    for name, dt_np, fmt in (("e_int16", np.int16, 0), ("e_int8", np.int8, 1)):
+        pin = capi.PinnedArray((max(n_ue, 1), G), dt_np)
+        g = torch.Generator()
+        g.manual_seed(77 + rank)
+        pin.array[...] = torch.randint(-16, 17, (max(n_ue, 1), G), dtype=torch.int16, generator=g).numpy().astype(dt_np)
+        descs = (capi.CbDesc * max(n, 1))()
+        isz = pin.array.itemsize
+        for u in range(n_ue):
+            for r in range(Cb):
+                i = u * Cb + r
+                d = descs[i]
+                d.in_ = pin.array.ctypes.data + (u * G + r * E) * isz
+                d.decoded_bytes = out.array.ctypes.data + i * (K // 8)
+                d.status = status.ctypes.data + i
+                d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable, d.dematch_enable = K, MAX_ITER, CRC_TYPE, 0, 1, 1
+                d.G, d.C, d.r, d.rvidx, d.clear, d.Qm, d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = G, Cb, r, 0, 1, Qm, 1, 8, 1, 1827072
+                d.tb_id = mine[u]
+                d.harq_pool = pool.handle
+                d.harq_slot = i
+                d.in_fmt = fmt
+
+        def call():
+            if n == 0:
+                return
+            h = C.c_void_p()
+            if capi.lib.oai_turbo_submit_batch(descs, n, 0, gpu, C.byref(h)) or capi.lib.oai_turbo_wait(h):
+                raise SystemExit("bench.py: multicell_ul batch failed: " + capi.last_error())
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        if n and not (status[:n] == MAX_ITER + 1).all():
+            raise SystemExit("bench.py: multicell_ul noise-regime blocks must report status 7")
+        res[name] = {"value": cells * S * Cb * K * args.steps / dt / 1e6, "unit": "Mbit/s", "ms_per_step": 1e3 * dt / args.steps,
+                     "h2d_bytes_per_step_per_gpu": n_ue * G * isz, "d2h_bytes_per_step_per_gpu": n * (K // 8 + 1),
+                     "h2d_gbs_per_gpu": n_ue * G * isz * args.steps / dt / 1e9}
+        del pin
+    pool.close()
+    counts = [sum(1 for r in owner if r == k) * Cb for k in range(world)]
+    res["config"] = {"workload": "BASELINE configs[3]: %d cells x %d subframes x (100 PRB MCS16 = 5 x K=6144, E=11520), noise regime, "
+                                 "%d iterations; fixed total work, cells -> GPUs by sharding.assign_by_cell, one HARQ pool per GPU, "
+                                 "page-locked e in, bytes out" % (cells, S, MAX_ITER),
+                     "blocks_total": cells * S * Cb, "blocks_per_gpu": counts, "scaling": "strong",
+                     "api": "oai_turbo_submit_batch(dematch_enable, harq_pool, gpu) + oai_turbo_wait per step"}
+    return res
 
 
 def run_llr8(args, capi, B, K, rank, world, dist):
@@ -487,6 +701,9 @@ def main():
                     help="bounded CPU-baseline sample (blocks): ~4 s of wall time on 16 host threads (~60 s of CPU work)")
     ap.add_argument("--e2e-in-flight", type=int, default=1, choices=[1, 2], help="host-buffer batches in flight in the e2e loop")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-multicell", action="store_true", help="skip the BASELINE configs[3] multi-cell uplink measurement")
+    ap.add_argument("--mc-subframes", type=int, default=128, help="subframes per cell and step of the multi-cell measurement "
+                    "(64 cells x 128 subframes x 5 blocks = 40960 code blocks per step in total)")
     ap.add_argument("--no-regimes", action="store_true", help="skip the clean / waterfall side measurements")
     ap.add_argument("--llr8", action="store_true", help="measure the 8-bit decoder (BASELINE configs[4]) instead")
     ap.add_argument("--K", type=int, default=K_BITS, help="block size for --llr8 / side measurements")

@@ -156,6 +156,11 @@ typedef struct {
   uint32_t  scr_c_init;
   uint32_t  scr_offset;
   uint8_t   scr_enable;
+  /* format of `in` for front-end blocks (dematch_enable != 0): 0 = int16 soft bits (the reference's type), 1 = int8
+   * soft bits (int8_t[E] behind the pointer; the values a caller's demapper already clips to 8 bits for the 8-bit
+   * decoder).  Same arithmetic on the device (the dematcher accumulates into int16 w); half the bytes on the host link.
+   * Must be 0 when dematch_enable == 0. */
+  uint8_t   in_fmt;
 } oai_cb_desc_t;
 
 /* HARQ soft-buffer pool in HBM.  The reference keeps w[r] (int16[3*Kpi]) per (UE, HARQ process, code block) in host
@@ -181,6 +186,30 @@ int oai_turbo_submit_batch(const oai_cb_desc_t *cbs, int ncb, unsigned flags, in
 /* Blocks until the batch is finished, scatters decoded_bytes/status/w back to the
  * host pointers of the descriptors and frees the handle. */
 int oai_turbo_wait(oai_turbo_batch_t *handle);
+
+/* Transport-block outputs.  A transport block is C consecutive descriptors of the cbs array, r = 0..C-1
+ * in order.  After the decode, the GPU evaluates the reference's transport-block rules and assembles `b`:
+ *   uplink == 0 : dlsch_decoding.c:417,448-451 (err_flag), :455-483 (return value), :486-512 (reassembly only when every
+ *                 block passed; on a NACK *ret = 1 + max_iterations, *valid_bytes = 0 and b is left untouched);
+ *   uplink != 0 : ulsch_decoding.c:1380-1409 (a failed block is skipped without advancing the offset; *ret = status of
+ *                 the last passing block, or 1 + max_iterations once a block has failed).
+ * b receives sum(Kr/8) - (F>>3) - (C > 1 ? 3*C : 0) bytes at most (filler bytes of block 0 skipped, CRC24B of every
+ * block stripped when C > 1); one device->host copy per batch carries all transport blocks, so the descriptors of
+ * their code blocks may leave decoded_bytes NULL (no per-block copy then).  max_iterations and F are taken from the
+ * descriptor of block 0. */
+typedef struct {
+  uint32_t  first_cb;        /* index of block r = 0 in the cbs array */
+  uint32_t  C;               /* 1..16 */
+  uint8_t  *b;               /* out (host), may be NULL */
+  uint32_t  b_capacity;      /* bytes available behind b */
+  uint8_t  *ret;             /* out (host), may be NULL: the value dlsch_decoding / ulsch_decoding would return */
+  uint32_t *valid_bytes;     /* out (host), may be NULL: bytes written to b (the reference's final `offset`) */
+  uint8_t   uplink;
+} oai_tb_desc_t;
+
+/* oai_turbo_submit_batch plus transport-block outputs; wait with oai_turbo_wait. */
+int oai_turbo_submit_tbs(const oai_cb_desc_t *cbs, int ncb, const oai_tb_desc_t *tbs, int ntb, unsigned flags, int gpu,
+                         oai_turbo_batch_t **handle);
 
 /* Page-locked host memory for batch inputs / outputs.  Buffers from this allocator (or any
  * other cudaHostAlloc / cudaHostRegister memory) are copied from and to directly; pageable

@@ -26,7 +26,7 @@ LIB_PATH = _build.LIB
 
 EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_turbo_decoder16",
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
-           "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_wait",
+           "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_submit_tbs", "oai_turbo_wait",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
            "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
            "oai_turbo_harq_pool_create", "oai_turbo_harq_pool_read", "oai_turbo_harq_pool_destroy",
@@ -44,7 +44,14 @@ class CbDesc(C.Structure):
                 ("Nsoft", C.c_uint32), ("C", C.c_uint8), ("r", C.c_uint8), ("rvidx", C.c_uint8),
                 ("clear", C.c_uint8), ("Qm", C.c_uint8), ("Nl", C.c_uint8), ("Mdlharq", C.c_uint8),
                 ("Kmimo", C.c_uint8), ("tb_id", C.c_uint32), ("harq_pool", C.c_void_p), ("harq_slot", C.c_uint32),
-                ("scr_c_init", C.c_uint32), ("scr_offset", C.c_uint32), ("scr_enable", C.c_uint8)]
+                ("scr_c_init", C.c_uint32), ("scr_offset", C.c_uint32), ("scr_enable", C.c_uint8),
+                ("in_fmt", C.c_uint8)]
+
+
+class TbDesc(C.Structure):
+    """oai_tb_desc_t"""
+    _fields_ = [("first_cb", C.c_uint32), ("C", C.c_uint32), ("b", C.c_void_p), ("b_capacity", C.c_uint32),
+                ("ret", C.c_void_p), ("valid_bytes", C.c_void_p), ("uplink", C.c_uint8)]
 
 
 class TxDesc(C.Structure):
@@ -78,6 +85,7 @@ lib.lte_rate_matching_turbo.restype = C.c_uint32
 lib.oai_turbo_tx_batch.argtypes = [C.POINTER(TxDesc), C.c_int, C.c_uint, C.c_int]
 lib.oai_turbo_tx_batch.restype = C.c_int
 lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
+lib.oai_turbo_submit_tbs.argtypes = [C.POINTER(CbDesc), C.c_int, C.POINTER(TbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
 lib.oai_lte_segmentation_params.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 6
 lib.oai_lte_segmentation_params.restype = C.c_int
@@ -201,8 +209,11 @@ def tx_batch(blocks, gpu=-1):
     return [outs[i][:descs[i].E].copy() for i in range(n)]
 
 
-def decode_batch(blocks, flags=0, gpu=-1):
+def decode_batch(blocks, flags=0, gpu=-1, tbs=None, cb_out=True):
     """blocks: list of dicts {y, K, max_iterations, crc_type, F=0, tb_id=0, llr8=0, decode_enable=1}.
+    tbs: optional list of dicts {first_cb, C, uplink} -> oai_turbo_submit_tbs; the function then returns a third value,
+    the list of (ret, valid_bytes, b) per transport block (b: uint8 array of the bytes the GPU assembled; a 0xA5 fill
+    pattern shows what was left untouched).  cb_out=False leaves decoded_bytes NULL (transport-block outputs only).
     With "dematch": {G, C, r, rvidx, clear, Qm, Nl=1, Mdlharq=8, Kmimo=1, Nsoft=1827072, w=int16 array or None}
     `y` is the block's slice of rate-matched soft bits e and the front end runs on the GPU first.
     One submit + wait; returns (list of uint8 arrays, list of status ints)."""
@@ -211,13 +222,13 @@ def decode_batch(blocks, flags=0, gpu=-1):
     keep, outs = [], []
     status = np.full(n, 255, dtype=np.uint8)
     for i, b in enumerate(blocks):
-        y = np.ascontiguousarray(b["y"], dtype=np.int16)
+        y = np.ascontiguousarray(b["y"], dtype=np.int8 if b.get("in_fmt") else np.int16)
         out = np.zeros(b["K"] // 8 + 4, dtype=np.uint8)
         keep.append(y)
         outs.append(out)
         d = descs[i]
         d.in_ = y.ctypes.data
-        d.decoded_bytes = out.ctypes.data
+        d.decoded_bytes = out.ctypes.data if cb_out else None
         d.status = status.ctypes.data + i
         d.K = b["K"]
         d.max_iterations = b["max_iterations"]
@@ -226,6 +237,7 @@ def decode_batch(blocks, flags=0, gpu=-1):
         d.llr8 = b.get("llr8", 0)
         d.decode_enable = b.get("decode_enable", 1)
         d.tb_id = b.get("tb_id", 0)
+        d.in_fmt = b.get("in_fmt", 0)
         dm = b.get("dematch")
         if dm:
             d.dematch_enable = 1
@@ -242,14 +254,32 @@ def decode_batch(blocks, flags=0, gpu=-1):
                 d.harq_pool = dm["harq_pool"].handle
                 d.harq_slot = dm["harq_slot"]
     h = C.c_void_p()
-    rc = lib.oai_turbo_submit_batch(descs, n, flags, gpu, C.byref(h))
+    if tbs is None:
+        rc = lib.oai_turbo_submit_batch(descs, n, flags, gpu, C.byref(h))
+    else:
+        nt = len(tbs)
+        tds = (TbDesc * max(nt, 1))()
+        rets = np.full(nt, 0xEE, dtype=np.uint8)
+        valid = np.full(nt, 0xFFFFFFFF, dtype=np.uint32)
+        bs = []
+        for i, t in enumerate(tbs):
+            cap = sum(blocks[t["first_cb"] + r]["K"] // 8 for r in range(t["C"])) + 8
+            bb = np.full(cap, 0xA5, dtype=np.uint8)
+            bs.append(bb)
+            tds[i].first_cb, tds[i].C, tds[i].uplink = t["first_cb"], t["C"], t.get("uplink", 0)
+            tds[i].b, tds[i].b_capacity = bb.ctypes.data, cap
+            tds[i].ret, tds[i].valid_bytes = rets.ctypes.data + i, valid.ctypes.data + 4 * i
+        rc = lib.oai_turbo_submit_tbs(descs, n, tds, nt, flags, gpu, C.byref(h))
     if rc != 0:
         raise RuntimeError("oai_turbo_submit_batch failed (%d): %s" % (rc, last_error()))
     if h.value:
         rc = lib.oai_turbo_wait(h)
         if rc != 0:
             raise RuntimeError("oai_turbo_wait failed (%d): %s" % (rc, last_error()))
-    return [o[: b["K"] // 8] for o, b in zip(outs, blocks)], [int(s) for s in status]
+    res = [o[: b["K"] // 8] for o, b in zip(outs, blocks)], [int(s) for s in status]
+    if tbs is None:
+        return res
+    return res[0], res[1], [(int(rets[i]), int(valid[i]), bs[i]) for i in range(len(tbs))]
 
 
 def debug_map16(y, K, term, policy=0):

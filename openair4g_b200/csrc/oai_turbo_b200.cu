@@ -21,6 +21,7 @@
 #include "rm_kernels.cuh"
 #include "td8_kernels.cuh"
 #include "tx_kernels.cuh"
+#include "tb_kernels.cuh"
 
 namespace oai {
 
@@ -666,6 +667,41 @@ struct HostBatch {
   std::vector<RmBlock> rm;
   std::vector<int> rm_desc;        // descriptor index of each RmBlock
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // OAI_TURBO_TRACE: submit, H2D done, kernels done, D2H done
+  // transport-block outputs (oai_turbo_submit_tbs): reassembled b + return value per transport block, built on the device
+  std::vector<oai_tb_desc_t> tbs;
+  std::vector<TbMeta> tb_meta;
+  std::vector<TbBlk> tb_blk;
+  TbMeta* d_tbmeta = nullptr; TbBlk* d_tbblk = nullptr; TbResult* d_tbres = nullptr; TbResult* h_tbres = nullptr;
+  uint8_t* d_tbpool = nullptr; uint8_t* h_tbpool = nullptr;
+  int cap_tb = 0, cap_tbblk = 0; size_t cap_tbpool = 0;
+  bool want_cb_out = true;         // some descriptor has decoded_bytes != NULL
+  int ensure_tb(int ntb, int nblk, size_t pool_bytes) {
+    if (ntb > cap_tb) {
+      if (d_tbmeta) cudaFree(d_tbmeta);
+      if (d_tbres) cudaFree(d_tbres);
+      if (h_tbres) cudaFreeHost(h_tbres);
+      d_tbmeta = nullptr; d_tbres = nullptr; h_tbres = nullptr; cap_tb = 0;
+      CU(cudaMalloc(&d_tbmeta, sizeof(TbMeta) * ntb));
+      CU(cudaMalloc(&d_tbres, sizeof(TbResult) * ntb));
+      CU(cudaMallocHost(&h_tbres, sizeof(TbResult) * ntb));
+      cap_tb = ntb;
+    }
+    if (nblk > cap_tbblk) {
+      if (d_tbblk) cudaFree(d_tbblk);
+      d_tbblk = nullptr; cap_tbblk = 0;
+      CU(cudaMalloc(&d_tbblk, sizeof(TbBlk) * nblk));
+      cap_tbblk = nblk;
+    }
+    if (pool_bytes > cap_tbpool) {
+      if (d_tbpool) cudaFree(d_tbpool);
+      if (h_tbpool) cudaFreeHost(h_tbpool);
+      d_tbpool = nullptr; h_tbpool = nullptr; cap_tbpool = 0;
+      CU(cudaMalloc(&d_tbpool, pool_bytes));
+      CU(cudaMallocHost(&h_tbpool, pool_bytes));
+      cap_tbpool = pool_bytes;
+    }
+    return 0;
+  }
   // bookkeeping of the submitted batch
   std::vector<oai_cb_desc_t> descs;
   std::vector<int> order;          // GPU block i <-> descriptor order[i]
@@ -778,6 +814,14 @@ struct HostBatch {
     if (d_gseq) { cudaFree(d_gseq); d_gseq = nullptr; }
     if (d_gold) { cudaFree(d_gold); d_gold = nullptr; }
     cap_gseq = 0; cap_gold = 0;
+    if (d_tbmeta) cudaFree(d_tbmeta);
+    if (d_tbres) cudaFree(d_tbres);
+    if (h_tbres) cudaFreeHost(h_tbres);
+    if (d_tbblk) cudaFree(d_tbblk);
+    if (d_tbpool) cudaFree(d_tbpool);
+    if (h_tbpool) cudaFreeHost(h_tbpool);
+    d_tbmeta = nullptr; d_tbres = nullptr; h_tbres = nullptr; d_tbblk = nullptr; d_tbpool = nullptr; h_tbpool = nullptr;
+    cap_tb = cap_tbblk = 0; cap_tbpool = 0;
     cap_e = cap_w = 0; cap_rm = 0;
     if (h_in) { cudaFreeHost(h_in); h_in = nullptr; }
     if (d_in) { cudaFree(d_in); d_in = nullptr; }
@@ -798,9 +842,16 @@ struct HostBatch {
     cap_blocks = cap_K = 0; cap_in = cap_out = 0;
   }
 
-  int submit(const oai_cb_desc_t* cbs, int ncb, unsigned fl, int gpu) {
+  int submit(const oai_cb_desc_t* cbs, int ncb, unsigned fl, int gpu, const oai_tb_desc_t* tb_in = nullptr, int ntb = 0) {
     descs.assign(cbs, cbs + ncb);
     flags = fl;
+    tbs.clear(); tb_meta.clear(); tb_blk.clear();
+    for (int i = 0; i < ntb; ++i) {
+      const oai_tb_desc_t& t = tb_in[i];
+      if (t.C == 0 || t.C > (uint32_t)TB_MAX_C || (unsigned long long)t.first_cb + t.C > (unsigned long long)ncb)
+        return fail(-4, "transport block %d: code blocks [%u, %u) are not inside the descriptor array / C > 16", i, t.first_cb, t.first_cb + t.C);
+    }
+    if (ntb > 0) tbs.assign(tb_in, tb_in + ntb);
     static const bool trace = getenv("OAI_TURBO_TRACE") != nullptr;
     // handles are recycled: nothing of the previous batch may survive an early return below (wait() walks these)
     order.clear(); rm.clear(); rm_desc.clear(); gseq.clear(); direct_out = false;
@@ -812,6 +863,7 @@ struct HostBatch {
       // without the front end a block that is not decoded needs no GPU work at all; with it the
       // HARQ buffer is still combined (dlsch_decoding.c:333-385 runs before the err_flag test)
       if (!d.decode_enable && !d.dematch_enable) { if (d.status) *d.status = 0xFE; continue; }
+      if (d.in_fmt > 1 || (d.in_fmt && !d.dematch_enable)) return fail(-4, "block %d: in_fmt %d is only defined for front-end blocks (int8 soft bits e)", i, (int)d.in_fmt);
       order.push_back(i);
       Kmax = std::max<int>(Kmax, d.K);
     }
@@ -823,7 +875,11 @@ struct HostBatch {
     };
     if (!std::is_sorted(order.begin(), order.end(), before)) std::stable_sort(order.begin(), order.end(), before);
     const int n = (int)order.size();
-    if (n == 0) return 0;
+    if (n == 0) {                                            // no block reaches the GPU: every transport block has failed
+      for (auto& t : tbs) { if (t.ret) *t.ret = (uint8_t)(1 + descs[t.first_cb].max_iterations); if (t.valid_bytes) *t.valid_bytes = 0; }
+      tbs.clear();
+      return 0;
+    }
     n16 = 0;
     int Kmax8 = 0;
     for (int i = 0; i < n; ++i) {
@@ -899,9 +955,9 @@ struct HostBatch {
       }
     }
     std::vector<CbMeta> meta(n);
-    size_t e_hw = 0, w_hw = 0;
+    size_t e_hw = 0, w_hw = 0, e_bytes_run = 0;
     oai_turbo_harq_pool* pool = nullptr;
-    const int16_t* prev_e_end = nullptr;
+    const char* prev_e_end = nullptr;
     std::unordered_map<uint32_t, int> seq_of;                // c_init -> index in gseq
     std::vector<int> rm_seq;                                 // per rm block: its sequence or -1
     for (int i = 0; i < n; ++i) {
@@ -928,13 +984,18 @@ struct HostBatch {
         }
         // soft bits that follow the previous block's in the caller's memory (r_offset slices of one e buffer,
         // ulsch_decoding.c:1259) keep that spacing on the device, so that a run goes over with one copy
-        const bool cont = !rm.empty() && d.in == prev_e_end;
-        if (!cont) e_hw = (e_hw + 7) & ~(size_t)7;
-        prev_e_end = d.in + q.E;
+        // (int8 soft bits, in_fmt 1: a run must start on an int16 boundary of the pool, so only even-length predecessors
+        // continue a run -- E is a multiple of Qm*Nl, odd only for odd Nl*Qm, which LTE does not have)
+        rb.e_fmt = d.in_fmt ? 1u : 0u;
+        const size_t e_bytes = d.in_fmt ? (size_t)q.E : 2 * (size_t)q.E;
+        const bool cont = !rm.empty() && (const char*)d.in == prev_e_end && rm.back().e_fmt == rb.e_fmt && !(e_bytes_run & 1);
+        if (!cont) { e_hw = (e_hw + 7) & ~(size_t)7; e_bytes_run = 0; }
+        prev_e_end = (const char*)d.in + e_bytes;
+        e_bytes_run += e_bytes;
         rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
         rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
-        e_hw += (size_t)q.E;
+        e_hw += (e_bytes + 1) >> 1;
         if (!d.harq_pool) w_hw += (size_t)3 * q.Kpi;
         rb.gold_off = 0xffffffffu; rb.scr_off = d.scr_offset;
         int sq = -1;
@@ -953,14 +1014,17 @@ struct HostBatch {
       for (size_t j = jlo; j < jhi;) {
         const oai_cb_desc_t& d0 = descs[rm_desc[j]];
         const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
-        size_t len = rm[j].E, k = j + 1;
-        while (k < jhi && descs[rm_desc[k]].in == d0.in + len) { len += rm[k].E; ++k; }
+        // lengths in bytes; a block continues the run when it follows in the caller's memory AND in the device pool
+        auto nbytes = [&](size_t x) -> size_t { return rm[x].e_fmt ? (size_t)rm[x].E : 2 * (size_t)rm[x].E; };
+        auto eoff = [&](size_t x) -> size_t { return 2 * (((size_t)rm[x].e_off_hi << 32) | rm[x].e_off_lo); };
+        size_t len = nbytes(j), k = j + 1;
+        while (k < jhi && (const char*)descs[rm_desc[k]].in == (const char*)d0.in + len && eoff(k) == 2 * eo + len) { len += nbytes(k); ++k; }
         cudaPointerAttributes at;
         const bool pinned = (cudaPointerGetAttributes(&at, d0.in) == cudaSuccess) && at.type == cudaMemoryTypeHost;
         cudaGetLastError();
-        const int16_t* src = d0.in;
-        if (!pinned) { memcpy(h_e + eo, d0.in, sizeof(int16_t) * len); src = h_e + eo; }
-        CU(cudaMemcpyAsync(d_e + eo, src, len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+        const void* src = d0.in;
+        if (!pinned) { memcpy(h_e + eo, d0.in, len); src = h_e + eo; }
+        CU(cudaMemcpyAsync(d_e + eo, src, len, cudaMemcpyHostToDevice, cs));
         j = k;
       }
       return 0;
@@ -1020,7 +1084,9 @@ struct HostBatch {
         cudaGetLastError();
       }
       direct_out = ok;
-      if (!direct_out) { rc = ensure_stage_out(); if (rc) return rc; }
+      want_cb_out = false;                                   // no descriptor wants its block's bytes (transport-block outputs only)
+      for (int i = 0; i < n && !want_cb_out; ++i) want_cb_out = descs[order[i]].decoded_bytes != nullptr;
+      if (!direct_out && want_cb_out) { rc = ensure_stage_out(); if (rc) return rc; }
     }
     CU(cudaMemsetAsync(d_out, 0, out_b, st));
     if (n16 > 0) {
@@ -1051,7 +1117,7 @@ struct HostBatch {
       CU(cudaEventRecord(ev_done[part], st));
       CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
       const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
-      CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
+      if (want_cb_out) CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
     }
     if (trace) cudaEventRecord(ev[1], st);
     if (n16 > 0 && parts == 1) {
@@ -1064,12 +1130,44 @@ struct HostBatch {
       rc = b8.decode8(d_in, d_out, d_status + n16, st);
       if (rc < 0) return rc;
     }
+    if (!tbs.empty()) {
+      // transport-block reassembly + return values on the device (tb_kernels.cuh); runs after every decode of the batch
+      std::vector<int> gpu_of(descs.size(), -1);
+      for (int i = 0; i < n; ++i) gpu_of[order[i]] = i;
+      size_t pool_b = 0;
+      for (const auto& t : tbs) {
+        TbMeta m;
+        memset(&m, 0, sizeof(m));
+        m.first = (uint32_t)tb_blk.size(); m.C = t.C; m.F = descs[t.first_cb].F; m.b_off = (uint32_t)pool_b;
+        m.uplink = t.uplink ? 1 : 0; m.max_iter = descs[t.first_cb].max_iterations;
+        m.stop_after_failure = (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) ? 1 : 0;
+        size_t tb_bytes = 0;
+        for (uint32_t r = 0; r < t.C; ++r) {
+          const int di = (int)(t.first_cb + r), gi = gpu_of[di];
+          // blocks that cannot deliver bytes count as failed: not on the GPU, not decoded, or fewer than 2 iterations
+          // (no hard decision, TD16:1267)
+          const bool usable = gi >= 0 && descs[di].decode_enable && descs[di].max_iterations >= 2;
+          tb_blk.push_back(TbBlk{usable ? gi : -1, usable ? out_off[gi] : 0u, (uint32_t)(descs[di].K >> 3)});
+          tb_bytes += descs[di].K >> 3;
+        }
+        tb_meta.push_back(m);
+        pool_b += (tb_bytes + 15) & ~(size_t)15;
+      }
+      rc = ensure_tb((int)tbs.size(), (int)tb_blk.size(), pool_b);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(d_tbmeta, tb_meta.data(), sizeof(TbMeta) * tb_meta.size(), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_tbblk, tb_blk.data(), sizeof(TbBlk) * tb_blk.size(), cudaMemcpyHostToDevice, st));
+      k_tb_assemble<<<(int)tbs.size(), TB_THREADS, 0, st>>>(d_tbmeta, (int)tbs.size(), d_tbblk, d_out, d_status, d_tbpool, d_tbres);
+      ++g_launches;
+      CU(cudaMemcpyAsync(h_tbpool, d_tbpool, pool_b, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(h_tbres, d_tbres, sizeof(TbResult) * tbs.size(), cudaMemcpyDeviceToHost, st));
+    }
     if (trace) cudaEventRecord(ev[2], st);
     const size_t out_used = (size_t)out_off[n - 1] + (descs[order[n - 1]].K >> 3);
     if (parts > 1) {
       CU(cudaEventRecord(ev_out, st_out));
       CU(cudaStreamWaitEvent(st, ev_out, 0));
-    } else {
+    } else if (want_cb_out) {
       CU(cudaMemcpyAsync(direct_out ? descs[order[0]].decoded_bytes : h_out, d_out, direct_out ? out_used : out_b, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
@@ -1095,6 +1193,14 @@ struct HostBatch {
     for (size_t j = 0; j < rm.size(); ++j) {                     // HARQ buffers back to their owners
       const oai_cb_desc_t& d = descs[rm_desc[j]];
       if (d.w && !rm[j].w_sel) memcpy(d.w, h_w + rm[j].w_off, sizeof(int16_t) * rm[j].Ncb);
+    }
+    for (size_t i = 0; i < tbs.size(); ++i) {                   // transport blocks assembled on the device
+      const oai_tb_desc_t& t = tbs[i];
+      const uint32_t nb = h_tbres[i].valid_bytes;
+      if (t.ret) *t.ret = h_tbres[i].ret;
+      if (t.valid_bytes) *t.valid_bytes = nb;
+      // downlink NACK: valid_bytes is 0 and b stays untouched like in the reference (dlsch_decoding.c:455-469)
+      if (t.b && nb) memcpy(t.b, h_tbpool + tb_meta[i].b_off, std::min<uint32_t>(nb, t.b_capacity));
     }
     if (flags & OAI_BATCH_DL_STOP_AFTER_FAILURE) {
       // dlsch_decoding.c:400,417,448-451: after the first failing block of a transport block the
@@ -1181,6 +1287,21 @@ int oai_turbo_submit_batch(const oai_cb_desc_t* cbs, int ncb, unsigned flags, in
   }
   if (!h) h = new oai_turbo_batch();
   int rc = h->hb.submit(cbs, ncb, flags, gpu);
+  if (rc) { h->hb.release(); delete h; return rc; }
+  *handle = h;
+  return 0;
+}
+
+int oai_turbo_submit_tbs(const oai_cb_desc_t* cbs, int ncb, const oai_tb_desc_t* tbs, int ntb, unsigned flags, int gpu,
+                         oai_turbo_batch_t** handle) {
+  if (!cbs || ncb <= 0 || !handle || ntb < 0 || (ntb > 0 && !tbs)) return fail(-1, "bad arguments");
+  oai_turbo_batch* h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool.empty()) { h = g_pool.back(); g_pool.pop_back(); }
+  }
+  if (!h) h = new oai_turbo_batch();
+  int rc = h->hb.submit(cbs, ncb, flags, gpu, tbs, ntb);
   if (rc) { h->hb.release(); delete h; return rc; }
   *handle = h;
   return 0;

@@ -29,6 +29,7 @@ struct RmBlock {
   uint32_t y_off_lo, y_off_hi;   // int16 offset of the decoder input y (3K+12) written by k_deint
   uint32_t gold_off;        // word offset of this block's scrambling sequence in the Gold pool, 0xffffffff: soft bits are not scrambled
   uint32_t scr_off;         // position of this block's first soft bit in that sequence (r_offset, dlsch_decoding.c:333-347)
+  uint32_t e_fmt;           // 0: soft bits are int16 (the reference's type), 1: int8 (narrow host feed; same values)
 };
 
 // Pseudo-random sequences of 36.211 7.2, 32 bits per step like the reference's lte_gold_generic
@@ -124,6 +125,8 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
   const RmBlock b = blocks[blk];
   int16_t* w = (b.w_sel ? harq_pool : w_pool) + b.w_off;
   const int16_t* e = e_pool + (((long)b.e_off_hi << 32) | b.e_off_lo);
+  const int8_t* e8 = reinterpret_cast<const int8_t*>(e);           // e_fmt == 1: the same soft bits, one byte each
+  const bool narrow = b.e_fmt != 0;
   const uint8_t* dm = (b.dummy_off == 0xffffffffu) ? nullptr : dummy_pool + b.dummy_off;
   const uint32_t magic = 0xffffffffu / b.RTC + 1;
   const uint32_t* gs = (gold && b.gold_off != 0xffffffffu) ? gold + b.gold_off : nullptr;
@@ -150,11 +153,12 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
       if (gs) {
         for (uint32_t k = rank; k < b.E; k += N) {
           const uint32_t pos = b.scr_off + k;
-          const int v = e[k];
+          const int v = narrow ? (int)e8[k] : (int)e[k];
           acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
         }
       } else {
-        for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+        if (narrow) { for (uint32_t k = rank; k < b.E; k += N) acc += e8[k]; }
+        else { for (uint32_t k = rank; k < b.E; k += N) acc += e[k]; }
       }
     }
     w[i] = (int16_t)acc;                                 // wraps like the reference's int16 +=

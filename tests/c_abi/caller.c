@@ -5,7 +5,8 @@
  *   (1) the per-code-block loop of dlsch_decoding.c:303-453 (generate_dummy_w -> lte_rate_matching_turbo_rx ->
  *       sub_block_deinterleaving_turbo -> memset c[r] -> tc(), err_flag rule) and the transport-block reassembly of
  *       :486-512, through the library's section-1 entry points, and
- *   (2) the batched equivalent (oai_turbo_submit_batch with the fused front end and OAI_BATCH_DL_STOP_AFTER_FAILURE)
+ *   (2) the batched equivalent (oai_turbo_submit_tbs: fused front end, OAI_BATCH_DL_STOP_AFTER_FAILURE, transport-block
+ *       reassembly and return value on the GPU)
  * on one transport block read from a vector file, comparing c[r], ret and b with the expectations stored in the file
  * (produced by the oracle chain in tests/test_gpu_c_caller.py).  Test infrastructure, not product code.
  *
@@ -53,12 +54,13 @@ static int check(const char *what, const hdr_t *h, harq_t *hq, uint32_t ret, uin
     if (memcmp(hq->c[r], c_exp[r], Kr >> 3)) { printf("%s: c[%d] differs\n", what, r); bad = 1; }
   }
   if ((int)ret != h->expected_ret) { printf("%s: ret %u, expected %d\n", what, ret, h->expected_ret); bad = 1; }
-  if (h->b_bytes && memcmp(hq->b, b_exp, h->b_bytes)) { printf("%s: transport block b differs\n", what); bad = 1; }
+  if (b_exp && h->b_bytes && memcmp(hq->b, b_exp, h->b_bytes)) { printf("%s: transport block b differs\n", what); bad = 1; }
   return bad;
 }
 
 int main(int argc, char **argv)
 {
+  setvbuf(stdout, NULL, _IONBF, 0);
   if (argc < 2) { fprintf(stderr, "usage: caller <vector file>\n"); return 2; }
   FILE *f = fopen(argv[1], "rb");
   int32_t magic = 0;
@@ -173,18 +175,25 @@ int main(int argc, char **argv)
     }
   }
   oai_turbo_batch_t *hb;
-  if (oai_turbo_submit_batch(cb, h.C, OAI_BATCH_DL_STOP_AFTER_FAILURE, -1, &hb) || oai_turbo_wait(hb)) {
+  oai_tb_desc_t tbd;
+  uint8_t tb_ret = 0xEE;
+  uint32_t tb_valid = 0;
+  memset(&tbd, 0, sizeof(tbd));
+  memset(hq.b, 0x5A, h.b_bytes + 64);
+  tbd.first_cb = 0; tbd.C = h.C; tbd.b = hq.b; tbd.b_capacity = h.b_bytes + 64; tbd.ret = &tb_ret; tbd.valid_bytes = &tb_valid;
+  tbd.uplink = 0;
+  if (oai_turbo_submit_tbs(cb, h.C, &tbd, 1, OAI_BATCH_DL_STOP_AFTER_FAILURE, -1, &hb) || oai_turbo_wait(hb)) {
     printf("caller: batched call failed: %s\n", oai_turbo_b200_last_error());
     return 1;
   }
-  ret = status[h.C - 1];
-  err_flag = 0;
-  for (r = 0; r < (uint32_t)h.C; r++)
-    if (status[r] == 0xFE || status[r] >= 1 + h.max_turbo_iterations) err_flag = 1;
-  if (err_flag) ret = 1 + h.max_turbo_iterations;
-  for (r = 0; r < (uint32_t)h.C && !err_flag; r++)
-    if (status[r] != ret_exp[r]) { printf("batched: status[%u] = %u, expected %u\n", r, status[r], ret_exp[r]); bad = 1; }
-  bad |= check("batched submit", &h, &hq, ret, c_exp, NULL);
+  err_flag = (tb_ret >= 1 + h.max_turbo_iterations);
+  for (r = 0; r < (uint32_t)h.C; r++) {
+    uint8_t want = ret_exp[r];                 /* 0xFE in the vector = not decoded (after the first failing block) */
+    if (status[r] != want) { printf("batched: status[%u] = %u, expected %u\n", r, status[r], want); bad = 1; }
+  }
+  if ((int)tb_valid != (err_flag ? 0 : h.b_bytes)) { printf("batched: %u bytes of b, expected %d\n", tb_valid, err_flag ? 0 : h.b_bytes); bad = 1; }
+  if (err_flag && hq.b[0] != 0x5A) { printf("batched: b written on a NACK\n"); bad = 1; }
+  bad |= check("batched submit (b and ret from the GPU)", &h, &hq, tb_ret, c_exp, err_flag ? NULL : b_exp);
 
   free_td16();
   free_td8();

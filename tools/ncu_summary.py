@@ -28,3 +28,32 @@ for k in keys:
     if k in hdr:
         i = hdr.index(k)
         print("%-85s %-12s %s" % (k, units[i], " | ".join(r[i] for r in data)))
+
+# --json OUT KERNEL_SUBSTR BLOCKS K : the per-launch means bench.py's roofline object reads (profiles/ncu_kmap16.json)
+if "--json" in sys.argv:
+    import json
+    a = sys.argv.index("--json")
+    out, sub, blocks, K = sys.argv[a + 1], sys.argv[a + 2], int(sys.argv[a + 3]), int(sys.argv[a + 4])
+    col = {k: hdr.index(k) for k in hdr}
+    sel = [r for r in data if sub in r[col["Kernel Name"]]]
+
+    def val(r, k):                                     # value in base units (ncu prints Gbyte / Mbyte / Kbyte per column)
+        v = float(r[col[k]].replace(",", ""))
+        u = units[col[k]].lower()
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+
+    def mean(k):
+        return sum(val(r, k) for r in sel) / len(sel)
+    js = {"kernel": sub, "launches_captured": len(sel), "blocks_per_launch": blocks, "K": K,
+          "dram_bytes_per_launch": mean("dram__bytes_read.sum") + mean("dram__bytes_write.sum"),
+          "dram_bytes_read_per_launch": mean("dram__bytes_read.sum"), "dram_bytes_write_per_launch": mean("dram__bytes_write.sum"),
+          "warp_instructions_per_launch": mean("smsp__inst_executed.sum"),
+          "duration_us_under_ncu": mean("gpu__time_duration.sum"),
+          "utilisation_pct": {"issue_slots": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                              "alu_pipe": mean("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                              "fma_pipe": mean("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                              "dram_of_ncu_peak": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                              "warps_active": mean("sm__warps_active.avg.pct_of_peak_sustained_active")},
+          "source": "ncu --set full --clock-control none capture %s (tools/ncu_summary.py --json)" % rep}
+    json.dump(js, open(out, "w"), indent=1)
+    print("wrote", out)
