@@ -263,7 +263,7 @@ def decode_batch(blocks, flags=0, gpu=-1, tbs=None, cb_out=True):
         valid = np.full(nt, 0xFFFFFFFF, dtype=np.uint32)
         bs = []
         for i, t in enumerate(tbs):
-            cap = sum(blocks[t["first_cb"] + r]["K"] // 8 for r in range(t["C"])) + 8
+            cap = sum(blocks[j]["K"] // 8 for j in range(t["first_cb"], min(t["first_cb"] + t["C"], n))) + 8
             bb = np.full(cap, 0xA5, dtype=np.uint8)
             bs.append(bb)
             tds[i].first_cb, tds[i].C, tds[i].uplink = t["first_cb"], t["C"], t.get("uplink", 0)
