@@ -197,6 +197,45 @@ int oai_turbo_wait(oai_turbo_batch_t *handle);
  * block stripped when C > 1); one device->host copy per batch carries all transport blocks, so the descriptors of
  * their code blocks may leave decoded_bytes NULL (no per-block copy then).  max_iterations and F are taken from the
  * descriptor of block 0. */
+/* Optional uplink front end of a transport block: the part of ulsch_decoding that builds e[] from the
+ * demodulator's soft bits -- ulsch_decoding.c:600-733 (descrambling with c_init, placeholder handling, channel
+ * de-interleaver), :775-873 (HARQ-ACK / RI soft sums), :877-1002 (CQI soft bits, e fill), :1052-1153 (ACK / RI decisions).
+ * With it, `in` of the transport block's code-block descriptors is ignored (they must have dematch_enable != 0): e stays
+ * on the GPU and block r reads its E soft bits at the running offset of ulsch_decoding.c:1259.
+ * Sizes come from oai_ulsch_control_sizes().  llr holds Hpp*Qm soft bits, column by column of the interleaver matrix, as
+ * rx_ulsch leaves them in lte_eNB_pusch_vars->llr.  Bit-exact to the reference when Hpp*Qm is a multiple of 32 (any
+ * allocation with 12 data symbols); otherwise the reference multiplies its last soft bits by uninitialised stack
+ * (ulsch_decoding.c:605-611 fills whole 32-bit words of the sequence only) and this library continues the sequence. */
+typedef struct {
+  const void *llr;           /* int16_t[Hpp*Qm], or int8_t[Hpp*Qm] with llr_fmt = 1 */
+  uint8_t   llr_fmt;
+  uint32_t  c_init;          /* (rnti<<14) + (subframe<<9) + Nid_cell, ulsch_decoding.c:296 */
+  uint8_t   Qm;              /* 2, 4, 6 */
+  uint8_t   Ncp;             /* 0 normal, 1 extended cyclic prefix (selects the RI / ACK column sets) */
+  uint8_t   O_ACK;           /* 0, 1, 2 */
+  uint8_t   O_RI;            /* 0, 1 */
+  uint8_t   bundling;        /* ulsch->bundling */
+  uint8_t   Nbundled;
+  uint16_t  Cmux;            /* Nsymb_pusch */
+  uint32_t  Qprime_RI, Qprime_ACK, Qprime_CQI, Hprime;   /* oai_ulsch_control_sizes */
+  /* outputs (host memory, each may be NULL) */
+  int16_t  *q_ACK;           /* 18 entries, after the bundling combination of :1059-1092 */
+  int16_t  *q_RI;            /* 6 entries */
+  int8_t   *q_cqi;           /* Qm*Qprime_CQI soft bits for the convolutional decoder (ulsch_harq->q) */
+  uint8_t  *o_ACK;           /* 2 entries */
+  uint8_t  *o_RI;            /* 1 entry */
+} oai_ul_front_t;
+
+/* Control-information sizes of one PUSCH allocation, ulsch_decoding.c:381-468 (host integer rule).  sumKr = sum of the
+ * code-block sizes of the transport block; the beta offsets are the reference's *_times8 values.  G is what remains for
+ * the data (the G of lte_rate_matching_turbo_rx), Hprime = (G + Qm*Qprime_CQI)/Qm, Hpp = Hprime + Qprime_RI.
+ * Returns 0, or -1 when the control information does not fit (:449-452). */
+int oai_ulsch_control_sizes(uint32_t O_RI, uint32_t O_ACK, uint32_t Or1, uint32_t Msc_initial, uint32_t Nsymb_initial,
+                            uint32_t beta_offset_ri_times8, uint32_t beta_offset_harqack_times8, uint32_t beta_offset_cqi_times8,
+                            uint32_t sumKr, uint32_t nb_rb, uint32_t Qm, uint32_t Nsymb_pusch,
+                            uint32_t *Qprime_RI, uint32_t *Qprime_ACK, uint32_t *Qprime_CQI, uint32_t *G, uint32_t *Hprime,
+                            uint32_t *Hpp);
+
 typedef struct {
   uint32_t  first_cb;        /* index of block r = 0 in the cbs array */
   uint32_t  C;               /* 1..16 */
@@ -205,6 +244,7 @@ typedef struct {
   uint8_t  *ret;             /* out (host), may be NULL: the value dlsch_decoding / ulsch_decoding would return */
   uint32_t *valid_bytes;     /* out (host), may be NULL: bytes written to b (the reference's final `offset`) */
   uint8_t   uplink;
+  const oai_ul_front_t *ul_front;   /* NULL: the code blocks bring their own soft bits */
 } oai_tb_desc_t;
 
 /* oai_turbo_submit_batch plus transport-block outputs; wait with oai_turbo_wait. */

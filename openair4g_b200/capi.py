@@ -26,7 +26,7 @@ LIB_PATH = _build.LIB
 
 EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_turbo_decoder16",
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
-           "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_submit_tbs", "oai_turbo_wait",
+           "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_submit_tbs", "oai_turbo_wait", "oai_ulsch_control_sizes",
            "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
            "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
            "oai_turbo_harq_pool_create", "oai_turbo_harq_pool_read", "oai_turbo_harq_pool_destroy",
@@ -48,10 +48,18 @@ class CbDesc(C.Structure):
                 ("in_fmt", C.c_uint8)]
 
 
+class UlFront(C.Structure):
+    """oai_ul_front_t"""
+    _fields_ = [("llr", C.c_void_p), ("llr_fmt", C.c_uint8), ("c_init", C.c_uint32), ("Qm", C.c_uint8), ("Ncp", C.c_uint8),
+                ("O_ACK", C.c_uint8), ("O_RI", C.c_uint8), ("bundling", C.c_uint8), ("Nbundled", C.c_uint8), ("Cmux", C.c_uint16),
+                ("Qprime_RI", C.c_uint32), ("Qprime_ACK", C.c_uint32), ("Qprime_CQI", C.c_uint32), ("Hprime", C.c_uint32),
+                ("q_ACK", C.c_void_p), ("q_RI", C.c_void_p), ("q_cqi", C.c_void_p), ("o_ACK", C.c_void_p), ("o_RI", C.c_void_p)]
+
+
 class TbDesc(C.Structure):
     """oai_tb_desc_t"""
     _fields_ = [("first_cb", C.c_uint32), ("C", C.c_uint32), ("b", C.c_void_p), ("b_capacity", C.c_uint32),
-                ("ret", C.c_void_p), ("valid_bytes", C.c_void_p), ("uplink", C.c_uint8)]
+                ("ret", C.c_void_p), ("valid_bytes", C.c_void_p), ("uplink", C.c_uint8), ("ul_front", C.POINTER(UlFront))]
 
 
 class TxDesc(C.Structure):
@@ -87,6 +95,7 @@ lib.oai_turbo_tx_batch.restype = C.c_int
 lib.oai_turbo_submit_batch.argtypes = [C.POINTER(CbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_submit_tbs.argtypes = [C.POINTER(CbDesc), C.c_int, C.POINTER(TbDesc), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
 lib.oai_turbo_wait.argtypes = [C.c_void_p]
+lib.oai_ulsch_control_sizes.argtypes = [C.c_uint32] * 12 + [C.POINTER(C.c_uint32)] * 6
 lib.oai_lte_segmentation_params.argtypes = [C.c_uint32] + [C.POINTER(C.c_uint32)] * 6
 lib.oai_lte_segmentation_params.restype = C.c_int
 lib.oai_turbo_harq_pool_create.argtypes = [C.c_int, C.c_uint32, C.c_uint16, C.POINTER(C.c_void_p)]
@@ -222,12 +231,12 @@ def decode_batch(blocks, flags=0, gpu=-1, tbs=None, cb_out=True):
     keep, outs = [], []
     status = np.full(n, 255, dtype=np.uint8)
     for i, b in enumerate(blocks):
-        y = np.ascontiguousarray(b["y"], dtype=np.int8 if b.get("in_fmt") else np.int16)
+        y = None if b.get("y") is None else np.ascontiguousarray(b["y"], dtype=np.int8 if b.get("in_fmt") else np.int16)
         out = np.zeros(b["K"] // 8 + 4, dtype=np.uint8)
         keep.append(y)
         outs.append(out)
         d = descs[i]
-        d.in_ = y.ctypes.data
+        d.in_ = None if y is None else y.ctypes.data       # None: the transport block's ul_front supplies the soft bits
         d.decoded_bytes = out.ctypes.data if cb_out else None
         d.status = status.ctypes.data + i
         d.K = b["K"]
@@ -269,6 +278,23 @@ def decode_batch(blocks, flags=0, gpu=-1, tbs=None, cb_out=True):
             tds[i].first_cb, tds[i].C, tds[i].uplink = t["first_cb"], t["C"], t.get("uplink", 0)
             tds[i].b, tds[i].b_capacity = bb.ctypes.data, cap
             tds[i].ret, tds[i].valid_bytes = rets.ctypes.data + i, valid.ctypes.data + 4 * i
+            uf = t.get("ul_front")
+            if uf is not None:           # dict: llr (int16 / int8 array), c_init, Qm, Ncp, O_ACK, O_RI, bundling, Nbundled, Cmux, sizes
+                f = UlFront()
+                llr = np.ascontiguousarray(uf["llr"])
+                assert llr.dtype in (np.int16, np.int8)
+                f.llr, f.llr_fmt = llr.ctypes.data, 1 if llr.dtype == np.int8 else 0
+                for k in ("c_init", "Qm", "Ncp", "O_ACK", "O_RI", "bundling", "Nbundled", "Cmux", "Qprime_RI", "Qprime_ACK",
+                          "Qprime_CQI", "Hprime"):
+                    setattr(f, k, uf.get(k, 0))
+                o = {"q_ACK": np.full(18, 0x7777, dtype=np.int16), "q_RI": np.full(6, 0x7777, dtype=np.int16),
+                     "q_cqi": np.full(max(f.Qm * f.Qprime_CQI, 1), 0x55, dtype=np.int8), "o_ACK": np.full(2, 0xEE, dtype=np.uint8),
+                     "o_RI": np.full(1, 0xEE, dtype=np.uint8)}
+                for k, a in o.items():
+                    setattr(f, k, a.ctypes.data)
+                keep.extend([llr, f, o])
+                uf["out"] = o
+                tds[i].ul_front = C.pointer(f)
         rc = lib.oai_turbo_submit_tbs(descs, n, tds, nt, flags, gpu, C.byref(h))
     if rc != 0:
         raise RuntimeError("oai_turbo_submit_batch failed (%d): %s" % (rc, last_error()))
@@ -280,6 +306,14 @@ def decode_batch(blocks, flags=0, gpu=-1, tbs=None, cb_out=True):
     if tbs is None:
         return res
     return res[0], res[1], [(int(rets[i]), int(valid[i]), bs[i]) for i in range(len(tbs))]
+
+
+def ulsch_control_sizes(O_RI, O_ACK, Or1, Msc_initial, Nsymb_initial, beta_ri_x8, beta_ack_x8, beta_cqi_x8, sumKr, nb_rb, Qm, Nsymb_pusch):
+    """oai_ulsch_control_sizes: returns (rc, dict(Qprime_RI, Qprime_ACK, Qprime_CQI, G, Hprime, Hpp))."""
+    v = [C.c_uint32(0) for _ in range(6)]
+    rc = lib.oai_ulsch_control_sizes(O_RI, O_ACK, Or1, Msc_initial, Nsymb_initial, beta_ri_x8, beta_ack_x8, beta_cqi_x8, sumKr,
+                                     nb_rb, Qm, Nsymb_pusch, *[C.byref(x) for x in v])
+    return rc, dict(zip(("Qprime_RI", "Qprime_ACK", "Qprime_CQI", "G", "Hprime", "Hpp"), [int(x.value) for x in v]))
 
 
 def debug_map16(y, K, term, policy=0):

@@ -22,6 +22,7 @@
 #include "td8_kernels.cuh"
 #include "tx_kernels.cuh"
 #include "tb_kernels.cuh"
+#include "ul_kernels.cuh"
 
 namespace oai {
 
@@ -675,6 +676,49 @@ struct HostBatch {
   uint8_t* d_tbpool = nullptr; uint8_t* h_tbpool = nullptr;
   int cap_tb = 0, cap_tbblk = 0; size_t cap_tbpool = 0;
   bool want_cb_out = true;         // some descriptor has decoded_bytes != NULL
+  // uplink front end (oai_ul_front_t): soft bits of the allocations -> e[] on the device
+  std::vector<UlFrontDev> ulf;
+  std::vector<int> ulf_tb;         // transport-block index of each entry
+  std::vector<oai_ul_front_t> ulf_desc;
+  UlFrontDev* d_ulf = nullptr; UlFrontOut* d_ulfout = nullptr; UlFrontOut* h_ulfout = nullptr;
+  uint8_t* d_llr = nullptr; uint8_t* h_llr = nullptr; int8_t* d_cqi = nullptr; int8_t* h_cqi = nullptr;
+  int cap_ulf = 0; size_t cap_llr = 0, cap_h_llr = 0, cap_cqi = 0, cqi_bytes = 0;
+  int ensure_ulf(int n, size_t llr_bytes, size_t cqi_b) {
+    if (n > cap_ulf) {
+      if (d_ulf) cudaFree(d_ulf);
+      if (d_ulfout) cudaFree(d_ulfout);
+      if (h_ulfout) cudaFreeHost(h_ulfout);
+      d_ulf = nullptr; d_ulfout = nullptr; h_ulfout = nullptr; cap_ulf = 0;
+      CU(cudaMalloc(&d_ulf, sizeof(UlFrontDev) * n));
+      CU(cudaMalloc(&d_ulfout, sizeof(UlFrontOut) * n));
+      CU(cudaMallocHost(&h_ulfout, sizeof(UlFrontOut) * n));
+      cap_ulf = n;
+    }
+    if (llr_bytes > cap_llr) {
+      if (d_llr) cudaFree(d_llr);
+      d_llr = nullptr; cap_llr = 0;
+      CU(cudaMalloc(&d_llr, llr_bytes));
+      cap_llr = llr_bytes;
+    }
+    if (cqi_b > cap_cqi) {
+      if (d_cqi) cudaFree(d_cqi);
+      if (h_cqi) cudaFreeHost(h_cqi);
+      d_cqi = nullptr; h_cqi = nullptr; cap_cqi = 0;
+      CU(cudaMalloc(&d_cqi, cqi_b));
+      CU(cudaMallocHost(&h_cqi, cqi_b));
+      cap_cqi = cqi_b;
+    }
+    return 0;
+  }
+  int ensure_stage_llr() {
+    if (cap_h_llr < cap_llr) {
+      if (h_llr) cudaFreeHost(h_llr);
+      h_llr = nullptr; cap_h_llr = 0;
+      CU(cudaMallocHost(&h_llr, cap_llr));
+      cap_h_llr = cap_llr;
+    }
+    return 0;
+  }
   int ensure_tb(int ntb, int nblk, size_t pool_bytes) {
     if (ntb > cap_tb) {
       if (d_tbmeta) cudaFree(d_tbmeta);
@@ -822,6 +866,15 @@ struct HostBatch {
     if (h_tbpool) cudaFreeHost(h_tbpool);
     d_tbmeta = nullptr; d_tbres = nullptr; h_tbres = nullptr; d_tbblk = nullptr; d_tbpool = nullptr; h_tbpool = nullptr;
     cap_tb = cap_tbblk = 0; cap_tbpool = 0;
+    if (d_ulf) cudaFree(d_ulf);
+    if (d_ulfout) cudaFree(d_ulfout);
+    if (h_ulfout) cudaFreeHost(h_ulfout);
+    if (d_llr) cudaFree(d_llr);
+    if (h_llr) cudaFreeHost(h_llr);
+    if (d_cqi) cudaFree(d_cqi);
+    if (h_cqi) cudaFreeHost(h_cqi);
+    d_ulf = nullptr; d_ulfout = nullptr; h_ulfout = nullptr; d_llr = nullptr; h_llr = nullptr; d_cqi = nullptr; h_cqi = nullptr;
+    cap_ulf = 0; cap_llr = cap_h_llr = cap_cqi = 0;
     cap_e = cap_w = 0; cap_rm = 0;
     if (h_in) { cudaFreeHost(h_in); h_in = nullptr; }
     if (d_in) { cudaFree(d_in); d_in = nullptr; }
@@ -852,6 +905,46 @@ struct HostBatch {
         return fail(-4, "transport block %d: code blocks [%u, %u) are not inside the descriptor array / C > 16", i, t.first_cb, t.first_cb + t.C);
     }
     if (ntb > 0) tbs.assign(tb_in, tb_in + ntb);
+    // uplink front ends: descriptor index -> (entry, running soft-bit offset inside the allocation's e[])
+    ulf.clear(); ulf_tb.clear(); ulf_desc.clear();
+    std::vector<int> ul_of(ncb, -1);
+    std::vector<uint32_t> ul_roff(ncb, 0);
+    size_t ul_e_hw = 0, ul_llr_b = 0, ul_cqi_b = 0;
+    for (int i = 0; i < ntb; ++i) {
+      const oai_tb_desc_t& t = tbs[i];
+      if (!t.ul_front) continue;
+      const oai_ul_front_t& f = *t.ul_front;
+      if (!f.llr || (f.Qm != 2 && f.Qm != 4 && f.Qm != 6) || f.Cmux == 0 || f.O_ACK > 2 || f.O_RI > 1 || f.llr_fmt > 1 ||
+          f.Hprime < f.Qprime_CQI || (f.Hprime + f.Qprime_RI) % f.Cmux)
+        return fail(-4, "transport block %d: invalid uplink front-end parameters (ulsch_decoding returns -1 for O_ACK > 2 / O_RI > 1)", i);
+      UlFrontDev u;
+      memset(&u, 0, sizeof(u));
+      const uint32_t Hpp = f.Hprime + f.Qprime_RI;
+      u.llr_off_lo = (uint32_t)(ul_llr_b & 0xffffffffu); u.llr_off_hi = (uint32_t)((unsigned long long)ul_llr_b >> 32);
+      u.llr_fmt = f.llr_fmt;
+      u.e_off_lo = (uint32_t)(ul_e_hw & 0xffffffffu); u.e_off_hi = (uint32_t)((unsigned long long)ul_e_hw >> 32);
+      u.Qm = f.Qm; u.Cmux = f.Cmux; u.Rp = Hpp / f.Cmux;
+      u.Qprime_RI = f.Qprime_RI; u.Qprime_ACK = f.Qprime_ACK; u.Qprime_CQI = f.Qprime_CQI; u.Hprime = f.Hprime;
+      u.Ncp = f.Ncp; u.O_ACK = f.O_ACK; u.O_RI = f.O_RI; u.bundling = f.bundling; u.Nbundled = f.Nbundled;
+      u.cqi_off = (uint32_t)ul_cqi_b;
+      const uint32_t G = (f.Hprime - f.Qprime_CQI) * f.Qm;          // data soft bits: the G of lte_rate_matching_turbo_rx
+      uint32_t roff = 0;
+      for (uint32_t r = 0; r < t.C; ++r) {
+        const oai_cb_desc_t& d = descs[t.first_cb + r];
+        RmParams q;
+        if (!d.dematch_enable || d.G != G || rm_params(d.K, d.G, d.C, d.Nsoft, d.Mdlharq, d.Kmimo, d.rvidx, d.Qm, d.Nl, d.r, 0, &q))
+          return fail(-4, "transport block %d, block %u: with ul_front every block needs dematch_enable and G = (Hprime - Qprime_CQI) * Qm = %u", i, r, G);
+        ul_of[t.first_cb + r] = (int)ulf.size();
+        ul_roff[t.first_cb + r] = roff;
+        roff += q.E;
+      }
+      if (roff > G) return fail(-4, "transport block %d: its blocks consume %u soft bits, the allocation carries %u", i, roff, G);
+      ul_e_hw += ((size_t)G + 7) & ~(size_t)7;
+      ul_llr_b += (((size_t)Hpp * f.Qm * (f.llr_fmt ? 1 : 2)) + 15) & ~(size_t)15;
+      ul_cqi_b += (((size_t)f.Qprime_CQI * f.Qm) + 15) & ~(size_t)15;
+      ulf.push_back(u); ulf_tb.push_back(i); ulf_desc.push_back(f);
+    }
+    cqi_bytes = ul_cqi_b;
     static const bool trace = getenv("OAI_TURBO_TRACE") != nullptr;
     // handles are recycled: nothing of the previous batch may survive an early return below (wait() walks these)
     order.clear(); rm.clear(); rm_desc.clear(); gseq.clear(); direct_out = false;
@@ -877,7 +970,7 @@ struct HostBatch {
     const int n = (int)order.size();
     if (n == 0) {                                            // no block reaches the GPU: every transport block has failed
       for (auto& t : tbs) { if (t.ret) *t.ret = (uint8_t)(1 + descs[t.first_cb].max_iterations); if (t.valid_bytes) *t.valid_bytes = 0; }
-      tbs.clear();
+      tbs.clear(); ulf.clear(); ulf_desc.clear();
       return 0;
     }
     n16 = 0;
@@ -955,7 +1048,8 @@ struct HostBatch {
       }
     }
     std::vector<CbMeta> meta(n);
-    size_t e_hw = 0, w_hw = 0, e_bytes_run = 0;
+    size_t e_hw = ul_e_hw, w_hw = 0, e_bytes_run = 0;       // the allocations' e[] regions come first in the pool
+    std::vector<char> rm_nocopy;                              // per rm block: soft bits come from k_ul_front
     oai_turbo_harq_pool* pool = nullptr;
     const char* prev_e_end = nullptr;
     std::unordered_map<uint32_t, int> seq_of;                // c_init -> index in gseq
@@ -987,12 +1081,23 @@ struct HostBatch {
         // (int8 soft bits, in_fmt 1: a run must start on an int16 boundary of the pool, so only even-length predecessors
         // continue a run -- E is a multiple of Qm*Nl, odd only for odd Nl*Qm, which LTE does not have)
         rb.e_fmt = d.in_fmt ? 1u : 0u;
-        const size_t e_bytes = d.in_fmt ? (size_t)q.E : 2 * (size_t)q.E;
-        const bool cont = !rm.empty() && (const char*)d.in == prev_e_end && rm.back().e_fmt == rb.e_fmt && !(e_bytes_run & 1);
+        const bool from_ul = ul_of[order[i]] >= 0;          // e[] is produced on the device by k_ul_front: nothing to copy
+        const size_t e_bytes = from_ul ? 0 : (d.in_fmt ? (size_t)q.E : 2 * (size_t)q.E);
+        if (from_ul) {
+          const UlFrontDev& u = ulf[ul_of[order[i]]];
+          const size_t eo = ((((size_t)u.e_off_hi) << 32) | u.e_off_lo) + ul_roff[order[i]];
+          rb.e_fmt = 0;
+          rb.e_off_lo = (uint32_t)(eo & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)eo >> 32);
+          prev_e_end = nullptr;
+        } else {
+        if (!d.in) return fail(-4, "block %d: null input pointer", order[i]);
+        const bool cont = !rm.empty() && !rm_nocopy.back() && (const char*)d.in == prev_e_end && rm.back().e_fmt == rb.e_fmt && !(e_bytes_run & 1);
         if (!cont) { e_hw = (e_hw + 7) & ~(size_t)7; e_bytes_run = 0; }
         prev_e_end = (const char*)d.in + e_bytes;
         e_bytes_run += e_bytes;
         rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
+        }
+        rm_nocopy.push_back(from_ul);
         rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
         e_hw += (e_bytes + 1) >> 1;
@@ -1012,13 +1117,14 @@ struct HostBatch {
     // soft bits of rm blocks [jlo, jhi): one copy per run that is contiguous in the caller's memory, staged only if pageable
     auto copy_e_runs = [&](size_t jlo, size_t jhi, cudaStream_t cs) -> int {
       for (size_t j = jlo; j < jhi;) {
+        if (rm_nocopy[j]) { ++j; continue; }
         const oai_cb_desc_t& d0 = descs[rm_desc[j]];
         const size_t eo = ((size_t)rm[j].e_off_hi << 32) | rm[j].e_off_lo;
         // lengths in bytes; a block continues the run when it follows in the caller's memory AND in the device pool
         auto nbytes = [&](size_t x) -> size_t { return rm[x].e_fmt ? (size_t)rm[x].E : 2 * (size_t)rm[x].E; };
         auto eoff = [&](size_t x) -> size_t { return 2 * (((size_t)rm[x].e_off_hi << 32) | rm[x].e_off_lo); };
         size_t len = nbytes(j), k = j + 1;
-        while (k < jhi && (const char*)descs[rm_desc[k]].in == (const char*)d0.in + len && eoff(k) == 2 * eo + len) { len += nbytes(k); ++k; }
+        while (k < jhi && !rm_nocopy[k] && (const char*)descs[rm_desc[k]].in == (const char*)d0.in + len && eoff(k) == 2 * eo + len) { len += nbytes(k); ++k; }
         cudaPointerAttributes at;
         const bool pinned = (cudaPointerGetAttributes(&at, d0.in) == cudaSuccess) && at.type == cudaMemoryTypeHost;
         cudaGetLastError();
@@ -1043,15 +1149,45 @@ struct HostBatch {
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
       if (rc) return rc;
+      std::vector<int> ulf_seq(ulf.size());
+      for (size_t u = 0; u < ulf.size(); ++u) {              // one sequence per uplink allocation (whole words, + 1 for a tail)
+        ulf_seq[u] = (int)gseq.size();
+        gseq.push_back(GoldSeq{ulf_desc[u].c_init, 0u, ulf[u].Rp * ulf[u].Cmux * ulf[u].Qm / 32 + 1});
+      }
       if (!gseq.empty()) {                                   // scrambling sequences of the codewords of this batch
         uint32_t words = 0;
         for (auto& g : gseq) { g.off = words; words += g.nwords; }
         for (size_t j = 0; j < rm.size(); ++j) if (rm_seq[j] >= 0) rm[j].gold_off = gseq[rm_seq[j]].off;
+        for (size_t u = 0; u < ulf.size(); ++u) ulf[u].gold_off = gseq[ulf_seq[u]].off;
         if ((int)gseq.size() > cap_gseq) { if (d_gseq) cudaFree(d_gseq); cap_gseq = (int)gseq.size(); CU(cudaMalloc(&d_gseq, sizeof(GoldSeq) * cap_gseq)); }
         if (words > cap_gold) { if (d_gold) cudaFree(d_gold); cap_gold = words; CU(cudaMalloc(&d_gold, sizeof(uint32_t) * cap_gold)); }
         CU(cudaMemcpyAsync(d_gseq, gseq.data(), sizeof(GoldSeq) * gseq.size(), cudaMemcpyHostToDevice, st));
         k_gold<<<((int)gseq.size() + 63) / 64, 64, 0, st>>>(d_gseq, (int)gseq.size(), d_gold);
         ++g_launches;
+      }
+      if (!ulf.empty()) {
+        // uplink front ends: the allocations' soft bits go over, k_ul_front leaves e[] in the batch's soft-bit pool
+        rc = ensure_ulf((int)ulf.size(), ul_llr_b, std::max<size_t>(ul_cqi_b, 16));
+        if (rc) return rc;
+        for (size_t u = 0; u < ulf.size(); ++u) {
+          const size_t off = ((size_t)ulf[u].llr_off_hi << 32) | ulf[u].llr_off_lo;
+          const size_t nb = (size_t)ulf[u].Rp * ulf[u].Cmux * ulf[u].Qm * (ulf[u].llr_fmt ? 1 : 2);
+          cudaPointerAttributes at;
+          const bool pinned = (cudaPointerGetAttributes(&at, ulf_desc[u].llr) == cudaSuccess) && at.type == cudaMemoryTypeHost;
+          cudaGetLastError();
+          const void* src = ulf_desc[u].llr;
+          if (!pinned) {
+            rc = ensure_stage_llr();
+            if (rc) return rc;
+            memcpy(h_llr + off, ulf_desc[u].llr, nb); src = h_llr + off;
+          }
+          CU(cudaMemcpyAsync(d_llr + off, src, nb, cudaMemcpyHostToDevice, st));
+        }
+        CU(cudaMemcpyAsync(d_ulf, ulf.data(), sizeof(UlFrontDev) * ulf.size(), cudaMemcpyHostToDevice, st));
+        k_ul_front<<<(int)ulf.size(), ULF_THREADS, 0, st>>>(d_ulf, (int)ulf.size(), d_llr, d_e, d_gold, d_cqi, d_ulfout);
+        ++g_launches;
+        CU(cudaMemcpyAsync(h_ulfout, d_ulfout, sizeof(UlFrontOut) * ulf.size(), cudaMemcpyDeviceToHost, st));
+        if (ul_cqi_b) CU(cudaMemcpyAsync(h_cqi, d_cqi, ul_cqi_b, cudaMemcpyDeviceToHost, st));
       }
       CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
       if (!fe_parts) {
@@ -1193,6 +1329,15 @@ struct HostBatch {
     for (size_t j = 0; j < rm.size(); ++j) {                     // HARQ buffers back to their owners
       const oai_cb_desc_t& d = descs[rm_desc[j]];
       if (d.w && !rm[j].w_sel) memcpy(d.w, h_w + rm[j].w_off, sizeof(int16_t) * rm[j].Ncb);
+    }
+    for (size_t u = 0; u < ulf.size(); ++u) {                   // control information of the uplink allocations
+      const oai_ul_front_t& f = ulf_desc[u];
+      const UlFrontOut& o = h_ulfout[u];
+      if (f.q_ACK) memcpy(f.q_ACK, o.q_ACK, sizeof(o.q_ACK));
+      if (f.q_RI) memcpy(f.q_RI, o.q_RI, sizeof(o.q_RI));
+      if (f.o_ACK) memcpy(f.o_ACK, o.o_ACK, 2);
+      if (f.o_RI) f.o_RI[0] = o.o_RI;
+      if (f.q_cqi && f.Qprime_CQI) memcpy(f.q_cqi, h_cqi + ulf[u].cqi_off, (size_t)f.Qprime_CQI * f.Qm);
     }
     for (size_t i = 0; i < tbs.size(); ++i) {                   // transport blocks assembled on the device
       const oai_tb_desc_t& t = tbs[i];
@@ -1381,6 +1526,32 @@ int oai_lte_segmentation_params(uint32_t B, uint32_t* C, uint32_t* Cplus, uint32
     *Cplus = *C - *Cminus;
   }
   *F = (*Cplus) * (*Kplus) + (*Cminus) * (*Kminus) - Bp;
+  return 0;
+}
+
+// ulsch_decoding.c:381-468
+int oai_ulsch_control_sizes(uint32_t O_RI, uint32_t O_ACK, uint32_t Or1, uint32_t Msc_initial, uint32_t Nsymb_initial,
+                            uint32_t beta_ri_x8, uint32_t beta_ack_x8, uint32_t beta_cqi_x8, uint32_t sumKr, uint32_t nb_rb,
+                            uint32_t Qm, uint32_t Nsymb_pusch, uint32_t* Qprime_RI, uint32_t* Qprime_ACK, uint32_t* Qprime_CQI,
+                            uint32_t* G, uint32_t* Hprime, uint32_t* Hpp) {
+  if (!Qprime_RI || !Qprime_ACK || !Qprime_CQI || !G || !Hprime || !Hpp || sumKr == 0 || Qm == 0) return fail(-1, "bad arguments");
+  auto coded_symbols = [&](uint32_t payload_bits, uint32_t beta_x8, bool capped) -> uint32_t {       // :381-431
+    uint32_t q = payload_bits * Msc_initial * Nsymb_initial * beta_x8;
+    if (q == 0) return 0;
+    q = (q % (8 * sumKr)) ? 1 + q / (8 * sumKr) : q / (8 * sumKr);
+    return (capped && q > 4 * nb_rb * 12) ? 4 * nb_rb * 12 : q;
+  };
+  const uint32_t Gtot = nb_rb * (12 * Qm) * Nsymb_pusch;
+  *Qprime_RI = coded_symbols(O_RI, beta_ri_x8, true);
+  *Qprime_ACK = coded_symbols(O_ACK, beta_ack_x8, true);
+  uint32_t qc = Or1 ? coded_symbols(Or1 + (Or1 < 12 ? 0 : 8), beta_cqi_x8, false) : 0;
+  if (qc > Gtot - O_RI) qc = Gtot - O_RI;                                   // :438-439, as written there
+  *Qprime_CQI = qc;
+  const uint32_t g = Gtot - Qm * (*Qprime_RI) - Qm * qc;                      // :447
+  if ((int32_t)g < 0) return -1;                                              // :449-452
+  *G = g;
+  *Hprime = (g + Qm * qc) / Qm;
+  *Hpp = *Hprime + *Qprime_RI;
   return 0;
 }
 

@@ -77,16 +77,60 @@ def demap_maxlog(sym, Qm, n0, llr_scale):
     return np.clip(llr, -32768, 32767).astype(np.int16)
 
 
+CS_RI = ((1, 4, 7, 10), (0, 3, 5, 8))          # 36.212 table 5.2.2.8-1: RI columns, normal / extended cyclic prefix
+
+
+def ul_multiplex(e, ctrl, sizes, Qm, c_init, rng, Cmux=12, Ncp=0):
+    """Transmit-side mirror of the uplink front end (36.212 5.2.2.7-8 + 36.211 5.3.1 as the reference's receiver reads
+    them, ulsch_decoding.c:600-1002): the data soft bits e (G values) are placed into the channel interleaver matrix behind
+    the CQI symbols, `ctrl` soft values fill the CQI / RI / HARQ-ACK positions, and the matrix is read out column by column
+    and scrambled -- the soft bits a demodulator would leave in lte_eNB_pusch_vars->llr.  Returns int16[Hpp*Qm]."""
+    Hprime, Qri, Qcqi = sizes["Hprime"], sizes["Qprime_RI"], sizes["Qprime_CQI"]
+    nsym = Hprime + Qri
+    Rp = nsym // Cmux
+    cs = CS_RI[1 if Ncp else 0]
+
+    def is_ri(sym):
+        r, col = divmod(sym, Cmux)
+        if col not in cs:
+            return False
+        return 4 * (Rp - 1 - r) + ((4 - cs.index(col)) & 3) < Qri
+    L = 0
+    while L < nsym and is_ri(L):
+        L += 1
+    y = np.array(ctrl, dtype=np.int64).reshape(nsym, Qm).copy()
+    y[L + Qcqi:L + Hprime] = np.asarray(e, dtype=np.int64).reshape(-1, Qm)
+    sign = 2 * tx.gold_sequence(c_init, nsym * Qm).astype(np.int64).reshape(nsym, Qm) - 1     # by input symbol col*Rp + r
+    sym = np.arange(nsym)
+    src = (sym % Cmux) * Rp + sym // Cmux
+    llr = np.zeros((nsym, Qm), dtype=np.int64)
+    llr[src] = y * sign[src]
+    return np.clip(llr.reshape(-1), -32767, 32767).astype(np.int16)
+
+
 class LinkSim:
-    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1, gpu_tx=False):
-        """gpu_tx: encode / interleave / rate-match on the GPU (oai_turbo_tx_batch) instead of the numpy TX chain."""
+    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1, gpu_tx=False, ul_front=None):
+        """gpu_tx: encode / interleave / rate-match on the GPU (oai_turbo_tx_batch) instead of the numpy TX chain.
+        ul_front (uplink only): dict(O_ACK, O_RI, Or1) -- every subframe carries that control information, the harness
+        hands the GPU the multiplexed, scrambled soft bits of the whole allocation (oai_ul_front_t) and the transport
+        block comes back assembled (oai_turbo_submit_tbs)."""
         self.cfg, self.max_it, self.llr8, self.scale, self.gpu_tx = cfg, max_iterations, llr8, llr_scale, gpu_tx
+        self.ul_front = ul_front
         self.rng = np.random.default_rng(seed)
         B = cfg.tbs + 24
         self.C, self.Cp, self.Cm, self.Kp, self.Km, self.F = tx.segmentation(B)
         assert self.Cm == 0, "mixed segment sizes are not exercised by the BASELINE shapes"
         self.K = self.Kp
         self.crc_type = 0 if self.C == 1 else 1
+        self.G = cfg.G                                   # soft bits left for the data
+        if ul_front is not None:
+            assert not cfg.downlink
+            from .. import capi
+            nb_rb = cfg.G // (144 * cfg.Qm)
+            rc, self.ul_sizes = capi.ulsch_control_sizes(ul_front.get("O_RI", 0), ul_front.get("O_ACK", 0), ul_front.get("Or1", 0),
+                                                         12 * nb_rb, 12, 40, 40, 16, self.C * self.K, nb_rb, cfg.Qm, 12)
+            assert rc == 0
+            self.G = self.ul_sizes["G"]
 
     # ---- transmit n transport blocks; returns code blocks (n, C, K) and the coded bits (n*C, 3K+12) ----
     def make_blocks(self, n):
@@ -123,7 +167,7 @@ class LinkSim:
             from .. import capi
             packed = np.packbits(d, axis=2)
             sent = capi.tx_batch([{"c": packed[i, r], "K": self.K, "F": self.F if r == 0 else 0, "filler_null": 1,
-                                   "G": cfg.G, "C": self.C, "r": r, "rvidx": rv, "Qm": cfg.Qm, "Nl": cfg.Nl,
+                                   "G": self.G, "C": self.C, "r": r, "rvidx": rv, "Qm": cfg.Qm, "Nl": cfg.Nl,
                                    "Mdlharq": cfg.Mdlharq, "Kmimo": cfg.Kmimo}
                                   for r in range(self.C) for i in range(d.shape[0])])
         for r in range(self.C):
@@ -131,7 +175,7 @@ class LinkSim:
                 bits = np.stack(sent[r * d.shape[0]:(r + 1) * d.shape[0]])
                 E = bits.shape[1]
             else:
-                bits, E = tx.rate_match(d[:, r], self.K, self.F if r == 0 else 0, cfg.G, self.C, cfg.Qm, cfg.Nl, r, rv,
+                bits, E = tx.rate_match(d[:, r], self.K, self.F if r == 0 else 0, self.G, self.C, cfg.Qm, cfg.Nl, r, rv,
                                         cfg.Mdlharq, cfg.Kmimo)
             if cfg.downlink:
                 bits = bits ^ c[None, off:off + E]
@@ -157,7 +201,7 @@ class LinkSim:
         w = np.zeros((n_subframes, C, 3 * Kpi), dtype=np.int16)                # caller-owned HARQ buffers
         alive = np.ones(n_subframes, dtype=bool)
         res = {"snr_db": snr_db, "tb_err": [], "cb_err": [], "iters": np.zeros(self.max_it + 2, dtype=np.int64),
-               "gpu_s": 0.0, "decoded_info_bits": 0, "mismatch_vs_tx": 0}
+               "gpu_s": 0.0, "decoded_info_bits": 0, "mismatch_vs_tx": 0, "iters_failed": 0}
         want = np.packbits(cb, axis=2)
         for rnd in range(max_rounds):
             idx = np.nonzero(alive)[0]
@@ -166,22 +210,40 @@ class LinkSim:
                 res["cb_err"].append(0)
                 continue
             es, offs = self.transmit(d[idx], RV_SEQ[rnd % 4], snr_db)
-            blocks = []
+            blocks, tbs = [], None
+            if self.ul_front is not None:
+                # the whole allocation's soft bits, multiplexed with control positions and scrambled, go to the GPU
+                tbs = []
+                z, uf = self.ul_sizes, self.ul_front
+                for ii, sf in enumerate(idx):
+                    nbits = (z["Hprime"] + z["Qprime_RI"]) * cfg.Qm
+                    ctrl = self.rng.integers(-24, 25, size=nbits)
+                    llr = ul_multiplex(np.concatenate([es[r][ii] for r in range(C)]), ctrl, z, cfg.Qm, cfg.c_init, self.rng)
+                    tbs.append({"first_cb": ii * C, "C": C, "uplink": 1,
+                                "ul_front": {"llr": llr, "c_init": cfg.c_init, "Qm": cfg.Qm, "Ncp": 0, "O_ACK": uf.get("O_ACK", 0),
+                                             "O_RI": uf.get("O_RI", 0), "bundling": 0, "Nbundled": 1, "Cmux": 12,
+                                             "Qprime_RI": z["Qprime_RI"], "Qprime_ACK": z["Qprime_ACK"],
+                                             "Qprime_CQI": z["Qprime_CQI"], "Hprime": z["Hprime"]}})
             for ii, sf in enumerate(idx):
                 for r in range(C):
-                    blocks.append({"y": np.ascontiguousarray(es[r][ii]), "K": K, "max_iterations": self.max_it,
+                    blocks.append({"y": None if tbs is not None else np.ascontiguousarray(es[r][ii]), "K": K, "max_iterations": self.max_it,
                                    "crc_type": self.crc_type, "F": self.F if r == 0 else 0, "llr8": self.llr8,
                                    "tb_id": int(sf),
-                                   "dematch": {"G": cfg.G, "C": C, "r": r, "rvidx": RV_SEQ[rnd % 4], "clear": 1 if rnd == 0 else 0,
+                                   "dematch": {"G": self.G, "C": C, "r": r, "rvidx": RV_SEQ[rnd % 4], "clear": 1 if rnd == 0 else 0,
                                                "Qm": cfg.Qm, "Nl": cfg.Nl, "Mdlharq": cfg.Mdlharq, "Kmimo": cfg.Kmimo,
                                                "w": w[sf, r],
                                                "scr_c_init": cfg.c_init if cfg.downlink else None, "scr_offset": offs[r]}})
             t0 = time.perf_counter()
-            outs, status = capi.decode_batch(blocks, flags=capi.BATCH_DL_STOP_AFTER_FAILURE if cfg.downlink else 0)
+            if tbs is None:
+                outs, status = capi.decode_batch(blocks, flags=capi.BATCH_DL_STOP_AFTER_FAILURE if cfg.downlink else 0)
+            else:
+                outs, status, tbo = capi.decode_batch(blocks, tbs=tbs)
+                res.setdefault("tb_results", []).append([(t[0], t[1]) for t in tbo])
             res["gpu_s"] += time.perf_counter() - t0
             st = np.array(status).reshape(idx.size, C)
             ok_cb = (st <= self.max_it)                                         # 0xFE (not decoded) counts as failed
             ok_tb = ok_cb.all(axis=1)
+            res["iters_failed"] += int((st == self.max_it + 1).sum())
             for ii, sf in enumerate(idx):
                 for r in range(C):
                     if ok_cb[ii, r]:
@@ -194,7 +256,11 @@ class LinkSim:
             alive[idx[ok_tb]] = False
         res["bler_round0"] = res["tb_err"][0] / n_subframes
         res["residual_bler"] = int(alive.sum()) / n_subframes
-        res["avg_iterations"] = float((res["iters"] * np.arange(res["iters"].size)).sum() / max(res["iters"].sum(), 1))
+        # mean iterations over every block that was decoded: a block whose CRC never passed ran max_iterations
+        # (blocks skipped by the downlink stop-after-failure rule ran none and are not counted); None without a decode
+        res["iters"][self.max_it] += res["iters_failed"]
+        res["avg_iterations"] = (float((res["iters"] * np.arange(res["iters"].size)).sum() / res["iters"].sum())
+                                 if res["iters"].sum() else None)
         return res
 
 

@@ -80,8 +80,54 @@ def port():
     L.orc_turbo_decoder16_batch.argtypes = [i16p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_uint16,
                                             C.c_uint8, C.c_uint8, C.c_int]
     L.orc_turbo_decoder16_batch.restype = None
+    L.orc_ulsch_control_sizes.argtypes = [C.c_uint32] * 12 + [C.POINTER(UlSizes)]
+    L.orc_ulsch_front.argtypes = [i16p, C.c_uint32, C.c_uint32, C.POINTER(UlSizes)] + [C.c_uint32] * 5 + \
+        [i16p, i16p, i16p, np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS"), u8p, u8p]
     _port = L
     return L
+
+
+class UlSizes(C.Structure):
+    """orc_ul_sizes_t"""
+    _fields_ = [(k, C.c_uint32) for k in ("Qprime_RI", "Qprime_ACK", "Qprime_CQI", "Q_RI", "Q_CQI", "G", "H", "Hprime", "Hpp",
+                                          "Cmux", "Rmux_prime")]
+
+
+class RefUlParams(C.Structure):
+    """ref_ul_params_t of oracle/ref_tu/ulfront_tu.c"""
+    _fields_ = [(k, C.c_uint32) for k in ("TBS", "nb_rb", "Nsymb_pusch", "Nsymb_initial", "Msc_initial", "mcs", "rvidx", "round",
+                                          "O_ACK", "O_RI", "Or1", "bundling", "Nbundled", "Ncp", "beta_cqi_x8", "beta_ri_x8",
+                                          "beta_ack_x8", "rnti", "subframe", "Nid_cell", "max_iter", "Mdlharq", "llr8")]
+
+
+def ref_ulsch_decoding(params, llr, state=None):
+    """Runs the UNMODIFIED reference ulsch_decoding() (compiled behind oracle/ref_tu/shim4) on one subframe's soft bits.
+    params: dict of RefUlParams fields; state: the opaque HARQ state of a previous round (or None).
+    Returns dict(ret, e, q_ACK, q_RI, q_cqi, o_ACK, o_RI, c (16x768), b, w (16 x 18624), state)."""
+    L = ref()
+    L.ref_ul_state_size.restype = C.c_size_t
+    L.ref_ulsch_decoding_run.restype = C.c_uint
+    L.ref_ulsch_decoding_run.argtypes = [C.POINTER(RefUlParams)] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + \
+        [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    if state is None:
+        state = np.zeros(L.ref_ul_state_size() + 64, dtype=np.uint8)
+    p = RefUlParams()
+    for k, v in params.items():
+        setattr(p, k, v)
+    ll = aligned(llr.size + 64, np.int16)
+    ll[:llr.size] = llr
+    e = np.zeros(14 * 1200 * 6, dtype=np.int16)
+    q_ack, q_ri = np.zeros(18, dtype=np.int16), np.zeros(6, dtype=np.int16)
+    q_cqi = np.zeros(2560, dtype=np.int8)
+    o_ack, o_ri = np.zeros(4, dtype=np.uint8), np.zeros(2, dtype=np.uint8)
+    c = np.zeros((16, 768), dtype=np.uint8)
+    b = np.zeros(16 * 768, dtype=np.uint8)
+    w = np.zeros((16, 3 * (6144 + 64)), dtype=np.int16)
+    ret = L.ref_ulsch_decoding_run(C.byref(p), state.ctypes.data, ll.ctypes.data, e.ctypes.data, e.size, q_ack.ctypes.data,
+                                   q_ri.ctypes.data, q_cqi.ctypes.data, q_cqi.size, o_ack.ctypes.data, o_ri.ctypes.data,
+                                   c.ctypes.data, b.ctypes.data, b.size, w.ctypes.data)
+    return {"ret": int(ret), "e": e, "q_ACK": q_ack, "q_RI": q_ri, "q_cqi": q_cqi, "o_ACK": o_ack, "o_RI": o_ri, "c": c, "b": b,
+            "w": w, "state": state}
 
 
 def ref():

@@ -83,4 +83,14 @@ uint32_t orc_lte_gold_generic(uint32_t *x1, uint32_t *x2, uint8_t reset);
 void orc_gold_words(uint32_t c_init, uint32_t *words, int nwords);
 void orc_dlsch_unscrambling(uint32_t c_init, int16_t *llr, int n);
 
+/* Uplink front end (LTE_TRANSPORT/ulsch_decoding.c:381-1153): control sizes, descrambling + channel de-interleaver,
+ * ACK / RI / CQI extraction, e fill, ACK / RI decisions */
+typedef struct { uint32_t Qprime_RI, Qprime_ACK, Qprime_CQI, Q_RI, Q_CQI, G, H, Hprime, Hpp, Cmux, Rmux_prime; } orc_ul_sizes_t;
+int orc_ulsch_control_sizes(uint32_t O_RI, uint32_t O_ACK, uint32_t Or1, uint32_t Msc_initial, uint32_t Nsymb_initial,
+                            uint32_t beta_ri_x8, uint32_t beta_ack_x8, uint32_t beta_cqi_x8, uint32_t sumKr, uint32_t nb_rb,
+                            uint32_t Qm, uint32_t Nsymb_pusch, orc_ul_sizes_t *o);
+int orc_ulsch_front(const int16_t *llr, uint32_t c_init, uint32_t Qm, const orc_ul_sizes_t *z, uint32_t Ncp, uint32_t O_ACK,
+                    uint32_t O_RI, uint32_t bundling, uint32_t Nbundled, int16_t *e, int16_t *q_ACK, int16_t *q_RI,
+                    int8_t *q_cqi, uint8_t *o_ACK, uint8_t *o_RI);
+
 #endif

@@ -128,3 +128,65 @@ def test_gpu_tx_switch_gives_identical_runs(capi):
             assert all(np.array_equal(x["y"], y["y"]) for x, y in zip(ca[0], cb[0]))
             assert all(np.array_equal(x, y) for x, y in zip(ca[2], cb[2]))
             assert all(np.array_equal(x, y) for x, y in zip(ca[3], cb[3]))
+
+
+def test_ulsim_through_the_uplink_front_end(capi):
+    """LinkSim(ul_front=...): every subframe reaches the GPU as the multiplexed, scrambled soft bits of the whole PUSCH
+    allocation (HARQ-ACK + RI + CQI present) and comes back as an assembled transport block; every subframe is re-run
+    through the oracle (port of ulsch_decoding's front + the uplink chain) from the same soft bits and must agree."""
+    from openair4g_b200.sim import linksim
+    from oracle import chain
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def decode_batch(self, blocks, flags=0, tbs=None):
+            w0 = [b["dematch"]["w"].copy() for b in blocks]
+            res = capi.decode_batch(blocks, flags=flags, tbs=tbs)
+            self.calls.append((blocks, tbs, w0, [b["dematch"]["w"].copy() for b in blocks], res))
+            return res
+    rec = Rec()
+    rec.BATCH_DL_STOP_AFTER_FAILURE = capi.BATCH_DL_STOP_AFTER_FAILURE
+    sim = linksim.LinkSim(linksim.ULSIM_25PRB_MCS16, max_iterations=4, seed=9, ul_front={"O_ACK": 2, "O_RI": 1, "Or1": 20})
+    z = sim.ul_sizes
+    assert z["Qprime_ACK"] > 0 and z["Qprime_RI"] > 0 and z["Qprime_CQI"] > 0 and sim.G < linksim.ULSIM_25PRB_MCS16.G
+    bler = []
+    for snr in (5.5, 7.0, 9.5):
+        r = sim.run(snr, 16, max_rounds=2, capi=rec)
+        bler.append(r["bler_round0"])
+        assert r["mismatch_vs_tx"] == 0
+    assert bler[0] > 0.5 and bler[-1] == 0.0, bler
+    P = loader.port()
+    checked = 0
+    for blocks, tbs, w0, w1, (outs, status, tbo) in rec.calls:
+        for t, (ret, valid, b) in zip(tbs, tbo):
+            uf = t["ul_front"]
+            zz = loader.UlSizes()
+            Qm, Cn = uf["Qm"], t["C"]
+            zz.Qprime_RI, zz.Qprime_ACK, zz.Qprime_CQI, zz.Hprime = uf["Qprime_RI"], uf["Qprime_ACK"], uf["Qprime_CQI"], uf["Hprime"]
+            zz.Hpp, zz.Cmux = uf["Hprime"] + uf["Qprime_RI"], uf["Cmux"]
+            zz.Rmux_prime, zz.Q_CQI = zz.Hpp // zz.Cmux, Qm * uf["Qprime_CQI"]
+            zz.G = (uf["Hprime"] - uf["Qprime_CQI"]) * Qm
+            e = np.zeros(zz.G + 8, dtype=np.int16)
+            qa, qr = np.zeros(18, dtype=np.int16), np.zeros(6, dtype=np.int16)
+            qc = np.zeros(zz.Q_CQI + 8, dtype=np.int8)
+            oa, orr = np.zeros(4, dtype=np.uint8), np.zeros(2, dtype=np.uint8)
+            assert P.orc_ulsch_front(uf["llr"], uf["c_init"], Qm, C.byref(zz), 0, uf["O_ACK"], uf["O_RI"], 0, 1, e, qa, qr, qc, oa, orr) == 0
+            o = uf["out"]
+            assert np.array_equal(o["q_ACK"][:3], qa[:3]) and np.array_equal(o["q_RI"][:Qm], qr[:Qm])
+            assert np.array_equal(o["q_cqi"][:zz.Q_CQI], qc[:zz.Q_CQI]) and np.array_equal(o["o_ACK"], oa[:2]) and o["o_RI"][0] == orr[0]
+            bl = blocks[t["first_cb"]:t["first_cb"] + Cn]
+            dm = bl[0]["dematch"]
+            Gp = zz.G // Qm
+            tb = {"seg": (Cn, Cn, 0, bl[0]["K"], 0, 0), "Ks": [x["K"] for x in bl], "G": zz.G, "Qm": Qm, "Nl": 1, "Mdlharq": 8, "Kmimo": 1,
+                  "rv": dm["rvidx"], "e": e[:zz.G].copy(), "E": [Qm * (Gp // Cn + (1 if r >= Cn - Gp % Cn else 0)) for r in range(Cn)]}
+            rx = chain.rx_tb(tb, bl[0]["max_iterations"], downlink=False, w=[x.copy() for x in w0[t["first_cb"]:t["first_cb"] + Cn]],
+                             clear=dm["clear"])
+            assert ret == rx["ret"] and valid == rx["b_valid"] and np.array_equal(b[:valid], rx["b"][:valid])
+            for r in range(Cn):
+                i = t["first_cb"] + r
+                assert status[i] == rx["status"][r] and np.array_equal(outs[i], rx["c"][r])
+                assert np.array_equal(w1[i], rx["w"][r])
+            checked += 1
+    assert checked >= 48

@@ -33,3 +33,27 @@ def test_harness_gold_sequence_matches_oracle(port):
         pos = np.arange(n)
         want = ((words[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1).astype(np.uint8)
         assert np.array_equal(txchain.gold_sequence(c_init, n), want), hex(c_init)
+
+
+def test_ulsch_control_sizes_match_the_port():
+    """oai_ulsch_control_sizes (host integer rule of the C ABI, ulsch_decoding.c:381-468) against the pinned port"""
+    import ctypes as C
+    import numpy as np
+    from openair4g_b200 import capi
+    from oracle import loader
+    P = loader.port()
+    rng = np.random.default_rng(5)
+    for _ in range(400):
+        nb_rb = int(rng.integers(1, 101))
+        Qm = int(rng.choice([2, 4, 6]))
+        Nsymb = int(rng.choice([9, 10, 11, 12]))
+        O_RI, O_ACK, Or1 = int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.choice([0, 4, 11, 12, 20, 64]))
+        sumKr = int(rng.integers(40, nb_rb * 144 * Qm + 41))
+        betas = [int(rng.integers(8, 161)) for _ in range(3)]
+        z = loader.UlSizes()
+        want = P.orc_ulsch_control_sizes(O_RI, O_ACK, Or1, 12 * nb_rb, Nsymb, betas[0], betas[1], betas[2], sumKr, nb_rb, Qm, Nsymb, C.byref(z))
+        rc, got = capi.ulsch_control_sizes(O_RI, O_ACK, Or1, 12 * nb_rb, Nsymb, betas[0], betas[1], betas[2], sumKr, nb_rb, Qm, Nsymb)
+        assert rc == want
+        if rc == 0:
+            assert got == {"Qprime_RI": z.Qprime_RI, "Qprime_ACK": z.Qprime_ACK, "Qprime_CQI": z.Qprime_CQI, "G": z.G,
+                           "Hprime": z.Hprime, "Hpp": z.Hpp}

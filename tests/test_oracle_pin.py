@@ -309,3 +309,39 @@ def test_gold_sequence_matches_reference(port, ref):
         c = (int(words[k >> 5]) >> (k & 31)) & 1
         v = int(want[k]) if c else -int(want[k])
         assert int(llr[k]) == ((v + 32768) % 65536) - 32768, k
+
+
+def test_ul_front_port_matches_compiled_ulsch_decoding(ref):
+    """oracle/port/ulfront_port.c against the reference's own ulsch_decoding() (compiled in place behind shim4) on random
+    soft bits: every Qm, both cyclic prefixes, 0/1/2 ACK bits with and without bundling, RI, CQI, int16 extremes."""
+    import ctypes as C
+    from oracle import ulgen
+    P = loader.port()
+    rng = np.random.default_rng(77)
+    cases = [(25, 16, 7736, 12, 0, 0, 0, 0, 1, 0), (25, 16, 7736, 12, 2, 1, 20, 0, 1, 0), (100, 16, 30576, 12, 1, 1, 40, 0, 1, 0),
+             (100, 26, 61664, 12, 2, 1, 40, 0, 1, 0), (10, 5, 872, 12, 1, 1, 11, 0, 1, 0), (10, 5, 872, 12, 2, 0, 0, 1, 2, 0),
+             (10, 5, 872, 12, 1, 0, 0, 1, 3, 0), (25, 16, 6200, 10, 2, 1, 20, 0, 1, 1), (25, 16, 6200, 10, 1, 1, 20, 1, 4, 1),
+             (1, 5, 72, 12, 2, 1, 0, 0, 1, 0), (4, 26, 1000, 12, 2, 1, 0, 0, 1, 0), (8, 16, 2216, 12, 1, 1, 0, 0, 1, 0),
+             (50, 24, 30576, 12, 2, 1, 30, 1, 2, 0), (6, 10, 504, 12, 1, 1, 5, 0, 1, 0)]
+    for case in cases:
+        par = ulgen.params(*case, max_it=2)
+        z, Qm = par["z"], par["Qm"]
+        assert (z.Hpp * Qm) % 32 == 0
+        llr = rng.integers(-3000, 3001, size=z.Hpp * Qm).astype(np.int16)
+        llr[rng.integers(0, llr.size, 12)] = -32768
+        llr[rng.integers(0, llr.size, 12)] = 32767
+        r = loader.ref_ulsch_decoding(par["ref"], llr)
+        e = np.zeros(14 * 1200 * 6, dtype=np.int16)
+        qa, qr = np.zeros(18, dtype=np.int16), np.zeros(6, dtype=np.int16)
+        qc = np.zeros(2560, dtype=np.int8)
+        oa, orr = np.zeros(4, dtype=np.uint8), np.zeros(2, dtype=np.uint8)
+        assert P.orc_ulsch_front(llr, par["c_init"], Qm, C.byref(z), par["Ncp"], par["O_ACK"], par["O_RI"], par["bundling"],
+                                 par["Nbundled"], e, qa, qr, qc, oa, orr) == 0
+        ne = (z.Hprime - z.Qprime_CQI) * Qm
+        assert np.array_equal(e[:ne], r["e"][:ne]), case
+        assert np.array_equal(qc[:z.Q_CQI], r["q_cqi"][:z.Q_CQI]), case
+        if par["O_ACK"]:
+            k = 3 if par["O_ACK"] == 2 else 1
+            assert np.array_equal(qa[:k], r["q_ACK"][:k]) and np.array_equal(oa[:par["O_ACK"]], r["o_ACK"][:par["O_ACK"]]), case
+        if par["O_RI"]:
+            assert np.array_equal(qr[:Qm], r["q_RI"][:Qm]) and orr[0] == r["o_RI"][0], case
