@@ -4,7 +4,7 @@
 //   * the HARQ-ACK and RI soft sums and decisions, and the CQI soft bits q[] for the host's convolutional decoder.
 // Reference: openair1/PHY/LTE_TRANSPORT/ulsch_decoding.c:600-733 (Gold sequence, placeholder handling, de-interleaver),
 // :775-873 (q_ACK, q_RI), :877-1002 (CQI soft bits, e), :1052-1153 (decisions).  The quirks that define the result are
-// listed in oracle/port/ulfront_port.c; in short: placeholder signs are patched in the SEQUENCE (y-placeholder = sign of
+// listed in DESIGN.md (uplink front end); in short: placeholder signs are patched in the SEQUENCE (y-placeholder = sign of
 // the symbol's first bit, x-placeholders = -1), products are stored as int16, ACK positions are zeroed after they were
 // summed and stay in e, and the CQI / data walk only ever skips the run of RI symbols at the very start of the matrix.
 //
