@@ -13,6 +13,7 @@
 #include <tuple>
 #include <utility>
 #include <algorithm>
+#include <chrono>
 
 #include "../../include/oai_turbo_b200.h"
 #include "td_common.cuh"
@@ -25,6 +26,10 @@
 #include "ul_kernels.cuh"
 
 namespace oai {
+
+// host_pack.cpp: int16 -> int8 range check + pack on the caller's CPU cores (the narrow input feed)
+int host_pack_threads();
+int host_pack_i16_to_i8(const int16_t* src, int8_t* dst, size_t n);
 
 static const uint16_t kQpp[188][2] = {
 #include "qpp_table.inc"
@@ -188,6 +193,14 @@ constexpr int CKPT_S = MAP_CKPT_STEPS;
 constexpr int GUARD_B = 2954;     // 11 B + 256 <= 32767: the reference cannot saturate (DESIGN.md "fast-path guard"); our own no-wrap rule then allows M = B+1 <= 2499
 constexpr int MAX_PARTS = 8;      // pipeline stages of one host batch (copy of part i+1 overlaps the decode of part i)
 constexpr int MIN_PART_BLOCKS = 2960;   // smaller parts leave the MAP kernel latency-bound (measured: 16 parts 25 ms, 8 parts 18.6 ms per 23680 blocks)
+constexpr int PART_STREAMS = 3;   // the parts of a pipelined batch are decoded on this many compute streams in turn: a part fills
+                                  // a fraction of the SMs (one K=6144 wave of the MAP kernel is 14 208 blocks), consecutive
+                                  // parts overlap on the GPU instead of queueing behind each other
+
+// Narrow input feed: measured pack throughput decides whether it stays on.  Below ~1.3x the link rate packing cannot win
+// (several ranks sharing the host's cores, a small VM); the feed then pauses for a while and is probed again.
+static std::atomic<int> g_pack_pause{0};
+static double pack_min_gbs() { const char* e = getenv("OAI_TURBO_PACK_MIN_GBS"); return (e && *e) ? atof(e) : 70.0; }
 
 // optional per-launch CUDA-event timing (bench.py's roofline leg): class 0 demux, 1 map, 2 x1, 3 x2
 struct Profiler {
@@ -272,9 +285,10 @@ struct Batch {
     const void *in, *out, *status, *fe_rm, *fe_w, *fe_harq;
     int lo, n, part, max_iter, max_K;
     unsigned gen;                      // DevCtx::gen the graph was built against
+    int in8 = 0;
     bool operator==(const GraphKey& o) const {
       return in == o.in && out == o.out && status == o.status && fe_rm == o.fe_rm && fe_w == o.fe_w && fe_harq == o.fe_harq &&
-             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen;
+             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen && in8 == o.in8;
     }
   };
   struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; };
@@ -323,15 +337,17 @@ struct Batch {
   // `part` selects the batch-maximum cell, so that parts of one batch can run as independent pipeline stages.
   // fe_rm != nullptr: block i (of the whole batch) is rm block i and k_demux16 reads its input out of the dematched
   // circular buffers (fused sub-block deinterleaving) instead of in_dev
+  // in8: in_dev points at int8 soft bits (one byte per element, same element offsets)
   int decode16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, cudaStream_t st, int lo = 0, int cnt = -1,
-               int part = 0, const RmBlock* fe_rm = nullptr, const int16_t* fe_w = nullptr, const int16_t* fe_harq = nullptr) {
+               int part = 0, const RmBlock* fe_rm = nullptr, const int16_t* fe_w = nullptr, const int16_t* fe_harq = nullptr,
+               int in8 = 0) {
     const int n = (cnt < 0) ? this->n : cnt;
     if (n <= 0) return 0;
     // Small batches are launch-latency bound (one K=40 block: 31 launches, 0.24 ms): their launch sequence -- static for a
     // given block count, iteration limit and set of pointers, early exits are decided on the device -- is built once
     // as a CUDA graph and replayed.
     if (n <= GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
-      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen};
+      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen, in8};
       GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
@@ -341,7 +357,7 @@ struct Batch {
         if (cudaGraphCreate(&graph, 0) == cudaSuccess) {
           Launcher rec;
           rec.graph = graph;
-          l = enqueue16(in_dev, out_dev, status_dev, rec, lo, n, part, fe_rm, fe_w, fe_harq, false);
+          l = enqueue16(in_dev, out_dev, status_dev, rec, lo, n, part, fe_rm, fe_w, fe_harq, false, in8);
           if (!rec.ok || l < 0 || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
           cudaGraphDestroy(graph);
         }
@@ -360,10 +376,10 @@ struct Batch {
     }
     Launcher direct;
     direct.st = st;
-    return enqueue16(in_dev, out_dev, status_dev, direct, lo, n, part, fe_rm, fe_w, fe_harq, true);
+    return enqueue16(in_dev, out_dev, status_dev, direct, lo, n, part, fe_rm, fe_w, fe_harq, true, in8);
   }
   int enqueue16(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, Launcher& L, int lo, int n, int part,
-                const RmBlock* fe_rm, const int16_t* fe_w, const int16_t* fe_harq, bool count) {
+                const RmBlock* fe_rm, const int16_t* fe_w, const int16_t* fe_harq, bool count, int in8 = 0) {
     cudaStream_t st = L.st;                             // profiler events (never recorded into a graph: prof.on excludes graphs)
     int launches = 0;
     CbMeta* d_meta = this->d_meta + lo;
@@ -380,7 +396,7 @@ struct Batch {
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
     x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
-    x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq;
+    x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq; x.in8 = in8;
     L.zero_ints(nact[0], 2);
     L.zero_ints(d_batch_max, 1);
     MapArgs mp;
@@ -650,7 +666,20 @@ struct HostBatch {
   int cap8_blocks = 0, cap8_K = 0, n16 = 0;
   cudaStream_t st = nullptr;
   cudaStream_t st_copy = nullptr, st_out = nullptr;      // input / output copies of the pipelined form
-  cudaEvent_t ev_part[MAX_PARTS] = {}, ev_done[MAX_PARTS] = {}, ev_out = nullptr;
+  cudaStream_t st_part[PART_STREAMS] = {};               // compute streams of its parts
+  cudaEvent_t ev_part[MAX_PARTS] = {}, ev_done[MAX_PARTS] = {}, ev_out = nullptr, ev_setup = nullptr;
+  int8_t* d_in8 = nullptr; int8_t* h_in8 = nullptr; size_t cap_in8 = 0;   // narrow input feed: packed soft bits (pinned stage + device)
+  int ensure_in8(size_t bytes) {
+    if (bytes > cap_in8) {
+      if (d_in8) cudaFree(d_in8);
+      if (h_in8) cudaFreeHost(h_in8);
+      d_in8 = nullptr; h_in8 = nullptr; cap_in8 = 0;
+      CU(cudaMalloc(&d_in8, bytes));
+      CU(cudaMallocHost(&h_in8, bytes));
+      cap_in8 = bytes;
+    }
+    return 0;
+  }
   bool direct_out = false;
   int dev = -1;
   int cap_blocks = 0, cap_K = 0;
@@ -888,10 +917,15 @@ struct HostBatch {
     if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (st_copy) {
       cudaStreamDestroy(st_copy); st_copy = nullptr; cudaStreamDestroy(st_out); st_out = nullptr;
+      for (auto& s2 : st_part) { if (s2) cudaStreamDestroy(s2); s2 = nullptr; }
       for (auto& e : ev_part) { cudaEventDestroy(e); e = nullptr; }
       for (auto& e : ev_done) { cudaEventDestroy(e); e = nullptr; }
       cudaEventDestroy(ev_out); ev_out = nullptr;
+      if (ev_setup) { cudaEventDestroy(ev_setup); ev_setup = nullptr; }
     }
+    if (d_in8) cudaFree(d_in8);
+    if (h_in8) cudaFreeHost(h_in8);
+    d_in8 = nullptr; h_in8 = nullptr; cap_in8 = 0;
     cap_blocks = cap_K = 0; cap_in = cap_out = 0;
   }
 
@@ -1042,6 +1076,8 @@ struct HostBatch {
       if (!st_copy) {
         CU(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
+        for (auto& s2 : st_part) CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming));
         for (auto& e : ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
@@ -1140,11 +1176,11 @@ struct HostBatch {
     // when every block of the batch goes through the front end (and is a 16-bit block), sub-block deinterleaving is
     // fused into k_demux16: the decoder input y is never materialised
     const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
-    auto front_end = [&](size_t jlo, size_t jhi) {            // dematch (+ deinterleave) of rm blocks [jlo, jhi) on st
+    auto front_end = [&](size_t jlo, size_t jhi, cudaStream_t fs) {   // dematch (+ deinterleave) of rm blocks [jlo, jhi) on fs
       const int cnt = (int)(jhi - jlo);
-      k_rm_rx<<<cnt, RM_THREADS, 0, st>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);
+      k_rm_rx<<<cnt, RM_THREADS, 0, fs>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);
       ++g_launches;
-      if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, st>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
+      if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, fs>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
@@ -1200,7 +1236,7 @@ struct HostBatch {
           else memset(h_w + rm[j].w_off, 0, sizeof(int16_t) * 3 * rm[j].Kpi);
         }
         if (w_hw) CU(cudaMemcpyAsync(d_w, h_w, w_hw * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        front_end(0, rm.size());
+        front_end(0, rm.size(), st);
         if (w_hw) CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
       }
     }
@@ -1233,27 +1269,65 @@ struct HostBatch {
       rc = enqueue_inputs(0, n, st);
       if (rc) return rc;
     }
-    // all input copies are enqueued before the first kernel launch, AFTER the small metadata copy above: copies of one
-    // direction execute in issue order, and a metadata copy queued behind the inputs would serialise everything
-    // (measured: 48 instead of 32 ms per 42624 blocks)
-    for (int part = 0; parts > 1 && part < parts; ++part) {
-      // (with the front end in the parts, rm block j is block j of the batch: every block is an rm block)
-      rc = fe_parts ? copy_e_runs(part_lo(part), part_lo(part + 1), st_copy) : enqueue_inputs(part_lo(part), part_lo(part + 1), st_copy);
-      if (rc) return rc;
-      CU(cudaEventRecord(ev_part[part], st_copy));
-    }
-    for (int part = 0; parts > 1 && part < parts; ++part) {
-      const int lo = part_lo(part), hi = part_lo(part + 1);
-      CU(cudaStreamWaitEvent(st, ev_part[part], 0));
-      if (fe_parts) front_end(lo, hi);
-      rc = fuse_deint ? b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part, d_rm, d_w, hp)
-                      : b.decode16(d_in, d_out, d_status, st, lo, hi - lo, part);
-      if (rc < 0) return rc;
-      // this part's decoded bytes go back while the next parts are still being copied in / decoded
-      CU(cudaEventRecord(ev_done[part], st));
-      CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
-      const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
-      if (want_cb_out) CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
+    // Pipelined form.  Everything the parts depend on (metadata, tables of the front end, the zeroed output) is on st
+    // by now; the part streams wait for it once.  Per part: input copy on the copy stream (packed to int8 on the host
+    // first when the narrow feed is on and the values allow it), decode on one of the PART_STREAMS compute streams,
+    // decoded bytes back on the output stream.  The small metadata copies above were issued BEFORE the first input copy:
+    // copies of one direction execute in issue order, and a metadata copy queued behind the inputs would serialise
+    // everything (measured: 48 instead of 32 ms per 42624 blocks).
+    if (parts > 1) {
+      CU(cudaEventRecord(ev_setup, st));
+      for (auto& s2 : st_part) CU(cudaStreamWaitEvent(s2, ev_setup, 0));
+      bool narrow = !fe_parts && host_pack_threads() > 0 && !getenv("OAI_TURBO_NO_NARROW_FEED");
+      if (narrow && g_pack_pause.load() > 0) { g_pack_pause.fetch_sub(1); narrow = false; }
+      if (narrow) { rc = ensure_in8(in_hw); if (rc) return rc; }
+      double pack_s = 0, pack_bytes = 0;
+      for (int part = 0; part < parts; ++part) {
+        const int lo = part_lo(part), hi = part_lo(part + 1);
+        int in8 = 0;
+        if (narrow) {
+          // runs of blocks that are contiguous in the caller's memory are packed in one pass
+          const auto t0 = std::chrono::steady_clock::now();
+          int bad = 0;
+          for (int i = lo; i < hi && !bad;) {
+            const int16_t* base = descs[order[i]].in;
+            size_t len = (size_t)3 * descs[order[i]].K + 12;
+            int j = i + 1;
+            while (j < hi && descs[order[j]].in == base + len) { len += (size_t)3 * descs[order[j]].K + 12; ++j; }
+            bad = host_pack_i16_to_i8(base, h_in8 + in_off[i], len);
+            pack_bytes += 2.0 * (double)len;
+            i = j;
+          }
+          pack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          if (!bad) {
+            const size_t o0 = in_off[lo], o1 = in_off[hi - 1] + (size_t)3 * descs[order[hi - 1]].K + 12;
+            CU(cudaMemcpyAsync(d_in8 + o0, h_in8 + o0, o1 - o0, cudaMemcpyHostToDevice, st_copy));
+            in8 = 1;
+          } else if (bad < 0) narrow = false;
+          // (bad > 0: this part holds values beyond int8 and goes over as int16 below; later parts are tried again)
+        }
+        if (!in8) {
+          rc = fe_parts ? copy_e_runs(lo, hi, st_copy) : enqueue_inputs(lo, hi, st_copy);
+          if (rc) return rc;
+        }
+        CU(cudaEventRecord(ev_part[part], st_copy));
+        cudaStream_t sp = st_part[part % PART_STREAMS];
+        CU(cudaStreamWaitEvent(sp, ev_part[part], 0));
+        if (fe_parts) front_end(lo, hi, sp);
+        rc = fuse_deint ? b.decode16(d_in, d_out, d_status, sp, lo, hi - lo, part, d_rm, d_w, hp)
+                        : b.decode16(in8 ? reinterpret_cast<const int16_t*>(d_in8) : d_in, d_out, d_status, sp, lo, hi - lo, part,
+                                     nullptr, nullptr, nullptr, in8);
+        if (rc < 0) return rc;
+        // this part's decoded bytes go back while the next parts are still being copied in / decoded
+        CU(cudaEventRecord(ev_done[part], sp));
+        CU(cudaStreamWaitEvent(st_out, ev_done[part], 0));
+        const size_t o0 = out_off[lo], o1 = (size_t)out_off[hi - 1] + (descs[order[hi - 1]].K >> 3);
+        if (want_cb_out) CU(cudaMemcpyAsync((direct_out ? descs[order[0]].decoded_bytes : h_out) + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st_out));
+      }
+      for (int part = 0; part < parts; ++part) CU(cudaStreamWaitEvent(st, ev_done[part], 0));
+      // a pack pass slower than ~1.3x the link gains nothing: pause the narrow feed for the next batches
+      if (pack_s > 0 && pack_bytes / pack_s / 1e9 < pack_min_gbs()) g_pack_pause.store(16);
+      if (trace && pack_s > 0) fprintf(stderr, "[trace %p] narrow feed: packed %.0f MB at %.1f GB/s\n", (void*)this, pack_bytes / 1e6, pack_bytes / pack_s / 1e9);
     }
     if (trace) cudaEventRecord(ev[1], st);
     if (n16 > 0 && parts == 1) {

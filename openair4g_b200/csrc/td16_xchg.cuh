@@ -43,6 +43,7 @@ struct XchgArgs {
   const RmBlock* rm;
   const int16_t* w_pool;
   const int16_t* harq_pool;
+  int in8;                      // k_demux16: in_base points at int8 soft bits (same element offsets), the narrow host feed
 };
 
 // Active-block compaction: the kernels address blocks through a packed list of the blocks that are still being
@@ -178,6 +179,8 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
   if (!(m.flags & 1)) { if (threadIdx.x == 0) st->status = 0xFE; return; }
   const int K = m.K, A = p.A;
   const int16_t* y = p.in_base + (((long)m.in_off_hi << 32) | m.in_off_lo);
+  const int8_t* y8 = reinterpret_cast<const int8_t*>(p.in_base) + (((long)m.in_off_hi << 32) | m.in_off_lo);
+  const bool in8 = !FE && p.in8;
   int16_t* s0 = sm, *p1 = sm + A, *p2 = sm + 2 * A;
   const int16_t* sw = sm + 3 * A;
   uint32_t RTC = 0, Kpi = 0, ND = 0;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
   auto kof = [&](uint32_t j) -> uint32_t { return brev5(j & 31) * RTC + (j >> 5); };
   // decoder input element idx (0 .. 3K+11): the reference's d[3*ND + idx]
   auto ysrc = [&](int idx) -> int {
-    if (!FE) return y[idx];
+    if (!FE) return in8 ? (int)y8[idx] : (int)y[idx];
     const uint32_t q = 3 * ND + idx, r = q % 3;
     const uint32_t k = kof(r == 2 ? (q - 5) / 3 : q / 3);
     return r == 0 ? sw[k] : (r == 1 ? sw[Kpi + 2 * k] : sw[Kpi + 2 * k + 1]);
@@ -206,6 +209,8 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
     if (FE) {
       const uint32_t k0 = kof(ND + pos), k2 = kof(ND + pos - 1);      // ND >= 1 for every legal K (K+4 is never a multiple of 32)
       v0 = sw[k0]; v1 = sw[Kpi + 2 * k0]; v2 = sw[Kpi + 2 * k2 + 1];
+    } else if (in8) {
+      v0 = y8[3 * pos]; v1 = y8[3 * pos + 1]; v2 = y8[3 * pos + 2];
     } else {
       v0 = y[3 * pos]; v1 = y[3 * pos + 1]; v2 = y[3 * pos + 2];
     }

@@ -201,3 +201,40 @@ def test_small_batch_graph_replay_follows_new_inputs(capi):
                 assert st == wr, (rnd, pi, b["K"], st, wr)
                 if b["max_iterations"] > 1:
                     assert np.array_equal(ob, wb), (rnd, pi, b["K"])
+
+
+def test_narrow_feed_and_part_streams(capi, monkeypatch):
+    """The pipelined host batch packs parts whose soft bits fit int8 on the host (narrow feed) and decodes its parts on
+    several compute streams.  9000 blocks of K=6144 = 3 parts: one part holds a value beyond int8 and must go over as
+    int16, the others as int8 -- results must equal the oracle's and the un-pipelined, un-packed call's, from page-locked
+    and from pageable caller memory."""
+    K, n, nd = 6144, 9000, 9
+    ys, want, _ = _distinct(K, nd, 9400)
+    assert all(np.abs(y).max() <= 127 for y in ys)
+    big = ys[3].copy()
+    big[777] = 300                                        # one soft bit beyond int8
+    wbig = loader.port_decode16(big, K, 6, 1)
+    pin = capi.PinnedArray((n, 3 * K + 12), np.int16)
+    for i in range(n):
+        pin.array[i] = ys[(i * 7) % nd]
+    pin.array[4000] = big                                 # in the second part
+    call = capi.HostBatchCall(pin.array, K, 6, 1)
+    monkeypatch.setenv("OAI_TURBO_PACK_THREADS", "4")     # the narrow feed is opt-in
+    monkeypatch.setenv("OAI_TURBO_PACK_MIN_GBS", "0")     # keep it on whatever this box's pack rate is
+    out, st = call.run()
+    out, st = out.copy(), st.copy()
+    for i in range(n):
+        wb, wr = wbig if i == 4000 else want[(i * 7) % nd]
+        assert st[i] == wr and np.array_equal(out[i], wb), i
+    monkeypatch.setenv("OAI_TURBO_NO_NARROW_FEED", "1")
+    out2, st2 = call.run()
+    assert np.array_equal(out2, out) and np.array_equal(st2, st)
+    monkeypatch.setenv("OAI_TURBO_NO_PIPELINE", "1")
+    out3, st3 = call.run()
+    assert np.array_equal(out3, out) and np.array_equal(st3, st)
+    monkeypatch.delenv("OAI_TURBO_NO_PIPELINE")
+    monkeypatch.delenv("OAI_TURBO_NO_NARROW_FEED")
+    pageable = np.array(pin.array)                        # pageable caller memory: packed straight from it
+    call2 = capi.HostBatchCall(pageable, K, 6, 1)
+    out4, st4 = call2.run()
+    assert np.array_equal(out4, out) and np.array_equal(st4, st)
