@@ -581,8 +581,9 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
     """BASELINE configs[3] through the product path: 64 cells, every cell-subframe one 100 PRB MCS16 allocation
     (ulsch_decoding.c:1222-1369 shape: C = 5 code blocks of K = 6144, G = 57600, Qm = 4, E = 11520 soft bits per block),
     cells assigned to GPUs with sharding.assign_by_cell, one device-resident HARQ pool per GPU, rate-matched soft bits e
-    in page-locked host memory -> fused front end + decoder -> decoded bytes in page-locked host memory.  Fixed total work
-    (strong scaling over the 64 cells); timed on the host around submit + wait like `e2e`, max over ranks.
+    in page-locked host memory -> fused front end + decoder -> decoded bytes in page-locked host memory.  Fixed work
+    per GPU: the 64 cells are spread over the GPUs and the number of subframes batched per step grows with N (weak scaling in
+    time depth); timed on the host around submit + wait like `e2e`, max over ranks.
     Two feeds: the reference's int16 soft bits and the narrow int8 feed (oai_cb_desc_t.in_fmt = 1)."""
     import ctypes as C
     import numpy as np
@@ -590,7 +591,7 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
     from openair4g_b200 import sharding
     K, G, Cb, Qm, cells = K_BITS, 57600, 5, 4, 64
     E = G // Cb
-    S = args.mc_subframes
+    S = args.mc_subframes * world          # subframes batched per step grow with N: the 64 cells are fixed, every GPU keeps 64*128*5 blocks
     owner = sharding.assign_by_cell([c for c in range(cells) for _ in range(S)], world)     # one entry per cell-subframe
     mine = [i for i, r in enumerate(owner) if r == rank]
     n_ue = len(mine)
@@ -649,9 +650,10 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
     pool.close()
     counts = [sum(1 for r in owner if r == k) * Cb for k in range(world)]
     res["config"] = {"workload": "BASELINE configs[3]: %d cells x %d subframes x (100 PRB MCS16 = 5 x K=6144, E=11520), noise regime, "
-                                 "%d iterations; fixed total work, cells -> GPUs by sharding.assign_by_cell, one HARQ pool per GPU, "
+                                 "%d iterations; cells -> GPUs by sharding.assign_by_cell, one HARQ pool per GPU, "
                                  "page-locked e in, bytes out" % (cells, S, MAX_ITER),
-                     "blocks_total": cells * S * Cb, "blocks_per_gpu": counts, "scaling": "strong",
+                     "blocks_total": cells * S * Cb, "blocks_per_gpu": counts,
+                     "scaling": "weak (64 cells fixed; subframes batched per step = %d x n_gpus)" % args.mc_subframes,
                      "api": "oai_turbo_submit_batch(dematch_enable, harq_pool, gpu) + oai_turbo_wait per step"}
     return res
 

@@ -1,7 +1,8 @@
 """isolated-decoder sweep over batch size and block size K (device-resident plan, noise regime:
 uniform +-16 LLRs, CRC never passes -> exactly 6 iterations).  Prints time per batch and decoded information Mbit/s."""
 import sys
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from openair4g_b200 import capi
 capi.init_td16()
@@ -25,6 +26,13 @@ for K in (40, 512, 1024, 2048, 4096, 6144):
             plan.decode(y.data_ptr(), row, out.data_ptr(), K // 8, st.data_ptr(), s)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print("%6d %8d %12.1f %12.1f %10s" % (K, B, ms * 1e3, B * K / ms / 1e3, bool((st == 7).all())))
+        extra = ""
+        if B == 65536:                    # per-class kernel times of one decode (CUDA events around every launch)
+            plan.profile(True)
+            plan.decode(y.data_ptr(), row, out.data_ptr(), K // 8, st.data_ptr(), s)
+            torch.cuda.synchronize()
+            pm, pc = plan.profile(False, fetch=True)
+            extra = "   demux %.0f us, map %.0f us (%d), x1 %.0f us, x2 %.0f us" % (pm[0] * 1e3, pm[1] * 1e3, pc[1], pm[2] * 1e3, pm[3] * 1e3)
+        print("%6d %8d %12.1f %12.1f %10s%s" % (K, B, ms * 1e3, B * K / ms / 1e3, bool((st == 7).all()), extra))
         plan.close()
         del y, out, st
