@@ -581,78 +581,106 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
     """BASELINE configs[3] through the product path: 64 cells, every cell-subframe one 100 PRB MCS16 allocation
     (ulsch_decoding.c:1222-1369 shape: C = 5 code blocks of K = 6144, G = 57600, Qm = 4, E = 11520 soft bits per block),
     cells assigned to GPUs with sharding.assign_by_cell, one device-resident HARQ pool per GPU, rate-matched soft bits e
-    in page-locked host memory -> fused front end + decoder -> decoded bytes in page-locked host memory.  Fixed work
-    per GPU: the 64 cells are spread over the GPUs and the number of subframes batched per step grows with N (weak scaling in
-    time depth); timed on the host around submit + wait like `e2e`, max over ranks.
-    Two feeds: the reference's int16 soft bits and the narrow int8 feed (oai_cb_desc_t.in_fmt = 1)."""
+    in page-locked host memory -> fused front end + decoder -> decoded bytes in page-locked host memory.  The 64 cells are
+    spread over the GPUs and the number of subframes batched per step grows with N (weak scaling in time depth); timed on
+    the host around submit + wait like `e2e`, max over ranks.
+    Two feeds: the reference's int16 soft bits and the narrow int8 feed (oai_cb_desc_t.in_fmt = 1).
+    The GPUs are identical but their host links are not (profiles/r2d_link_ceiling.txt), so for N > 1 the cells are first
+    spread evenly, every rank's rate is measured on two untimed steps, and the cells are re-assigned in proportion."""
     import ctypes as C
     import numpy as np
     import torch
     from openair4g_b200 import sharding
     K, G, Cb, Qm, cells = K_BITS, 57600, 5, 4, 64
     E = G // Cb
-    S = args.mc_subframes * world          # subframes batched per step grow with N: the 64 cells are fixed, every GPU keeps 64*128*5 blocks
-    owner = sharding.assign_by_cell([c for c in range(cells) for _ in range(S)], world)     # one entry per cell-subframe
-    mine = [i for i, r in enumerate(owner) if r == rank]
-    n_ue = len(mine)
-    n = n_ue * Cb
-    out = capi.PinnedArray((max(n, 1), K // 8), np.uint8)
-    status = np.zeros(max(n, 1), dtype=np.uint8)
-    pool = capi.HarqPool(max(n, 1), K, gpu=gpu)
-    res = {}
-    for name, dt_np, fmt in (("e_int16", np.int16, 0), ("e_int8", np.int8, 1)):
-        pin = capi.PinnedArray((max(n_ue, 1), G), dt_np)
+    S = args.mc_subframes * world          # subframes batched per step grow with N: the 64 cells are fixed
+    cell_of = [c for c in range(cells) for _ in range(S)]                                   # one entry per cell-subframe
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def prepare(owner, dt_np, fmt):
+        mine = [i for i, r in enumerate(owner) if r == rank]
+        n_ue = len(mine)
+        n = n_ue * Cb
+        st = {"n": n, "n_ue": n_ue, "isz": np.dtype(dt_np).itemsize}
+        st["out"] = capi.PinnedArray((max(n, 1), K // 8), np.uint8)
+        st["status"] = np.zeros(max(n, 1), dtype=np.uint8)
+        st["pool"] = capi.HarqPool(max(n, 1), K, gpu=gpu)
+        st["pin"] = capi.PinnedArray((max(n_ue, 1), G), dt_np)
         g = torch.Generator()
         g.manual_seed(77 + rank)
-        pin.array[...] = torch.randint(-16, 17, (max(n_ue, 1), G), dtype=torch.int16, generator=g).numpy().astype(dt_np)
+        st["pin"].array[...] = torch.randint(-16, 17, (max(n_ue, 1), G), dtype=torch.int16, generator=g).numpy().astype(dt_np)
         descs = (capi.CbDesc * max(n, 1))()
-        isz = pin.array.itemsize
+        base, ob, sb = st["pin"].array.ctypes.data, st["out"].array.ctypes.data, st["status"].ctypes.data
         for u in range(n_ue):
             for r in range(Cb):
                 i = u * Cb + r
                 d = descs[i]
-                d.in_ = pin.array.ctypes.data + (u * G + r * E) * isz
-                d.decoded_bytes = out.array.ctypes.data + i * (K // 8)
-                d.status = status.ctypes.data + i
+                d.in_ = base + (u * G + r * E) * st["isz"]
+                d.decoded_bytes = ob + i * (K // 8)
+                d.status = sb + i
                 d.K, d.max_iterations, d.crc_type, d.F, d.decode_enable, d.dematch_enable = K, MAX_ITER, CRC_TYPE, 0, 1, 1
                 d.G, d.C, d.r, d.rvidx, d.clear, d.Qm, d.Nl, d.Mdlharq, d.Kmimo, d.Nsoft = G, Cb, r, 0, 1, Qm, 1, 8, 1, 1827072
                 d.tb_id = mine[u]
-                d.harq_pool = pool.handle
+                d.harq_pool = st["pool"].handle
                 d.harq_slot = i
                 d.in_fmt = fmt
+        st["descs"] = descs
+        return st
 
-        def call():
-            if n == 0:
-                return
-            h = C.c_void_p()
-            if capi.lib.oai_turbo_submit_batch(descs, n, 0, gpu, C.byref(h)) or capi.lib.oai_turbo_wait(h):
-                raise SystemExit("bench.py: multicell_ul batch failed: " + capi.last_error())
-        for _ in range(2):
-            call()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+    def call(st):
+        if st["n"] == 0:
+            return
+        h = C.c_void_p()
+        if capi.lib.oai_turbo_submit_batch(st["descs"], st["n"], 0, gpu, C.byref(h)) or capi.lib.oai_turbo_wait(h):
+            raise SystemExit("bench.py: multicell_ul batch failed: " + capi.last_error())
+
+    def timed(st, steps):
+        barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            call()
+        for _ in range(steps):
+            call(st)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    res = {}
+    for name, dt_np, fmt in (("e_int16", np.int16, 0), ("e_int8", np.int8, 1)):
+        owner = sharding.assign_by_cell(cell_of, world)
+        st = prepare(owner, dt_np, fmt)
+        call(st)
+        weights = None
+        if world > 1:
+            dt_cal = timed(st, 2)                                   # untimed calibration: this rank's blocks per second
+            weights = sharding.measured_weights(st["n"] / dt_cal, dist)
+            if max(weights) / min(weights) > 1.05:
+                owner = sharding.assign_by_cell(cell_of, world, weights=weights)
+                st["pool"].close()
+                del st
+                st = prepare(owner, dt_np, fmt)
+                call(st)
+        call(st)
+        dt = timed(st, args.steps)
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        if n and not (status[:n] == MAX_ITER + 1).all():
+        n, n_ue, isz = st["n"], st["n_ue"], st["isz"]
+        if n and not (st["status"][:n] == MAX_ITER + 1).all():
             raise SystemExit("bench.py: multicell_ul noise-regime blocks must report status 7")
+        counts = [sum(1 for r in owner if r == k) * Cb for k in range(world)]
         res[name] = {"value": cells * S * Cb * K * args.steps / dt / 1e6, "unit": "Mbit/s", "ms_per_step": 1e3 * dt / args.steps,
-                     "h2d_bytes_per_step_per_gpu": n_ue * G * isz, "d2h_bytes_per_step_per_gpu": n * (K // 8 + 1),
-                     "h2d_gbs_per_gpu": n_ue * G * isz * args.steps / dt / 1e9}
-        del pin
-    pool.close()
-    counts = [sum(1 for r in owner if r == k) * Cb for k in range(world)]
+                     "h2d_bytes_per_step_this_gpu": n_ue * G * isz, "d2h_bytes_per_step_this_gpu": n * (K // 8 + 1),
+                     "h2d_gbs_this_gpu": n_ue * G * isz * args.steps / dt / 1e9, "blocks_per_gpu": counts,
+                     "rank_weights": None if weights is None else [round(w, 3) for w in weights]}
+        st["pool"].close()
+        del st
     res["config"] = {"workload": "BASELINE configs[3]: %d cells x %d subframes x (100 PRB MCS16 = 5 x K=6144, E=11520), noise regime, "
-                                 "%d iterations; cells -> GPUs by sharding.assign_by_cell, one HARQ pool per GPU, "
-                                 "page-locked e in, bytes out" % (cells, S, MAX_ITER),
-                     "blocks_total": cells * S * Cb, "blocks_per_gpu": counts,
+                                 "%d iterations; cells -> GPUs by sharding.assign_by_cell (weighted by each rank's measured rate "
+                                 "when N > 1), one HARQ pool per GPU, page-locked e in, bytes out" % (cells, S, MAX_ITER),
+                     "blocks_total": cells * S * Cb,
                      "scaling": "weak (64 cells fixed; subframes batched per step = %d x n_gpus)" % args.mc_subframes,
                      "api": "oai_turbo_submit_batch(dematch_enable, harq_pool, gpu) + oai_turbo_wait per step"}
     return res

@@ -270,6 +270,7 @@ struct Batch {
   Profiler prof;
   DevCtx* ctx = nullptr;
   int cap = 0, n = 0, A = 0, max_iter = 0, max_K = 0;
+  int cur_max_K = 6144;        // largest K of the batch that is loaded (set_meta): sizes the exchange CTAs
   long slot_hw = 0, ckpt_words = 0;
   CbMeta* d_meta = nullptr;
   CbState* d_state = nullptr;
@@ -286,9 +287,10 @@ struct Batch {
     int lo, n, part, max_iter, max_K;
     unsigned gen;                      // DevCtx::gen the graph was built against
     int in8 = 0;
+    int cur_K = 0;                     // largest K of the loaded batch (sizes the exchange CTAs)
     bool operator==(const GraphKey& o) const {
       return in == o.in && out == o.out && status == o.status && fe_rm == o.fe_rm && fe_w == o.fe_w && fe_harq == o.fe_harq &&
-             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen && in8 == o.in8;
+             lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen && in8 == o.in8 && cur_K == o.cur_K;
     }
   };
   struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; };
@@ -329,7 +331,8 @@ struct Batch {
     h_meta = m;
     n = (int)m.size();
     max_iter = 0;
-    for (auto& x : m) if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter);
+    cur_max_K = 40;
+    for (auto& x : m) { if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter); cur_max_K = std::max<int>(cur_max_K, x.K); }
     CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
@@ -347,7 +350,7 @@ struct Batch {
     // given block count, iteration limit and set of pointers, early exits are decided on the device -- is built once
     // as a CUDA graph and replayed.
     if (n <= GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
-      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen, in8};
+      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen, in8, cur_max_K};
       GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
@@ -418,7 +421,20 @@ struct Batch {
       ++launches;
     };
     prof.begin(0, st);
+    const int xth = xchg_threads_for(cur_max_K);
+    auto launch_x1 = [&]() {
+      if (xth == 64) L.run(k_x1_16<64>, dim3(n), dim3(64), A * sizeof(int16_t), x);
+      else if (xth == 128) L.run(k_x1_16<128>, dim3(n), dim3(128), A * sizeof(int16_t), x);
+      else L.run(k_x1_16<256>, dim3(n), dim3(256), A * sizeof(int16_t), x);
+    };
+    auto launch_x2 = [&]() {
+      if (xth == 64) L.run(k_x2_16<64>, dim3(n), dim3(64), A * sizeof(int16_t), x);
+      else if (xth == 128) L.run(k_x2_16<128>, dim3(n), dim3(128), A * sizeof(int16_t), x);
+      else L.run(k_x2_16<256>, dim3(n), dim3(256), A * sizeof(int16_t), x);
+    };
     if (fe_rm) L.run(k_demux16_t<true>, dim3(n), dim3(XCHG_THREADS), (3 * A + 3 * 32 * ((max_K + 4 + 31) / 32)) * sizeof(int16_t), x);
+    else if (xth == 64) L.run(k_demux16_t<false, 64>, dim3(n), dim3(64), 3 * A * sizeof(int16_t), x);
+    else if (xth == 128) L.run(k_demux16_t<false, 128>, dim3(n), dim3(128), 3 * A * sizeof(int16_t), x);
     else L.run(k_demux16_t<false>, dim3(n), dim3(XCHG_THREADS), 3 * A * sizeof(int16_t), x);
     prof.end(st);
     ++launches;
@@ -427,11 +443,11 @@ struct Batch {
     for (int it = 1; it <= max_iter; ++it) {                    // reference :1201
       x.iter = it;
       prof.begin(2, st);
-      L.run(k_x1_16, dim3(n), dim3(XCHG_THREADS), A * sizeof(int16_t), x);
+      launch_x1();
       prof.end(st);
       map(ARR_SYS, ARR_P2, ARR_EXT2, 1, it, 0);                  // :1236
       prof.begin(3, st);
-      L.run(k_x2_16, dim3(n), dim3(XCHG_THREADS), A * sizeof(int16_t), x);
+      launch_x2();
       prof.end(st);
       launches += 2;
       if (it < max_iter) {

@@ -16,7 +16,11 @@
 
 namespace oai {
 
-constexpr int XCHG_THREADS = 256;
+constexpr int XCHG_THREADS = 256;      // upper bound; short blocks are launched with fewer threads (xchg_threads_for)
+// One CTA per code block: a K=512 block has 64 uint4 per array, so 256 threads would leave three quarters of the CTA idle
+// and -- at 8 resident CTAs of 256 threads per SM -- the SM mostly waiting on CTA start-up and barriers (65 536 blocks of
+// K=512: k_x2_16 228 us per launch with 256 threads).  The CRC stage needs one thread per 32 decoded bits.
+inline int xchg_threads_for(int max_K) { return max_K <= 1024 ? 64 : (max_K <= 2048 ? 128 : 256); }
 constexpr int CRC_NM = 193;          // 32-bit words of the longest block (+1)
 
 struct XchgArgs {
@@ -109,7 +113,7 @@ __device__ __forceinline__ int blk_max_reduce(int v, int* red) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x < 32) {
-    int x = (threadIdx.x < (XCHG_THREADS >> 5)) ? red[threadIdx.x] : 0;
+    int x = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
     if (threadIdx.x == 0) red[0] = x;
@@ -168,8 +172,8 @@ __device__ __forceinline__ unsigned long long clmul32(u32 x, u32 y) {
 #ifndef DEMUX_MIN_CTAS
 #define DEMUX_MIN_CTAS 6
 #endif
-template <bool FE>
-__global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(XchgArgs p) {
+template <bool FE, int TH = XCHG_THREADS>
+__global__ void __launch_bounds__(TH, DEMUX_MIN_CTAS * (XCHG_THREADS / TH) > 32 ? 32 : DEMUX_MIN_CTAS * (XCHG_THREADS / TH)) k_demux16_t(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int red[XCHG_THREADS / 32];
   const int blk = blockIdx.x;
@@ -184,13 +188,13 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
   int16_t* s0 = sm, *p1 = sm + A, *p2 = sm + 2 * A;
   const int16_t* sw = sm + 3 * A;
   uint32_t RTC = 0, Kpi = 0, ND = 0;
-  for (int i = threadIdx.x; i < 3 * A / 2; i += XCHG_THREADS) reinterpret_cast<u32*>(sm)[i] = 0;
+  for (int i = threadIdx.x; i < 3 * A / 2; i += TH) reinterpret_cast<u32*>(sm)[i] = 0;
   if (FE) {
     const RmBlock b = p.rm[blk];
     RTC = b.RTC; Kpi = b.Kpi; ND = b.ND;
     const u32* w = reinterpret_cast<const u32*>((b.w_sel ? p.harq_pool : p.w_pool) + b.w_off);
     u32* dst = reinterpret_cast<u32*>(sm + 3 * A);
-    for (uint32_t i = threadIdx.x; i < 3 * Kpi / 2; i += XCHG_THREADS) dst[i] = w[i];
+    for (uint32_t i = threadIdx.x; i < 3 * Kpi / 2; i += TH) dst[i] = w[i];
   }
   __syncthreads();
   auto kof = [&](uint32_t j) -> uint32_t { return brev5(j & 31) * RTC + (j >> 5); };
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
   };
   int mx = 0;
   const uint16_t* H = p.pi_pool + m.pi_off;
-  for (int pos = threadIdx.x; pos < K; pos += XCHG_THREADS) {
+  for (int pos = threadIdx.x; pos < K; pos += TH) {
     const int h = H[pos];
     int v0, v1, v2;
     if (FE) {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
   if (threadIdx.x < 12) mx = max(mx, abs(ysrc(3 * K + threadIdx.x)));
   __syncthreads();
   int16_t* slot = p.ws + (long)blk * p.slot_hw;
-  for (int i = threadIdx.x; i < A / 8; i += XCHG_THREADS) {
+  for (int i = threadIdx.x; i < A / 8; i += TH) {
     reinterpret_cast<uint4*>(slot + (long)ARR_S0 * A)[i] = reinterpret_cast<uint4*>(s0)[i];
     reinterpret_cast<uint4*>(slot + (long)ARR_P1 * A)[i] = reinterpret_cast<uint4*>(p1)[i];
     reinterpret_cast<uint4*>(slot + (long)ARR_P2 * A)[i] = reinterpret_cast<uint4*>(p2)[i];
@@ -272,7 +276,8 @@ __global__ void __launch_bounds__(XCHG_THREADS, DEMUX_MIN_CTAS) k_demux16_t(Xchg
 #define k_demux16 k_demux16_t<false>
 
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
+template <int TH>
+__global__ void __launch_bounds__(TH) k_x1_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
   if (blockIdx.x == 0 && threadIdx.x < 2 && p.nactive_next) p.nactive_next[threadIdx.x] = 0;   // the list k_compact fills next
@@ -291,14 +296,14 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_x1_16(XchgArgs p) {
   // (the feedback ext = (ext (-) s1) (+) s0 of reference :1354-1375 is applied by the MAP kernel
   // that produced ext, see MapArgs::upd)
   MinMax2 mm;
-  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {
+  for (int i = threadIdx.x; i < n8; i += TH) {
     const uint4 e = gext[i];
     mm.add(e);
     reinterpret_cast<uint4*>(in)[i] = e;
   }
   __syncthreads();
   const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
-  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
+  for (int i = threadIdx.x; i < n8; i += TH) {      // s2[st(i)] = ext[st(pi(i))], :1209-1231
     // thread (chunk c, lane pair t) walks its 4 steps starting at step (c>>1)&3: the 8 chunks of a warp then
     // address 8 different rows mod 8 in every instruction -> conflict-free 16-bit accesses (see rot4)
     const int r = (i >> 3) & 3;
@@ -410,7 +415,8 @@ __device__ __forceinline__ bool block_crc_check(u32 bits, uint8_t* sbytes, uint8
 #ifndef X2_MIN_CTAS
 #define X2_MIN_CTAS 8      // 32 registers -> 8 CTAs/SM (shared-memory limit); measured 6 % faster than 40 registers / 6 CTAs
 #endif
-__global__ void __launch_bounds__(XCHG_THREADS, X2_MIN_CTAS) k_x2_16(XchgArgs p) {
+template <int TH>
+__global__ void __launch_bounds__(TH, X2_MIN_CTAS * (XCHG_THREADS / TH) > 32 ? 32 : X2_MIN_CTAS * (XCHG_THREADS / TH)) k_x2_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
   __shared__ u32 xred[2 * XCHG_THREADS / 32];
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, X2_MIN_CTAS) k_x2_16(XchgArgs p)
   const int n8 = c4_words(m.W) >> 2;
   int16_t* nat = sm;
   const uint4* T4 = reinterpret_cast<const uint4*>(p.t_pool + m.t_off);
-  for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {      // ext2 back to natural order (scatter)
+  for (int i = threadIdx.x; i < n8; i += TH) {      // ext2 back to natural order (scatter)
     const int r = (i >> 3) & 3;                                 // rotated step order: conflict-free banks (rot4)
     const uint4 v = rot4(gext2[i], r), tt = rot4(__ldg(T4 + i), r);
     const u32 vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {tt.x, tt.y, tt.z, tt.w};
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, X2_MIN_CTAS) k_x2_16(XchgArgs p)
     snib[((l0 + 1) * Wq + c) ^ 7] = (uint8_t)(nb2 >> 16);
   };
   if (nosat) {
-    for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 - ext) + s0, :1241-1265
+    for (int i = threadIdx.x; i < n8; i += TH) {     // s1 = (ext2 - ext) + s0, :1241-1265
       const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
       if (hd4) park(i, d);
       uint4 r;
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(XCHG_THREADS, X2_MIN_CTAS) k_x2_16(XchgArgs p)
       mm.add(r);
     }
   } else {
-    for (int i = threadIdx.x; i < n8; i += XCHG_THREADS) {     // s1 = (ext2 (-) ext) (+) s0
+    for (int i = threadIdx.x; i < n8; i += TH) {     // s1 = (ext2 (-) ext) (+) s0
       const uint4 d = reinterpret_cast<uint4*>(nat)[i], e = gext[i], s0 = gs0[i];
       if (hd4) park(i, d);
       uint4 r;

@@ -30,6 +30,21 @@ def test_assign_by_cell_keeps_cells_together_and_balances():
         assert load.max() - load.min() <= max(np.bincount(cells))
 
 
+def test_assign_by_cell_follows_rank_weights():
+    """ranks with a faster host link take proportionally more cells (the 8-GPU box: 4 x 23 GB/s, 4 x 35 GB/s)"""
+    cells = [c for c in range(64) for _ in range(128)]
+    w = [23.0] * 4 + [35.0] * 4
+    ranks = sharding.assign_by_cell(cells, 8, weights=w)
+    owner = {}
+    for c, r in zip(cells, ranks):
+        assert owner.setdefault(c, r) == r
+    load = np.bincount(ranks, minlength=8) / 128
+    assert load.sum() == 64 and set(load[:4]) <= {6.0, 7.0} and set(load[4:]) <= {9.0, 10.0}, load
+    t = load / np.array(w)
+    assert t.max() / t.min() < 1.25
+    assert sharding.assign_by_cell(cells, 8) == sharding.assign_by_cell(cells, 8, weights=[2.0] * 8)
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -44,6 +59,8 @@ def _worker(rank, world, port, q):
     # max-over-ranks timing reduction used by bench.py
     t = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    w = sharding.measured_weights(1.0 + rank, dist)
+    assert w == [2.0 / 3.0, 4.0 / 3.0]
     q.put((rank, [r.tolist() for r in recs], float(t.item())))
     dist.barrier()
     dist.destroy_process_group()
