@@ -82,9 +82,40 @@ struct DevCtx {
   u32* crc_xp = nullptr;              // [4][32][CRC_NM] powers of x mod the CRC polynomials
   bool ok = false;
   unsigned gen = 0;                   // bumped when the tables are (re)built: cached launch graphs hold table pointers
+  // rate-dematching prefix-count tables, one per (K, F) seen so far: cnt[i] = number of circular-buffer slots in [0, i)
+  // that carry a bit (generate_dummy_w's NULL map, lte_rate_matching.c:293-382); built on the host at first use
+  uint16_t* rm_tab = nullptr;
+  uint32_t rm_tab_used = 0;
+  std::unordered_map<uint32_t, uint32_t> rm_tab_off;     // (K << 8 | F) -> halfword offset
 };
+constexpr uint32_t RM_TAB_CAP = 64u * 18560u;            // halfwords: 64 tables of the largest size (2.4 MB)
 static DevCtx g_ctx[16];
 static std::mutex g_ctx_mu;
+
+// offset of the (K, F) prefix-count table in c->rm_tab, building it if needed; 0xffffffff when the pool is full (the
+// kernel then derives the ranks itself).  The caller holds a DevGuard on c->dev.
+static uint32_t rm_table(DevCtx* c, uint32_t K, uint32_t F) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  const uint32_t key = (K << 8) | (F & 0xffu);
+  auto it = c->rm_tab_off.find(key);
+  if (it != c->rm_tab_off.end()) return it->second;
+  const uint32_t D = K + 4, RTC = (D + 31) / 32, Kpi = 32 * RTC, ND = Kpi - D, n = 3 * Kpi + 1;
+  const uint32_t need = (n + 7) & ~7u;
+  if (!c->rm_tab) {
+    if (cudaMalloc(&c->rm_tab, sizeof(uint16_t) * RM_TAB_CAP) != cudaSuccess) { cudaGetLastError(); c->rm_tab = nullptr; return 0xffffffffu; }
+  }
+  if (c->rm_tab_used + need > RM_TAB_CAP) return 0xffffffffu;
+  std::vector<uint16_t> cnt(need, 0);
+  const uint32_t magic = 0xffffffffu / RTC + 1;
+  uint32_t run = 0;
+  for (uint32_t i = 0; i < 3 * Kpi; ++i) { cnt[i] = (uint16_t)run; run += dummy_is_null(i, RTC, Kpi, ND, F, magic) ? 0u : 1u; }
+  for (uint32_t i = 3 * Kpi; i < need; ++i) cnt[i] = (uint16_t)run;
+  const uint32_t off = c->rm_tab_used;
+  if (cudaMemcpy(c->rm_tab + off, cnt.data(), sizeof(uint16_t) * need, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return 0xffffffffu; }
+  c->rm_tab_used += need;
+  c->rm_tab_off[key] = off;
+  return off;
+}
 
 static u32 gf_xtimes(u32 r, u32 poly, int w) {
   u32 top = r & (1u << (w - 1));
@@ -182,6 +213,8 @@ static void ctx_release_all() {
   for (DevCtx& c : g_ctx) {
     if (!c.ok) continue;
     cudaFree(c.pi_pool); cudaFree(c.t_pool); cudaFree(c.qpp_pool); cudaFree(c.t8_pool); cudaFree(c.crc_xp);
+    if (c.rm_tab) cudaFree(c.rm_tab);
+    c.rm_tab = nullptr; c.rm_tab_used = 0; c.rm_tab_off.clear();
     c.pi_pool = c.t_pool = c.qpp_pool = c.t8_pool = nullptr; c.crc_xp = nullptr;
     c.ok = false;
   }
@@ -1150,7 +1183,8 @@ struct HostBatch {
         rb.e_off_lo = (uint32_t)(e_hw & 0xffffffffu); rb.e_off_hi = (uint32_t)((unsigned long long)e_hw >> 32);
         }
         rm_nocopy.push_back(from_ul);
-        rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F) on the device
+        rb.dummy_off = 0xffffffffu;                      // NULL map derived from (K,F): prefix-count table, or in the kernel
+        rb.cnt_off = rm_table(b.ctx, d.K, d.F);
         rb.y_off_lo = (uint32_t)(in_off[i] & 0xffffffffu); rb.y_off_hi = (uint32_t)((unsigned long long)in_off[i] >> 32);
         e_hw += (e_bytes + 1) >> 1;
         if (!d.harq_pool) w_hw += (size_t)3 * q.Kpi;
@@ -1194,7 +1228,7 @@ struct HostBatch {
     const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
     auto front_end = [&](size_t jlo, size_t jhi, cudaStream_t fs) {   // dematch (+ deinterleave) of rm blocks [jlo, jhi) on fs
       const int cnt = (int)(jhi - jlo);
-      k_rm_rx<<<cnt, RM_THREADS, 0, fs>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold);
+      k_rm_rx<<<cnt, RM_THREADS, 0, fs>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold, b.ctx->rm_tab);
       ++g_launches;
       if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, fs>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
@@ -1753,7 +1787,7 @@ int lte_rate_matching_turbo_rx(uint32_t RTC, uint32_t G, int16_t* w, uint8_t* du
   RmBlock b;
   memset(&b, 0, sizeof(b));
   b.K = 32 * RTC - 4; b.F = 0; b.RTC = RTC; b.Kpi = q.Kpi; b.ND = 0; b.Ncb = q.Ncb; b.k0 = q.k0; b.E = q.E; b.clear = clear;
-  b.w_off = 0; b.e_off_lo = 0; b.e_off_hi = 0; b.dummy_off = 0; b.gold_off = 0xffffffffu;
+  b.w_off = 0; b.e_off_lo = 0; b.e_off_hi = 0; b.dummy_off = 0; b.gold_off = 0xffffffffu; b.cnt_off = 0xffffffffu;
   char* h = (char*)sc.h; char* d = (char*)sc.d;
   memcpy(h, &b, sizeof(b));
   if (clear != 1) memcpy(h + o_w, w, (size_t)q.Ncb * 2);

@@ -30,6 +30,7 @@ struct RmBlock {
   uint32_t gold_off;        // word offset of this block's scrambling sequence in the Gold pool, 0xffffffff: soft bits are not scrambled
   uint32_t scr_off;         // position of this block's first soft bit in that sequence (r_offset, dlsch_decoding.c:333-347)
   uint32_t e_fmt;           // 0: soft bits are int16 (the reference's type), 1: int8 (narrow host feed; same values)
+  uint32_t cnt_off;         // halfword offset of this (K,F)'s prefix-count table in the table pool, 0xffffffff: none (scan in the kernel)
 };
 
 // Pseudo-random sequences of 36.211 7.2, 32 bits per step like the reference's lte_gold_generic
@@ -53,18 +54,31 @@ __global__ void k_gold(const GoldSeq* seqs, int nseq, uint32_t* pool) {
   for (uint32_t w = 0; w < q.nwords; ++w) { step(); pool[q.off + w] = x1 ^ x2; }
 }
 
-__device__ __forceinline__ uint32_t brev5(uint32_t c) { return __brev(c) >> 27; }
+__host__ __device__ __forceinline__ uint32_t brev5(uint32_t c) {
+#ifdef __CUDA_ARCH__
+  return __brev(c) >> 27;
+#else
+  return ((c & 1) << 4) | ((c & 2) << 2) | (c & 4) | ((c & 8) >> 2) | ((c & 16) >> 4);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t div_magic(uint32_t x, uint32_t magic) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(x, magic);
+#else
+  return (uint32_t)(((unsigned long long)x * magic) >> 32);
+#endif
+}
 
 // NULL predicate of generate_dummy_w for circular-buffer index `ind` (reference :329-370).
 // Only rows 0..2 are ever marked for streams 0/1 and row 0 for stream 2 -- restated as is.
 // magic = floor(2^32 / RTC) + 1: ind / RTC as one multiply-high (exact for ind < 2^16, RTC <= 193).
-__device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F, uint32_t magic) {
+__host__ __device__ __forceinline__ bool dummy_is_null(uint32_t ind, uint32_t RTC, uint32_t Kpi, uint32_t ND, uint32_t F, uint32_t magic) {
   if (ind < Kpi) {                                   // stream 0: w[k], k = col*RTC + row
-    const uint32_t col = __umulhi(ind, magic), row = ind - col * RTC;
+    const uint32_t col = div_magic(ind, magic), row = ind - col * RTC;
     return row <= 2 && brev5(col) + 32 * row < ND + F;
   }
   const uint32_t j = ind - Kpi, k = j >> 1;
-  const uint32_t col = __umulhi(k, magic), row = k - col * RTC;
+  const uint32_t col = div_magic(k, magic), row = k - col * RTC;
   if ((j & 1) == 0) return row <= 2 && brev5(col) + 32 * row < ND + F;       // stream 1: w[Kpi+2k]
   if (ND > 0 && ind == 3 * Kpi - 1) return true;                               // :369-370
   return row == 0 && brev5(col) + 1 < ND;                                      // stream 2: w[Kpi+2k+1]
@@ -116,9 +130,13 @@ __device__ __forceinline__ uint32_t rm_scan_groups(const uint32_t* s_bal, uint32
 // LTE_TRANSPORT/dlsch_scrambling.c:99-138): soft bit k is NEGATED where scrambling bit scr_off + k is 0.  (The reference
 // stores the product back as int16, so -32768 stays -32768; under the int16 wrap of the accumulation below, adding
 // +32768 instead is the same.)
+// cnt_tab: pool of per-(K,F) prefix-count tables (cnt[i] = number of slots in [0,i) that carry a bit; 3*Kpi + 1 entries,
+// built once on the host from the same NULL predicate): with one, the ranks are two coalesced table reads per slot and the
+// kernel needs neither ballots nor a scan nor a barrier.
 __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int nblk, int16_t* w_pool,
                                                       const int16_t* e_pool, const uint8_t* dummy_pool,
-                                                      int16_t* harq_pool = nullptr, const uint32_t* gold = nullptr) {
+                                                      int16_t* harq_pool = nullptr, const uint32_t* gold = nullptr,
+                                                      const uint16_t* cnt_tab = nullptr) {
   __shared__ uint32_t s_bal[RM_GROUPS_MAX], s_pre[RM_GROUPS_MAX], s_w[RM_THREADS / 32];
   const int blk = blockIdx.x;
   if (blk >= nblk) return;
@@ -133,6 +151,31 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
   const int lane = threadIdx.x & 31;
   // the first reference loop runs only when k0 < Ncb (:747)
   const uint32_t start = (b.k0 < b.Ncb) ? b.k0 : 0;
+  if (cnt_tab && b.cnt_off != 0xffffffffu && !dm) {
+    const uint16_t* cnt = cnt_tab + b.cnt_off;
+    const uint32_t N = cnt[b.Ncb], bs = cnt[start];
+    if (N == 0) return;
+    for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
+      const uint32_t c = cnt[i];
+      int acc = (b.clear == 1) ? 0 : (int)w[i];
+      if (cnt[i + 1] != c) {
+        const uint32_t rank = (c >= bs) ? (c - bs) : (c + N - bs);
+        if (gs) {
+          for (uint32_t k = rank; k < b.E; k += N) {
+            const uint32_t pos = b.scr_off + k;
+            const int v = narrow ? (int)e8[k] : (int)e[k];
+            acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
+          }
+        } else if (narrow) {
+          for (uint32_t k = rank; k < b.E; k += N) acc += e8[k];
+        } else {
+          for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+        }
+      }
+      w[i] = (int16_t)acc;
+    }
+    return;
+  }
   const uint32_t ng = (b.Ncb + 31) >> 5;
   for (uint32_t c0 = 0; c0 < b.Ncb; c0 += RM_THREADS) {
     const uint32_t i = c0 + threadIdx.x;
