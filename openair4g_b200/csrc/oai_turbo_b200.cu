@@ -427,7 +427,7 @@ struct Batch {
     int* nact[2] = {this->d_nactive + 4 * part, this->d_nactive + 4 * part + 2};
     int cur = 0;
     if (status_dev) status_dev += lo;
-    XchgArgs x;
+    XchgArgs x{};
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
@@ -435,7 +435,7 @@ struct Batch {
     x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq; x.in8 = in8;
     L.zero_ints(nact[0], 2);
     L.zero_ints(d_batch_max, 1);
-    MapArgs mp;
+    MapArgs mp{};
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
     // packs the running blocks into list c (its counter is zero: memset above / k_x1_16) and makes it current
@@ -577,7 +577,7 @@ struct Batch8 {
   int enqueue8(const int16_t* in_dev, uint8_t* out_dev, uint8_t* status_dev, Launcher& L, bool count) {
     cudaStream_t st = L.st;
     int launches = 0;
-    Td8Args a;
+    Td8Args a{};
     a.meta = d_meta; a.state = d_state; a.ws = d_ws; a.slot_b = slot_b; a.A = A; a.ck = d_ck; a.ck_words = ck_words;
     a.nblk = n; a.qpp = ctx->qpp_pool; a.t8 = ctx->t8_pool; a.crc_xp = ctx->crc_xp; a.in_base = in_dev; a.out_base = out_dev;
     a.status_out = status_dev; a.iter = 0; a.sys_arr = a.par_arr = a.out_arr = 0;
@@ -1998,13 +1998,13 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   rc = hb.b.set_meta(meta, hb.st);
   if (rc) return rc;
   Batch& b = hb.b;
-  XchgArgs x;
+  XchgArgs x{};
   x.meta = b.d_meta; x.state = b.d_state; x.ws = b.d_ws; x.slot_hw = b.slot_hw; x.A = b.A; x.nblk = 1;
   x.pi_pool = b.ctx->pi_pool; x.t_pool = b.ctx->t_pool; x.crc_xp = b.ctx->crc_xp; x.in_base = hb.d_in; x.out_base = hb.d_out;
   x.status_out = nullptr; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = b.d_batch_max; x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr; x.rm = nullptr; x.w_pool = nullptr; x.harq_pool = nullptr;
   cudaMemsetAsync(b.d_batch_max, 0, sizeof(int), hb.st);
   k_demux16<<<1, XCHG_THREADS, 3 * b.A * sizeof(int16_t), hb.st>>>(x);
-  MapArgs mp;
+  MapArgs mp{};
   mp.meta = b.d_meta; mp.state = b.d_state; mp.ws = b.d_ws; mp.slot_hw = b.slot_hw; mp.A = b.A;
   mp.ckpt = b.d_ckpt; mp.ckpt_words = b.ckpt_words; mp.nblk = 1; mp.batch_max = (policy == 3) ? b.d_batch_max : nullptr;
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
