@@ -155,24 +155,35 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_rx(const RmBlock* blocks, int
     const uint16_t* cnt = cnt_tab + b.cnt_off;
     const uint32_t N = cnt[b.Ncb], bs = cnt[start];
     if (N == 0) return;
-    for (uint32_t i = threadIdx.x; i < b.Ncb; i += RM_THREADS) {
-      const uint32_t c = cnt[i];
-      int acc = (b.clear == 1) ? 0 : (int)w[i];
-      if (cnt[i + 1] != c) {
+    auto slot = [&](uint32_t c, bool data, int old) -> int {
+      int acc = (b.clear == 1) ? 0 : old;                  // memset(w,0,Ncb) when clear==1 (:741-742)
+      if (data) {
         const uint32_t rank = (c >= bs) ? (c - bs) : (c + N - bs);
-        if (gs) {
-          for (uint32_t k = rank; k < b.E; k += N) {
-            const uint32_t pos = b.scr_off + k;
-            const int v = narrow ? (int)e8[k] : (int)e[k];
-            acc += ((gs[pos >> 5] >> (pos & 31)) & 1u) ? v : -v;
-          }
-        } else if (narrow) {
-          for (uint32_t k = rank; k < b.E; k += N) acc += e8[k];
-        } else {
-          for (uint32_t k = rank; k < b.E; k += N) acc += e[k];
+        for (uint32_t k = rank; k < b.E; k += N) {
+          int v = narrow ? (int)e8[k] : (int)e[k];
+          if (gs) { const uint32_t pos = b.scr_off + k; if (!((gs[pos >> 5] >> (pos & 31)) & 1u)) v = -v; }
+          acc += v;
         }
       }
-      w[i] = (int16_t)acc;
+      return acc;
+    };
+    // four slots per thread and step: one 8-byte table read (+ the next entry), one 8-byte read-modify-write of w.
+    // (table offsets are multiples of 8 entries; w_off is a multiple of 4 for every legal Kpi / pool slot)
+    const bool vec = ((b.w_off & 3u) == 0);
+    const uint32_t n4 = vec ? (b.Ncb >> 2) : 0;
+    uint2* w2 = reinterpret_cast<uint2*>(w);
+    for (uint32_t q = threadIdx.x; q < n4; q += RM_THREADS) {
+      const uint2 cc = reinterpret_cast<const uint2*>(cnt)[q];
+      const uint32_t c0 = cc.x & 0xffffu, c1 = cc.x >> 16, c2 = cc.y & 0xffffu, c3 = cc.y >> 16, c4 = cnt[4 * q + 4];
+      uint2 old = make_uint2(0u, 0u);
+      if (b.clear != 1) old = w2[q];
+      const int a0 = slot(c0, c1 != c0, (int)(int16_t)(old.x & 0xffffu)), a1 = slot(c1, c2 != c1, (int)(int16_t)(old.x >> 16));
+      const int a2 = slot(c2, c3 != c2, (int)(int16_t)(old.y & 0xffffu)), a3 = slot(c3, c4 != c3, (int)(int16_t)(old.y >> 16));
+      w2[q] = make_uint2(((u32)a0 & 0xffffu) | ((u32)a1 << 16), ((u32)a2 & 0xffffu) | ((u32)a3 << 16));
+    }
+    for (uint32_t i = 4 * n4 + threadIdx.x; i < b.Ncb; i += RM_THREADS) {      // tail (Ncb mod 4), or everything when unaligned
+      const uint32_t c = cnt[i];
+      w[i] = (int16_t)slot(c, cnt[i + 1] != c, (int)w[i]);
     }
     return;
   }
