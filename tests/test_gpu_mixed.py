@@ -101,3 +101,28 @@ def test_random_mixed_batch(capi, seed):
             got = pool.read(slot, Ncb) if slot is not None else w_gpu[:Ncb]
             assert np.array_equal(got, w_o[:Ncb]), (i, kind, "HARQ buffer")
     pool.close()
+
+
+def test_recycled_handle_after_front_end_batch_then_all_invalid_batch(capi):
+    """handles are pooled; a batch whose every block is rejected returns early from submit() and must not leave
+    the previous batch's front-end bookkeeping behind (wait() would copy a stale HARQ buffer into the caller's w)."""
+    from oracle import chain
+    tb = chain.make_tb(7736, 14400, 4, seed=2, sigma_over_A=0.5)
+    rx = chain.rx_tb(tb, 4, downlink=False)
+    blocks, off = [], 0
+    ws = [np.zeros(3 * 3936, dtype=np.int16) for _ in range(2)]
+    for r in range(2):
+        e = tb["e"][off:off + tb["E"][r]]
+        off += tb["E"][r]
+        blocks.append({"y": e, "K": 3904, "max_iterations": 4, "crc_type": 1,
+                       "dematch": {"G": 14400, "C": 2, "r": r, "rvidx": 0, "clear": 1, "Qm": 4, "w": ws[r]}})
+    outs, status = capi.decode_batch(blocks)                      # front-end batch with host-owned w
+    assert status == rx["status"] and all(np.array_equal(ws[r], rx["w"][r]) for r in range(2))
+    canary = [np.full(3 * 3936, 1234, dtype=np.int16) for _ in range(2)]
+    bad = [{"y": np.zeros(3 * 3904 + 12, dtype=np.int16), "K": 3900, "max_iterations": 4, "crc_type": 1,
+            "dematch": {"G": 14400, "C": 2, "r": r, "rvidx": 0, "clear": 1, "Qm": 4, "w": canary[r]}} for r in range(2)]
+    outs, status = capi.decode_batch(bad)                         # every block illegal: nothing reaches the GPU
+    assert status == [255, 255]
+    assert all((c == 1234).all() for c in canary), "a stale HARQ buffer was written back"
+    outs, status = capi.decode_batch(blocks)                      # and the handle still works
+    assert status == rx["status"]
