@@ -618,9 +618,12 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
         if dist is not None:
             dist.barrier()
 
-    def prepare(owner, dt_np, fmt):
+    def prepare(owner, dt_np, fmt, ul=False):
         """two lanes (descriptor sets with their own output buffers and HARQ pool) over one page-locked input buffer, so
-        that two batches can be in flight: consecutive subframe batches belong to different HARQ processes"""
+        that two batches can be in flight: consecutive subframe batches belong to different HARQ processes.
+        ul: the input is the demodulator's soft bits of the whole allocation (lte_eNB_pusch_vars->llr, 1 HARQ-ACK bit
+        multiplexed in), the uplink front end runs on the GPU (oai_ul_front_t) and the transport blocks come back assembled
+        (oai_turbo_submit_tbs; no per-block bytes cross the link)"""
         mine = [i for i, r in enumerate(owner) if r == rank]
         n_ue = len(mine)
         n = n_ue * Cb
@@ -649,14 +652,41 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
                     d.harq_slot = i
                     d.in_fmt = fmt
             ln["descs"] = descs
+            if ul:
+                tb_bytes = Cb * (K // 8) - 3 * Cb
+                ln["b"] = capi.PinnedArray((max(n_ue, 1), tb_bytes), np.uint8)
+                ln["ret"] = np.zeros(max(n_ue, 1), dtype=np.uint8)
+                ln["oack"] = np.zeros((max(n_ue, 1), 2), dtype=np.uint8)
+                ln["ufs"] = (capi.UlFront * max(n_ue, 1))()
+                ln["tbs"] = (capi.TbDesc * max(n_ue, 1))()
+                for u in range(n_ue):
+                    f = ln["ufs"][u]
+                    f.llr, f.llr_fmt, f.c_init = base + u * G * st["isz"], fmt, (0x1234 << 14) + (3 << 9) + (mine[u] % 504)
+                    f.Qm, f.Ncp, f.O_ACK, f.O_RI, f.bundling, f.Nbundled, f.Cmux = Qm, 0, 1, 0, 0, 1, 12
+                    f.Qprime_RI, f.Qprime_ACK, f.Qprime_CQI, f.Hprime = 0, ul_sizes["Qprime_ACK"], 0, ul_sizes["Hprime"]
+                    f.o_ACK = ln["oack"].ctypes.data + 2 * u
+                    t = ln["tbs"][u]
+                    t.first_cb, t.C, t.uplink = u * Cb, Cb, 1
+                    t.b, t.b_capacity, t.ret = ln["b"].array.ctypes.data + u * tb_bytes, tb_bytes, ln["ret"].ctypes.data + u
+                    t.ul_front = C.pointer(f)
+                    for r in range(Cb):
+                        descs[u * Cb + r].in_ = None
+                        descs[u * Cb + r].decoded_bytes = None
+                        descs[u * Cb + r].in_fmt = 0
             st["lanes"].append(ln)
+        st["ul"] = ul
         return st
 
     def submit(st, lane):
         if st["n"] == 0:
             return None
         h = C.c_void_p()
-        if capi.lib.oai_turbo_submit_batch(st["lanes"][lane]["descs"], st["n"], 0, gpu, C.byref(h)):
+        ln = st["lanes"][lane]
+        if st["ul"]:
+            rc = capi.lib.oai_turbo_submit_tbs(ln["descs"], st["n"], ln["tbs"], st["n_ue"], 0, gpu, C.byref(h))
+        else:
+            rc = capi.lib.oai_turbo_submit_batch(ln["descs"], st["n"], 0, gpu, C.byref(h))
+        if rc:
             raise SystemExit("bench.py: multicell_ul submit failed: " + capi.last_error())
         return h
 
@@ -681,10 +711,14 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
         for ln in st["lanes"]:
             ln["pool"].close()
 
+    rc, ul_sizes = capi.ulsch_control_sizes(0, 1, 0, 1200, 12, 40, 40, 16, Cb * K, 100, Qm, 12)     # 1 HARQ-ACK bit, no RI / CQI
+    if rc or ul_sizes["G"] != G:
+        raise SystemExit("bench.py: unexpected uplink control sizes %s" % ul_sizes)
     res = {}
-    for name, dt_np, fmt in (("e_int16", np.int16, 0), ("e_int8", np.int8, 1)):
+    for name, dt_np, fmt, ul in (("e_int16", np.int16, 0, False), ("e_int8", np.int8, 1, False),
+                                 ("llr_int16_ul_front", np.int16, 0, True), ("llr_int8_ul_front", np.int8, 1, True)):
         owner = sharding.assign_by_cell(cell_of, world)
-        st = prepare(owner, dt_np, fmt)
+        st = prepare(owner, dt_np, fmt, ul)
         timed(st, 4)                                                # untimed: both batch objects are created and warm
         weights = None
         if world > 1:
@@ -694,7 +728,7 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
                 owner = sharding.assign_by_cell(cell_of, world, weights=weights)
                 close(st)
                 del st
-                st = prepare(owner, dt_np, fmt)
+                st = prepare(owner, dt_np, fmt, ul)
                 timed(st, 4)
         dt = timed(st, args.steps)
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -704,16 +738,23 @@ def run_multicell_ul(args, capi, rank, world, dist, gpu):
         n, n_ue, isz = st["n"], st["n_ue"], st["isz"]
         if n and not all((ln["status"][:n] == MAX_ITER + 1).all() for ln in st["lanes"]):
             raise SystemExit("bench.py: multicell_ul noise-regime blocks must report status 7")
+        if ul and n and not all((ln["ret"][:n_ue] == MAX_ITER + 1).all() for ln in st["lanes"]):
+            raise SystemExit("bench.py: multicell_ul transport blocks of pure noise must report ret 7")
         counts = [sum(1 for r in owner if r == k) * Cb for k in range(world)]
         res[name] = {"value": cells * S * Cb * K * args.steps / dt / 1e6, "unit": "Mbit/s", "ms_per_step": 1e3 * dt / args.steps,
-                     "h2d_bytes_per_step_this_gpu": n_ue * G * isz, "d2h_bytes_per_step_this_gpu": n * (K // 8 + 1),
+                     "h2d_bytes_per_step_this_gpu": n_ue * G * isz,
+                     "d2h_bytes_per_step_this_gpu": (n_ue * (Cb * (K // 8) - 3 * Cb + 8) + n) if ul else n * (K // 8 + 1),
                      "h2d_gbs_this_gpu": n_ue * G * isz * args.steps / dt / 1e9, "blocks_per_gpu": counts,
                      "rank_weights": None if weights is None else [round(w, 3) for w in weights], "in_flight": 2}
         close(st)
         del st
     res["config"] = {"workload": "BASELINE configs[3]: %d cells x %d subframes x (100 PRB MCS16 = 5 x K=6144, E=11520), noise regime, "
                                  "%d iterations; cells -> GPUs by sharding.assign_by_cell (weighted by each rank's measured rate "
-                                 "when N > 1), one HARQ pool per GPU, page-locked e in, bytes out" % (cells, S, MAX_ITER),
+                                 "when N > 1), one HARQ pool per GPU, page-locked soft bits in, bytes out.  e_*: rate-matched soft bits e per code "
+                                 "block (what ulsch_decoding.c:1259 hands to lte_rate_matching_turbo_rx) -> decoded code blocks; "
+                                 "llr_*_ul_front: the demodulator's soft bits of the allocation (1 HARQ-ACK bit multiplexed in) -> uplink "
+                                 "front end on the GPU -> assembled transport blocks + return values (the whole data path of "
+                                 "ulsch_decoding.c:600-1409 in one call)" % (cells, S, MAX_ITER),
                      "blocks_total": cells * S * Cb,
                      "scaling": "weak (64 cells fixed; subframes batched per step = %d x n_gpus)" % args.mc_subframes,
                      "api": "oai_turbo_submit_batch(dematch_enable, harq_pool, gpu) + oai_turbo_wait per step, two batches in flight"}

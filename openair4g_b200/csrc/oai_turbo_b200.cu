@@ -360,13 +360,15 @@ struct Batch {
     cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ckpt); cudaFree(d_batch_max); cudaFree(d_active); cudaFree(d_nactive);
     d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ckpt = nullptr; d_batch_max = nullptr; d_active = nullptr; d_nactive = nullptr;
   }
-  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
+  // staged: page-locked copy of m.data() (asynchronous transfer), or nullptr: from h_meta (pageable; the call then blocks
+  // until the stream reaches the copy)
+  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st, const void* staged = nullptr) {
     h_meta = m;
     n = (int)m.size();
     max_iter = 0;
     cur_max_K = 40;
     for (auto& x : m) { if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter); cur_max_K = std::max<int>(cur_max_K, x.K); }
-    CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_meta, staged ? staged : (const void*)h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
   // enqueue the whole 16-bit decode of blocks [lo, lo+cnt) (cnt < 0: all); returns #kernels launched or <0.
@@ -527,12 +529,12 @@ struct Batch8 {
     cudaFree(d_meta); cudaFree(d_state); cudaFree(d_ws); cudaFree(d_ck);
     d_meta = nullptr; d_state = nullptr; d_ws = nullptr; d_ck = nullptr; cap = 0;
   }
-  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st) {
+  int set_meta(const std::vector<CbMeta>& m, cudaStream_t st, const void* staged = nullptr) {
     h_meta = m;
     n = (int)m.size();
     max_iter = 0;
     for (auto& x : m) if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter);
-    CU(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_meta, staged ? staged : (const void*)h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
   std::vector<Batch::GraphEntry> graphs;                      // small batches: cached launch graphs, see Batch::decode16
@@ -708,8 +710,44 @@ static Scratch& scratch_here() {
   return t_scratch_set.per_dev[dev];
 }
 
+// Page-locked staging for the metadata arrays that are copied LATE in submit(): the uplink front-end list (behind the
+// allocations' soft-bit copy) and the transport-block lists (behind the whole decode).  cudaMemcpyAsync from PAGEABLE
+// memory blocks the host until the stream reaches the copy, which made submit() synchronous for those batches (measured:
+// 12 ms of a 17 ms submit for 8 192 uplink allocations, and no overlap between two batches in flight).  From this arena
+// the copies are asynchronous.
+// The block / rate-matching lists copied at the START of submit() deliberately stay pageable: that copy returns when the
+// copy engine has finished the PREVIOUS batch's inputs, i.e. it paces a caller that keeps two batches in flight.  Making
+// it asynchronous as well was measured and is worse (e feed, two in flight, same box: 13.8 -> 9.5 Gbit/s int16, 19.0 ->
+// 16.7 int8: with everything of batch i+1 enqueued while batch i is still copying, the two batches' parts interleave on
+// the GPU and both finish late), also with an explicit event wait in its place (13.4 / 16.8).
+struct PinnedArena {
+  char* p = nullptr;
+  size_t cap = 0, used = 0;
+  int reset(size_t need) {                   // call while no copy of this batch object is in flight
+    used = 0;
+    if (need > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      const size_t want = need + (need >> 2) + 4096;
+      CU(cudaMallocHost(&p, want));
+      cap = want;
+    }
+    return 0;
+  }
+  const void* put(const void* src, size_t n) {
+    used = (used + 15) & ~(size_t)15;
+    if (used + n > cap || getenv("OAI_TURBO_NO_ARENA")) return src;          // (cannot happen with the bound computed in submit(); pageable fallback)
+    void* dst = p + used;
+    memcpy(dst, src, n);
+    used += n;
+    return dst;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = used = 0; }
+};
+
 // ---- host-buffer batches: pinned staging + one stream per batch object ---------------
 struct HostBatch {
+  PinnedArena arena;
   Batch b;
   Batch8 b8;                       // 8-bit decoder blocks of the same submit (placed after the 16-bit ones)
   int cap8_blocks = 0, cap8_K = 0, n16 = 0;
@@ -925,6 +963,7 @@ struct HostBatch {
     return 0;
   }
   void release() {
+    arena.release();
     b.release();
     b8.release(); cap8_blocks = cap8_K = 0; cap_status = 0;
     if (h_e) cudaFreeHost(h_e);
@@ -1029,6 +1068,11 @@ struct HostBatch {
     }
     cqi_bytes = ul_cqi_b;
     static const bool trace = getenv("OAI_TURBO_TRACE") != nullptr;
+    const auto t_sub0 = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {                        // OAI_TURBO_TRACE: host time spent in submit() so far
+      if (trace) fprintf(stderr, "[trace %p] submit +%.2f ms: %s\n", (void*)this,
+                         1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sub0).count(), what);
+    };
     // handles are recycled: nothing of the previous batch may survive an early return below (wait() walks these)
     order.clear(); rm.clear(); rm_desc.clear(); gseq.clear(); direct_out = false;
     int Kmax = 40;
@@ -1070,12 +1114,17 @@ struct HostBatch {
       in_off[i] = in_hw;  in_hw += (size_t)3 * d.K + 12;
       out_off[i] = (uint32_t)out_b; out_b += ((size_t)(d.K >> 3) + 15) & ~(size_t)15;
     }
+    phase("descriptors checked and ordered");
     DevCtx* dctx;
     int rc = ctx_get(gpu, &dctx);
     if (rc) return rc;
     DevGuard guard;                                          // the caller's current device is restored on every return path
     if (guard.enter(dctx->dev)) return fail(-100, "cannot select CUDA device %d", dctx->dev);
     rc = ensure(dctx, std::max(n16, 1), Kmax, in_hw, out_b, n - n16, Kmax8);
+    if (rc) return rc;
+    // upper bound of everything that goes through the metadata arena (see PinnedArena)
+    rc = arena.reset((size_t)n * (sizeof(CbMeta) + sizeof(RmBlock) + sizeof(GoldSeq) + 48) + (size_t)ncb * sizeof(TbBlk) +
+                     (size_t)ntb * (sizeof(TbMeta) + sizeof(UlFrontDev) + sizeof(GoldSeq) + 64) + 4096);
     if (rc) return rc;
     if (trace) { for (auto& e : ev) if (!e) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
     // host->device: runs of blocks that are contiguous in the caller's memory go with one copy;
@@ -1200,6 +1249,7 @@ struct HostBatch {
         rm.push_back(rb); rm_desc.push_back(order[i]);
       }
     }
+    phase("block metadata and rate-matching parameters");
     // soft bits of rm blocks [jlo, jhi): one copy per run that is contiguous in the caller's memory, staged only if pageable
     auto copy_e_runs = [&](size_t jlo, size_t jhi, cudaStream_t cs) -> int {
       for (size_t j = jlo; j < jhi;) {
@@ -1232,6 +1282,12 @@ struct HostBatch {
       ++g_launches;
       if (!fuse_deint) { k_deint<<<cnt, RM_THREADS, deint_smem, fs>>>(d_rm + jlo, cnt, d_w, d_in, 0, hp); ++g_launches; }
     };
+    // block metadata first (pageable source: see PinnedArena for why), before any bulk input copy of this batch
+    CU(cudaMemsetAsync(d_out, 0, out_b, st));
+    if (n16 > 0) {
+      rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
+      if (rc) return rc;
+    }
     if (!rm.empty()) {
       rc = ensure_rm(e_hw, w_hw, (int)rm.size());
       if (rc) return rc;
@@ -1247,17 +1303,23 @@ struct HostBatch {
         for (size_t u = 0; u < ulf.size(); ++u) ulf[u].gold_off = gseq[ulf_seq[u]].off;
         if ((int)gseq.size() > cap_gseq) { if (d_gseq) cudaFree(d_gseq); cap_gseq = (int)gseq.size(); CU(cudaMalloc(&d_gseq, sizeof(GoldSeq) * cap_gseq)); }
         if (words > cap_gold) { if (d_gold) cudaFree(d_gold); cap_gold = words; CU(cudaMalloc(&d_gold, sizeof(uint32_t) * cap_gold)); }
-        CU(cudaMemcpyAsync(d_gseq, gseq.data(), sizeof(GoldSeq) * gseq.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_gseq, arena.put(gseq.data(), sizeof(GoldSeq) * gseq.size()), sizeof(GoldSeq) * gseq.size(), cudaMemcpyHostToDevice, st));
         k_gold<<<((int)gseq.size() + 63) / 64, 64, 0, st>>>(d_gseq, (int)gseq.size(), d_gold);
         ++g_launches;
       }
+      // (after the Gold offsets are known, before the uplink front end's bulk copy)
+      CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
       if (!ulf.empty()) {
         // uplink front ends: the allocations' soft bits go over, k_ul_front leaves e[] in the batch's soft-bit pool
         rc = ensure_ulf((int)ulf.size(), ul_llr_b, std::max<size_t>(ul_cqi_b, 16));
         if (rc) return rc;
-        for (size_t u = 0; u < ulf.size(); ++u) {
-          const size_t off = ((size_t)ulf[u].llr_off_hi << 32) | ulf[u].llr_off_lo;
-          const size_t nb = (size_t)ulf[u].Rp * ulf[u].Cmux * ulf[u].Qm * (ulf[u].llr_fmt ? 1 : 2);
+        // allocations that follow each other in the caller's memory (and in the pool) go over with one copy
+        auto llr_off = [&](size_t u) -> size_t { return ((size_t)ulf[u].llr_off_hi << 32) | ulf[u].llr_off_lo; };
+        auto llr_bytes = [&](size_t u) -> size_t { return (size_t)ulf[u].Rp * ulf[u].Cmux * ulf[u].Qm * (ulf[u].llr_fmt ? 1 : 2); };
+        for (size_t u = 0; u < ulf.size();) {
+          const size_t off = llr_off(u);
+          size_t nb = llr_bytes(u), v = u + 1;
+          while (v < ulf.size() && (const char*)ulf_desc[v].llr == (const char*)ulf_desc[u].llr + nb && llr_off(v) == off + nb) { nb += llr_bytes(v); ++v; }
           cudaPointerAttributes at;
           const bool pinned = (cudaPointerGetAttributes(&at, ulf_desc[u].llr) == cudaSuccess) && at.type == cudaMemoryTypeHost;
           cudaGetLastError();
@@ -1268,14 +1330,14 @@ struct HostBatch {
             memcpy(h_llr + off, ulf_desc[u].llr, nb); src = h_llr + off;
           }
           CU(cudaMemcpyAsync(d_llr + off, src, nb, cudaMemcpyHostToDevice, st));
+          u = v;
         }
-        CU(cudaMemcpyAsync(d_ulf, ulf.data(), sizeof(UlFrontDev) * ulf.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_ulf, arena.put(ulf.data(), sizeof(UlFrontDev) * ulf.size()), sizeof(UlFrontDev) * ulf.size(), cudaMemcpyHostToDevice, st));
         k_ul_front<<<(int)ulf.size(), ULF_THREADS, 0, st>>>(d_ulf, (int)ulf.size(), d_llr, d_e, d_gold, d_cqi, d_ulfout);
         ++g_launches;
         CU(cudaMemcpyAsync(h_ulfout, d_ulfout, sizeof(UlFrontOut) * ulf.size(), cudaMemcpyDeviceToHost, st));
         if (ul_cqi_b) CU(cudaMemcpyAsync(h_cqi, d_cqi, ul_cqi_b, cudaMemcpyDeviceToHost, st));
       }
-      CU(cudaMemcpyAsync(d_rm, rm.data(), sizeof(RmBlock) * rm.size(), cudaMemcpyHostToDevice, st));
       if (!fe_parts) {
         rc = copy_e_runs(0, rm.size(), st);
         if (rc) return rc;
@@ -1290,6 +1352,7 @@ struct HostBatch {
         if (w_hw) CU(cudaMemcpyAsync(h_w, d_w, w_hw * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
       }
     }
+    phase("front-end tables, soft-bit copies enqueued");
     // device->host: when the callers' decoded_bytes are laid out like the device output (back to back,
     // every block decoded) in page-locked memory, the result is copied straight into them
     direct_out = false;
@@ -1309,11 +1372,6 @@ struct HostBatch {
       want_cb_out = false;                                   // no descriptor wants its block's bytes (transport-block outputs only)
       for (int i = 0; i < n && !want_cb_out; ++i) want_cb_out = descs[order[i]].decoded_bytes != nullptr;
       if (!direct_out && want_cb_out) { rc = ensure_stage_out(); if (rc) return rc; }
-    }
-    CU(cudaMemsetAsync(d_out, 0, out_b, st));
-    if (n16 > 0) {
-      rc = b.set_meta(std::vector<CbMeta>(meta.begin(), meta.begin() + n16), st);
-      if (rc) return rc;
     }
     if (parts == 1) {
       rc = enqueue_inputs(0, n, st);
@@ -1379,6 +1437,7 @@ struct HostBatch {
       if (pack_s > 0 && pack_bytes / pack_s / 1e9 < pack_min_gbs()) g_pack_pause.store(16);
       if (trace && pack_s > 0) fprintf(stderr, "[trace %p] narrow feed: packed %.0f MB at %.1f GB/s\n", (void*)this, pack_bytes / 1e6, pack_bytes / pack_s / 1e9);
     }
+    phase("parts enqueued");
     if (trace) cudaEventRecord(ev[1], st);
     if (n16 > 0 && parts == 1) {
       rc = fuse_deint ? b.decode16(d_in, d_out, d_status, st, 0, -1, 0, d_rm, d_w, hp) : b.decode16(d_in, d_out, d_status, st);
@@ -1415,8 +1474,8 @@ struct HostBatch {
       }
       rc = ensure_tb((int)tbs.size(), (int)tb_blk.size(), pool_b);
       if (rc) return rc;
-      CU(cudaMemcpyAsync(d_tbmeta, tb_meta.data(), sizeof(TbMeta) * tb_meta.size(), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_tbblk, tb_blk.data(), sizeof(TbBlk) * tb_blk.size(), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_tbmeta, arena.put(tb_meta.data(), sizeof(TbMeta) * tb_meta.size()), sizeof(TbMeta) * tb_meta.size(), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_tbblk, arena.put(tb_blk.data(), sizeof(TbBlk) * tb_blk.size()), sizeof(TbBlk) * tb_blk.size(), cudaMemcpyHostToDevice, st));
       k_tb_assemble<<<(int)tbs.size(), TB_THREADS, 0, st>>>(d_tbmeta, (int)tbs.size(), d_tbblk, d_out, d_status, d_tbpool, d_tbres);
       ++g_launches;
       CU(cudaMemcpyAsync(h_tbpool, d_tbpool, pool_b, cudaMemcpyDeviceToHost, st));
@@ -1432,6 +1491,7 @@ struct HostBatch {
     }
     CU(cudaMemcpyAsync(h_status, d_status, n, cudaMemcpyDeviceToHost, st));
     if (trace) cudaEventRecord(ev[3], st);
+    phase("done");
     return 0;
   }
 
