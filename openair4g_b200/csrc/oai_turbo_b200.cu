@@ -37,6 +37,8 @@ static const uint16_t kQpp[188][2] = {
 
 static std::atomic<unsigned long long> g_launches{0};
 static const bool g_use_graphs = [] { const char* e = getenv("OAI_TURBO_NO_GRAPHS"); return !(e && e[0] == '1'); }();
+// tracked fast passes beyond the a-priori guard (td16_map.cuh); OAI_TURBO_NO_TRACK=1 restores guard-or-exact
+static const int g_track = [] { const char* e = getenv("OAI_TURBO_NO_TRACK"); return (e && e[0] == '1') ? 0 : 1; }();
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
@@ -346,8 +348,8 @@ struct Batch {
     CU(cudaMalloc(&d_ws, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMalloc(&d_ckpt, sizeof(u32) * ckpt_words * ncb));
     CU(cudaMalloc(&d_batch_max, sizeof(int) * MAX_PARTS));
-    CU(cudaMalloc(&d_active, sizeof(int) * ncb * 2));            // two lists (current / next)
-    CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 4));     // per part: two lists x two class counters
+    CU(cudaMalloc(&d_active, sizeof(int) * ncb * 4));            // two lists (current / next) of 2 n entries per part (k_compact)
+    CU(cudaMalloc(&d_nactive, sizeof(int) * MAX_PARTS * 8));     // per part: two lists x three class counters (+ pad)
     CU(cudaMemset(d_ws, 0, sizeof(int16_t) * slot_hw * ncb));
     CU(cudaMemset(d_state, 0, sizeof(CbState) * ncb));
     // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which does not order with the
@@ -425,8 +427,8 @@ struct Batch {
     int16_t* d_ws = this->d_ws + (long)lo * slot_hw;
     u32* d_ckpt = this->d_ckpt + (long)lo * ckpt_words;
     int* d_batch_max = this->d_batch_max + part;
-    int* act[2] = {this->d_active + lo, this->d_active + cap + lo};      // packed lists of running blocks
-    int* nact[2] = {this->d_nactive + 4 * part, this->d_nactive + 4 * part + 2};
+    int* act[2] = {this->d_active + 2 * lo, this->d_active + 2 * cap + 2 * lo};      // packed lists of running blocks
+    int* nact[2] = {this->d_nactive + 8 * part, this->d_nactive + 8 * part + 4};
     int cur = 0;
     if (status_dev) status_dev += lo;
     XchgArgs x{};
@@ -435,23 +437,33 @@ struct Batch {
     x.status_out = status_dev; x.iter = 0; x.guard_b = GUARD_B; x.batch_max = d_batch_max;
     x.active = nullptr; x.nactive = nullptr; x.nactive_next = nullptr;                           // k_demux16 sees all blocks
     x.rm = fe_rm ? fe_rm + lo : nullptr; x.w_pool = fe_w; x.harq_pool = fe_harq; x.in8 = in8;
-    L.zero_ints(nact[0], 2);
+    L.zero_ints(nact[0], 8);                              // list counters of both lists + the retry flag of this part
     L.zero_ints(d_batch_max, 1);
     MapArgs mp{};
     mp.meta = d_meta; mp.state = d_state; mp.ws = d_ws; mp.slot_hw = slot_hw; mp.A = A;
     mp.ckpt = d_ckpt; mp.ckpt_words = ckpt_words; mp.nblk = n; mp.guard_b = GUARD_B; mp.batch_max = d_batch_max;
     // packs the running blocks into list c (its counter is zero: memset above / k_x1_16) and makes it current
     auto compact_into = [&](int c) {
-      L.run(k_compact, dim3((n + COMPACT_THREADS - 1) / COMPACT_THREADS), dim3(COMPACT_THREADS), 0, (const CbState*)d_state, n, act[c], nact[c], (int)GUARD_B);
+      L.run(k_compact, dim3((n + COMPACT_THREADS - 1) / COMPACT_THREADS), dim3(COMPACT_THREADS), 0, (const CbState*)d_state, n, act[c], nact[c], (int)GUARD_B, (int)g_track);
       ++launches;
       mp.active = act[c]; mp.nactive = nact[c]; x.active = act[c]; x.nactive = nact[c]; x.nactive_next = nact[1 - c];
     };
-    const int map_grid = ((n + 7) * 4 + MAP_THREADS - 1) / MAP_THREADS;     // + the padding between the two classes of the list
+    int map_seq = 0;
+    const int map_grid = ((n + 14) * 4 + MAP_THREADS - 1) / MAP_THREADS;    // + the padding between the three classes of the list
     const size_t map_smem = MAP_SMEM_BYTES;
     auto map = [&](int sys_arr, int par_arr, int out_arr, int term, int iter, int upd) {
       mp.sys_arr = sys_arr; mp.par_arr = par_arr; mp.out_arr = out_arr; mp.term = term; mp.iter = iter; mp.upd = upd;
+      mp.track = g_track; mp.retry = 0; mp.force = 0; mp.retry_flag = nact[1] + 3; mp.seq = ++map_seq;
       prof.begin(1, st);
       L.run(k_map16<MAP_SEG>, dim3(map_grid), dim3(MAP_THREADS), map_smem, mp);
+      if (g_track) {
+        // the retry launch: blocks whose tracked pass failed its range certificate repeat the pass on the exact policy
+        // (every other warp returns at once: a few microseconds when nothing failed)
+        mp.retry = 1;
+        L.run(k_map16<MAP_SEG>, dim3(map_grid), dim3(MAP_THREADS), map_smem, mp);
+        mp.retry = 0;
+        ++launches;
+      }
       prof.end(st);
       ++launches;
     };
@@ -2070,7 +2082,10 @@ int oai_turbo_debug_map16(const int16_t* y, uint16_t K, int term, int policy, in
   mp.guard_b = policy == 1 ? 0x7fffffff : (policy == 2 ? -1 : GUARD_B);
   mp.sys_arr = ARR_S0; mp.par_arr = term ? ARR_P2 : ARR_P1; mp.out_arr = ARR_EXT; mp.term = term; mp.iter = 1; mp.upd = 0;
   mp.active = nullptr; mp.nactive = nullptr;
+  mp.track = (policy == 0 || policy == 4) ? g_track : 0;
+  mp.force = (policy == 4) ? 3 : 0;                          // 4: force the tracked fast pass (falls back through the retry launch)
   k_map16<MAP_SEG><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp);
+  if (mp.track || policy == 4) { mp.retry = 1; k_map16<MAP_SEG><<<1, MAP_THREADS, MAP_SMEM_BYTES, hb.st>>>(mp); ++g_launches; }
   g_launches += 2;
   std::vector<int16_t> tmp(b.A);
   CU(cudaMemcpyAsync(tmp.data(), b.d_ws + (long)ARR_EXT * b.A, sizeof(int16_t) * b.A, cudaMemcpyDeviceToHost, hb.st));

@@ -59,8 +59,13 @@ struct MapArgs {
   int guard_b;           // fast path allowed when max(max_sys,max_in) + max_in <= guard_b
   const int* batch_max;  // max |y| over the batch: <= 127 selects the int8 parity / s0 copies
   int upd;               // 1: write ext = (ext (-) sys) (+) s0 (the feedback step, reference :1354-1375)
-  const int* active;     // compacted two-ended list of running blocks (k_compact) or nullptr = all nblk blocks
-  const int* nactive;    // its two counters
+  const int* active;     // compacted list of running blocks (k_compact) or nullptr = all nblk blocks
+  const int* nactive;    // its three counters (fast / tracked / exact class)
+  int retry;             // 1: the retry launch -- only blocks whose tracked pass failed run, on the exact policy
+  int* retry_flag;       // a failing tracked pass stores `seq` here; the retry launch returns at once unless it finds it
+  int seq;               // number of this MAP pass within the decode (1, 2, ...); the flag is zeroed when the decode starts
+  int track;             // 0: no tracked passes (blocks beyond the guard go to the exact policy, the round-1 behaviour)
+  int force;             // test hook: 0 = decide, 1 = untracked fast, 2 = exact, 3 = tracked fast
 };
 
 __device__ __forceinline__ u32 pick4(const uint4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
@@ -627,6 +632,39 @@ __device__ __forceinline__ void renorm(u32 (&a)[8]) {
   for (int s = 1; s < 8; ++s) a[s] = __vadd2(a[s], n);
 }
 
+// ---- a-posteriori range check ("tracked" fast pass) -----------------------------------------------------------------
+// The guard in front of the fast path is a worst-case bound (spread of a metric vector <= 10 Gmax + 128); measured spreads
+// are ~2.5 Gmax (coded signals at A = 256: sum of the two spreads + 2 Gmax = 18 000 in the last pass of a decode, where
+// the guard's bound is far beyond int16, and the reference never saturates).  A tracked pass runs the fast path with a
+// renormalisation every step and records what actually happened:
+//   sp_a / sp_b : the largest spread max_s - min_s of any alpha / beta vector of the pass (spreads are invariant to the
+//                 fast path's shifts, so they ARE the reference's spreads as long as nothing has wrapped),
+//   ext range   : the largest |LLR| before the feedback step.
+// Certificate, evaluated at the end of the pass (k_map16):  sp_a + sp_b + M <= 32767  with M = B + 1 >= 2 Gmax, |X|,|Y|,|Z|.
+// It implies (a) the reference saturated nowhere in this pass -- candidates a + g >= -(spread + Gmax), normalised values
+// n - max >= -(spread + 2 Gmax), LLR sums >= -(sp_a + sp_b + Gmax), LLR within +-(sp_a + sp_b + 2 Gmax) -- so its result is
+// exact integer arithmetic; and (b) the fast path wrapped nowhere: after the per-step renormalisation |a'| <= spread, so
+// every candidate, sum and LLR is within sp_a + sp_b + M.  Soundness of reading the spreads off possibly wrapped values:
+// let k* be the first step whose computation wraps or saturates; the vector entering it has its TRUE spread recorded, and
+// that spread (together with the other sweep's and M) already violates the certificate, because a true spread within the
+// bound makes step k* safe.  Spreads grow by at most 2 Gmax <= M per step, so the first unsafe vector is still
+// representable (<= 32767 + M - M) and is recorded correctly.  With the feedback step fused in, max|LLR| + Ms + Mi <= 32767
+// is checked as well (the reference's two saturating operations there).
+// A pass whose certificate fails has written garbage; its inputs are intact, so the block is flagged and the pass is
+// repeated on the exact policy by the retry launch that follows every k_map16 launch.
+struct Trk { u32 sp_a, sp_b, emx, emn; };
+__device__ __forceinline__ u32 vec_spread(const u32 (&a)[8]) {
+  const u32 mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(a[0], a[1], a[2]), a[3], a[4]), __vimax3_s16x2(a[5], a[6], a[7]));
+  const u32 mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(a[0], a[1], a[2]), a[3], a[4]), __vimin3_s16x2(a[5], a[6], a[7]));
+  return __vsub2(mx, mn);                      // per halfword, as unsigned 16-bit
+}
+template <bool TRACK>
+__device__ __forceinline__ void renorm_ta(u32 (&a)[8], Trk& tk) { if (TRACK) tk.sp_a = __vmaxu2(tk.sp_a, vec_spread(a)); renorm(a); }
+template <bool TRACK>
+__device__ __forceinline__ void renorm_tb(u32 (&b)[8], Trk& tk) { if (TRACK) tk.sp_b = __vmaxu2(tk.sp_b, vec_spread(b)); renorm(b); }
+template <bool TRACK>
+__device__ __forceinline__ void track_ext(u32 x, Trk& tk) { if (TRACK) { tk.emx = __vmaxs2(tk.emx, x); tk.emn = __vmins2(tk.emn, x); } }
+
 // shared-memory alpha buffer of the fast path: NE entries of 8 packed states per thread
 // (two conflict-free 128-bit rows per entry)
 struct FastSmem {
@@ -661,11 +699,15 @@ struct FastSmem {
 //   The registers of chunk j are refilled with chunk j of the NEXT segment as soon as the beta sweep
 //   has consumed them (chunk 0, which is needed first and freed last, goes through a spare set).
 // P8: parity (and s0) are read from the int8 copies: chunk c of this thread = 8 bytes at par8[c*4]
-template <int S, int PM, bool UPD, bool P8>
+template <int S, int PM, bool UPD, bool P8, bool TRACK = false>
 __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict__ par, const u32* __restrict__ s0,
                               u32* __restrict__ ext, u32* ck, int W, int t, unsigned gmask, const int16_t* Tv,
-                              unsigned char* smem, int tid) {
+                              unsigned char* smem, int tid, Trk* trk = nullptr) {
   static_assert(S == 16, "steady-state segment = 4 chunks of 4 steps");
+  static_assert(!TRACK || PM == 0, "a tracked pass renormalises (and records) every step");
+  Trk tk;
+  tk.sp_a = 0x00800080u;                                        // the start vectors (0, -128, ...) have spread 128
+  tk.sp_b = 0; tk.emx = 0x80008000u; tk.emn = 0x7fff7fffu;
   constexpr int NCH = S / 4;
   constexpr int HS = MAP_ABUF_ENTRIES;                         // boundary code works on sub-segments of HS steps
 #ifndef MAP_PF_SEGS
@@ -719,13 +761,13 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     for (int j = 0; j < NCH; ++j) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm(a);
+        if (((j * 4 + q) & PM) == 0 && (j | q) != 0) renorm_ta<TRACK>(a, tk);
         alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
       }
       const int cn = (seg + 1) * NCH + j;
       if (cn < nchunk) { sb[j] = __ldg(sys4 + cn * 4); pb[j] = ldp(cn); }
     }
-    renorm(a);                                                 // checkpoints are stored normalised
+    renorm_ta<TRACK>(a, tk);                                   // checkpoints are stored normalised
   }
   if (nfull < nseg) {                                          // partial last segment
     ckpt_put(ck + nfull * 32, a);
@@ -735,11 +777,12 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       for (int q = 0; q < 4; ++q) {
         const int e = j * 4 + q;
         if (nfull * S + e < W) {
-          if ((e & PM) == 0 && e != 0) renorm(a);
+          if ((e & PM) == 0 && e != 0) renorm_ta<TRACK>(a, tk);
           alpha_fast(a, fconst(pick4(sb[j], q), pk(pb[j], q)));
         }
       }
     }
+    if (TRACK) renorm_ta<TRACK>(a, tk);                        // the final vector of the lane is recorded too
   }
 
   // ---- alpha re-run seed (kept in the checkpoint pool, slot nseg) -----------------------
@@ -756,9 +799,10 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #pragma unroll
       for (int s = 0; s < 8; ++s) a[s] = seed[s];
       for (int k = 0; k < W; ++k) {
-        if ((k & PM) == 0) renorm(a);
+        if ((k & PM) == 0) renorm_ta<TRACK>(a, tk);
         alpha_fast(a, c1(k));
       }
+      if (TRACK) renorm_ta<TRACK>(a, tk);
     }
   }
 
@@ -769,6 +813,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
     b[s] = a[s];
     if (t == 3) b[s] = (a[s] & 0xffffu) | ((u32)(uint16_t)Tv[s] << 16);
   }
+  if (TRACK) tk.sp_b = __vmaxu2(tk.sp_b, vec_spread(b));          // lane 7 starts from the tail metrics
 
   // ---- backward sweep, pass 1 -----------------------------------------------------------
   // loads the inputs of a whole segment into the chunk registers and its checkpoint into a[]
@@ -813,7 +858,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
         if (seg == 0 && half == 0) {               // alpha[0..5] come from the re-run chain
           ckpt_get(ck + nseg * 32, a);
           for (int k = 0; k <= RERUN_STEPS && k < kb; ++k) {
-            if ((k & PM) == 0) renorm(a);
+            if ((k & PM) == 0) renorm_ta<TRACK>(a, tk);
             sm.put(k, tid, a);
             if (k < RERUN_STEPS) alpha_fast(a, c1(k));
           }
@@ -823,11 +868,12 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
           if (k <= W - 7) {                        // steps whose beta[k+1] is not replaced by the re-run
             sm.get(k - ka, tid, a);
             u32 x = ext_fast(a, b, c);
+            track_ext<TRACK>(x, tk);
             if (UPD) x = __vadd2(x, d1(k));
             ext[c4_word(k, 0)] = x;
           }
           beta_fast(b, c);
-          if ((k & PM) == 0) renorm(b);
+          if ((k & PM) == 0) renorm_tb<TRACK>(b, tk);
         }
       }
       loaded = false;
@@ -849,7 +895,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       ckpt_get(ck + nseg * 32, a);
 #pragma unroll
       for (int k = 0; k < RERUN_STEPS; ++k) {
-        if ((k & PM) == 0) renorm(a);
+        if ((k & PM) == 0) renorm_ta<TRACK>(a, tk);
         if ((k & 1) == 0) sm.put(k >> 1, tid, a);
         if (k < RERUN_STEPS - 1) alpha_fast(a, fconst(pick4(sb[k >> 2], k & 3), pk(pb[k >> 2], k & 3)));
       }
@@ -880,15 +926,18 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
           const u32 sve = pick4(sb[j], 2 * h), svo = pick4(sb[j], 2 * h + 1);
           const FC ce = fconst(sve, pk(pb[j], 2 * h)), co = fconst(svo, pk(pb[j], 2 * h + 1));
           alpha_fast(ao, ce);                                   // alpha[eo] from alpha[ee]
+          if (TRACK && seg == 0) tk.sp_a = __vmaxu2(tk.sp_a, vec_spread(ao));    // the odd entries of the re-run chain exist only here
           if ((eo & PM) == 0) renorm(ao);
           u32 xo = ext_fast(ao, b, co);
+          track_ext<TRACK>(xo, tk);
           if (UPD) xo = __vadd2(xo, __vsub2(pk(zb[j], 2 * h + 1), svo));
           beta_fast(b, co);
-          if ((eo & PM) == 0) renorm(b);
+          if ((eo & PM) == 0) renorm_tb<TRACK>(b, tk);
           u32 xe = ext_fast(ae, b, ce);
+          track_ext<TRACK>(xe, tk);
           if (UPD) xe = __vadd2(xe, __vsub2(pk(zb[j], 2 * h), sve));
           beta_fast(b, ce);
-          if ((ee & PM) == 0) renorm(b);
+          if ((ee & PM) == 0) renorm_tb<TRACK>(b, tk);
           e4[2 * h + 1] = xo; e4[2 * h] = xe;
         }
         *reinterpret_cast<uint4*>(ext + ((k0 >> 2) + j) * 16) = make_uint4(e4[0], e4[1], e4[2], e4[3]);
@@ -931,55 +980,69 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
       const FC c = c1(k);
       sm.get(k - kk0, tid, a);
       u32 x = ext_fast(a, b, c);
+      track_ext<TRACK>(x, tk);
       if (UPD) x = __vadd2(x, d1(k));
       ext[c4_word(k, 0)] = x;
       if (k >= W - RERUN_STEPS) {
         beta_fast(b, c);
-        if ((k & PM) == 0) renorm(b);
+        if ((k & PM) == 0) renorm_tb<TRACK>(b, tk);
       }
     }
   }
+  if (TRACK) *trk = tk;
 }
 
 #ifndef MAP_MAX_REGS
 #define MAP_MAX_REGS 168          // 6 CTAs (12 warps) per SM; measured against 128 / 144 / 184 / 200 / 216 / 243
 #endif
+// policy of one block for this pass: 16 / 4 / 1 = untracked fast pass with that renormalisation period (the a-priori guard
+// holds), -1 = tracked fast pass (beyond the guard, range check a posteriori), 0 = exact saturating policy
+constexpr int TRACK_CERT_LIMIT = 26000;   // of 32767: a tracked pass is attempted while the decoder's previous certificate was below this
+__device__ __forceinline__ int map_policy(const CbState& st, int guard_b, int track, int term) {
+  const int B = max(st.max_sys, st.max_in) + st.max_in, M = B + 1;
+  if (B <= guard_b) {
+    // no wrap needs (11 + 2P) * M + 276 <= 32767  (DESIGN.md "fast-path guard")
+    const int pmax = (32491 / M - 11) >> 1;
+    if (pmax >= 1) return pmax >= 16 ? 16 : (pmax >= 4 ? 4 : 1);
+  }
+  // beyond the guard: try the fast path with the a-posteriori certificate unless the block has failed one before, or its
+  // inputs alone (M >= 2 Gmax) leave no room for any spread
+  if (track && !(st.retry & 2) && M <= 16000 && st.cert[term] <= TRACK_CERT_LIMIT) return -1;
+  return 0;
+}
+
 template <int S>
 __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   extern __shared__ uint4 abuf[];
+  if (p.retry && p.retry_flag && *p.retry_flag != p.seq) return;      // nothing failed in the launch before this one
   const int tid = threadIdx.x;
   const int gt = blockIdx.x * MAP_THREADS + tid;
   const int t = gt & 3;
   int blk = gt >> 2;
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
-  if (p.active) {              // two-ended list: fast-policy blocks first (padded to whole warps), exact-policy blocks after
-    const int nf = p.nactive[0], nx = p.nactive[1], nfp = (nf + 7) & ~7;
+  if (p.active) {              // three classes, each padded to whole warps: fast from the front, tracked behind it, exact from the back
+    const int nf = p.nactive[0], nt = p.nactive[1], nx = p.nactive[2], nfp = (nf + 7) & ~7, ntp = (nt + 7) & ~7;
     if (blk < nf) blk = p.active[blk];
-    else if (blk >= nfp && blk - nfp < nx) blk = p.active[p.nblk - 1 - (blk - nfp)];
+    else if (blk >= nfp && blk - nfp < nt) blk = p.active[p.nblk + (blk - nfp)];          // (k_compact: tracked class at list[nblk + j])
+    else if (blk >= nfp + ntp && blk - nfp - ntp < nx) blk = p.active[p.nblk - 1 - (blk - nfp - ntp)];
     else blk = p.nblk;
   }
 
   bool active = false;
-  int W = 0, P = 64;           // P: largest renormalisation period this block's guard allows (0: exact path)
+  int W = 0, P = 64;           // P: see map_policy (64 = idle lane: does not constrain the warp)
   if (blk < p.nblk) {
     const CbMeta m = p.meta[blk];
     const CbState* st = &p.state[blk];
     active = (st->status == 0) && (m.flags & 1) && (p.iter <= m.max_iter);
+    if (p.retry) active = active && (st->retry & 1);
     W = m.W;
     if (active) {
-      // M bounds every branch constant |X|,|Y|,|Z| of this pass (tails included via max_in)
-      const int B = max(st->max_sys, st->max_in) + st->max_in;
-      const int M = B + 1;
-      if (B > p.guard_b) P = 0;
-      else {
-        // no wrap needs (11 + 2P) * M + 276 <= 32767  (DESIGN.md "fast-path guard")
-        const int pmax = (32491 / M - 11) >> 1;
-        P = pmax >= 16 ? 16 : (pmax >= 4 ? 4 : (pmax >= 1 ? 1 : 0));
-      }
+      P = p.retry ? 0 : map_policy(*st, p.guard_b, p.track, p.term);
+      if (p.force == 1) P = 1; else if (p.force == 2) P = 0; else if (p.force == 3 && !p.retry) P = -1;
     }
   }
-  // a warp carries 8 blocks: it runs the most conservative choice of its blocks (a shorter
-  // period, or the exact saturating policy, is valid for every block)
+  // a warp carries 8 blocks and runs ONE policy: the most conservative of its blocks (exact < tracked < shorter period <
+  // longer period; each is valid for every block that asked for a later one)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) P = min(P, __shfl_xor_sync(0xffffffffu, P, o));
   if (!active) return;
@@ -995,6 +1058,31 @@ __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
   const u32* s0 = reinterpret_cast<const u32*>(slot + (long)ARR_S0 * p.A) + t * 4;
   if (P == 0) {                                 // exact saturating policy, int16 arrays, 8-step segments
     map_pass<InvArith, MAP_ABUF_ENTRIES>(sys, par, s0, p.upd != 0, ext, ck, W, t, gmask, Tv, abuf, tid);
+    if (p.retry && t == 0) p.state[blk].retry = 2;          // done; this block stays on the exact policy
+    return;
+  }
+  if (P < 0) {                                  // tracked fast pass (int16 arrays, renormalisation every step)
+    Trk tk;
+    if (p.upd) map_pass_fast<S, 0, true, false, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid, &tk);
+    else       map_pass_fast<S, 0, false, false, true>(sys, par, s0, ext, ck, W, t, gmask, Tv, smem, tid, &tk);
+    // certificate of this block: maxima over its 4 threads (2 lanes each)
+    int sa = max((int)(tk.sp_a & 0xffffu), (int)(tk.sp_a >> 16)), sb = max((int)(tk.sp_b & 0xffffu), (int)(tk.sp_b >> 16));
+    int ex = max(max(lo16(tk.emx), hi16(tk.emx)), max(-lo16(tk.emn), -hi16(tk.emn)));
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      sa = max(sa, __shfl_xor_sync(gmask, sa, o, 4)); sb = max(sb, __shfl_xor_sync(gmask, sb, o, 4)); ex = max(ex, __shfl_xor_sync(gmask, ex, o, 4));
+    }
+    const CbState* st = &p.state[blk];
+    const int Ms = st->max_sys, Mi = st->max_in, M = max(Ms, Mi) + Mi + 1;
+    bool ok = (sa + sb + M <= 32767);
+    if (p.upd) ok = ok && (ex + Ms + Mi <= 32767);
+    if (t == 0) {
+      p.state[blk].cert[p.term] = sa + sb + M;
+      if (!ok) {                                    // repeat this pass on the exact policy (retry launch), and stay there
+        p.state[blk].retry = 3;
+        if (p.retry_flag) *p.retry_flag = p.seq;
+      }
+    }
     return;
   }
   // int8 copies of parity / s0 when the whole batch has |y| <= 127 (warp-uniform: one flag per batch)

@@ -56,41 +56,50 @@ struct XchgArgs {
 // packs its 1024 blocks (ascending) and reserves its range with one atomicAdd, so neighbouring list entries stay
 // neighbours in memory; k_x1_16 zeroes the counter of the list that is built next.
 constexpr int COMPACT_THREADS = 1024;
-// Two classes are kept apart so that a warp of the MAP kernel (8 blocks, one arithmetic policy per warp) does not mix
-// them: blocks whose guard allows the fast policy are packed from the FRONT of the list (count[0]), blocks that need the
-// exact saturating policy from the BACK (list[nblk-1-j], count[1]).  The class is taken from the maxima known when the
-// list is built (k_map16 re-derives the policy from the current ones, so this is grouping only, never correctness).
-__device__ __forceinline__ bool needs_exact_policy(const CbState& st, int guard_b) {
+// Three classes are kept apart so that a warp of the MAP kernel (8 blocks, one arithmetic policy per warp) does not mix
+// them: blocks whose guard allows the untracked fast pass are packed from the FRONT of the list (count[0]), blocks that get
+// the tracked fast pass right behind them (count[1]; the MAP kernel pads each class to whole warps), blocks on the exact
+// saturating policy from the BACK (list[nblk-1-j], count[2]).  The class is taken from the maxima known when the list is
+// built (k_map16 re-derives the policy from the current ones, so this is grouping only, never correctness).
+// class of a running block: 0 untracked fast, 1 tracked fast, 2 exact (mirrors map_policy in td16_map.cuh)
+__device__ __forceinline__ int policy_class(const CbState& st, int guard_b, int track) {
   const int B = max(st.max_sys, st.max_in) + st.max_in;
-  return B > guard_b || ((32491 / (B + 1) - 11) >> 1) < 1;
+  if (B <= guard_b && ((32491 / (B + 1) - 11) >> 1) >= 1) return 0;
+  return (track && !(st.retry & 2) && B + 1 <= 16000 && max(st.cert[0], st.cert[1]) <= 26000) ? 1 : 2;
 }
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count, int guard_b) {
-  __shared__ int wsum[2][COMPACT_THREADS / 32];
-  __shared__ int base[2];
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count, int guard_b, int track) {
+  __shared__ int wsum[3][COMPACT_THREADS / 32];
+  __shared__ int base[3];
   const int i = blockIdx.x * COMPACT_THREADS + threadIdx.x;
   const bool on = (i < nblk) && (state[i].status == 0);
-  const bool ex = on && needs_exact_policy(state[i], guard_b);
-  const unsigned balf = __ballot_sync(0xffffffffu, on && !ex), balx = __ballot_sync(0xffffffffu, ex);
+  const int cls = on ? policy_class(state[i], guard_b, track) : -1;
+  const unsigned bal0 = __ballot_sync(0xffffffffu, cls == 0), bal1 = __ballot_sync(0xffffffffu, cls == 1), bal2 = __ballot_sync(0xffffffffu, cls == 2);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { wsum[0][wid] = __popc(balf); wsum[1][wid] = __popc(balx); }
+  if (lane == 0) { wsum[0][wid] = __popc(bal0); wsum[1][wid] = __popc(bal1); wsum[2][wid] = __popc(bal2); }
   __syncthreads();
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 3) {
     int t = 0;
     for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int c = wsum[threadIdx.x][w]; wsum[threadIdx.x][w] = t; t += c; }
     base[threadIdx.x] = t ? atomicAdd(count + threadIdx.x, t) : 0;
   }
   __syncthreads();
+  // the fast and tracked classes share the front of the list: fast blocks at [0, nf), tracked ones at [nf, nf + nt).  nf is
+  // only known once every CTA has added its count, so the tracked class is written from the back of the FRONT HALF:
+  // entries nblk/2.. are not usable for that; instead it gets its own region: list2 = list + nblk (the list has 2 nblk slots
+  // per direction, see the allocation) -- fast [0..), tracked list[nblk + j], exact list[nblk - 1 - j].
   const unsigned lt = (1u << lane) - 1u;
-  if (on && !ex) list[base[0] + wsum[0][wid] + __popc(balf & lt)] = i;
-  if (ex) list[nblk - 1 - (base[1] + wsum[1][wid] + __popc(balx & lt))] = i;
+  if (cls == 0) list[base[0] + wsum[0][wid] + __popc(bal0 & lt)] = i;
+  if (cls == 1) list[nblk + base[1] + wsum[1][wid] + __popc(bal1 & lt)] = i;
+  if (cls == 2) list[nblk - 1 - (base[2] + wsum[2][wid] + __popc(bal2 & lt))] = i;
 }
 
-// entry `gi` of the two-ended list: the fast class occupies [0, nf), padded to a multiple of 8 (one warp of k_map16),
-// the exact class follows; -1: no block
+// entry `gi` of the list as the MAP kernel walks it: fast class [0, nf) padded to a multiple of 8 (one warp of k_map16),
+// then the tracked class (padded likewise), then the exact class; -1: no block
 __device__ __forceinline__ int active_block(const int* list, const int* count, int nblk, int gi) {
-  const int nf = count[0], nx = count[1], nfp = (nf + 7) & ~7;
+  const int nf = count[0], nt = count[1], nx = count[2], nfp = (nf + 7) & ~7, ntp = (nt + 7) & ~7;
   if (gi < nf) return list[gi];
-  if (gi >= nfp && gi - nfp < nx) return list[nblk - 1 - (gi - nfp)];
+  if (gi >= nfp && gi - nfp < nt) return list[nblk + (gi - nfp)];
+  if (gi >= nfp + ntp && gi - nfp - ntp < nx) return list[nblk - 1 - (gi - nfp - ntp)];
   return -1;
 }
 
@@ -267,6 +276,7 @@ __global__ void __launch_bounds__(TH, DEMUX_MIN_CTAS * (XCHG_THREADS / TH) > 32 
   if (threadIdx.x == 0) {
     st->max_in = mx;
     st->max_sys = mx;
+    st->retry = 0; st->cert[0] = 0; st->cert[1] = 0;
     // `while (iteration_cnt++ < max_iterations)` with max 0 returns 1 (reference :1201,1384)
     st->status = (m.max_iter == 0) ? 1 : 0;
     if (m.max_iter == 0 && p.status_out) p.status_out[blk] = 1;
@@ -280,7 +290,7 @@ template <int TH>
 __global__ void __launch_bounds__(TH) k_x1_16(XchgArgs p) {
   extern __shared__ int16_t sm[];
   __shared__ int smax;
-  if (blockIdx.x == 0 && threadIdx.x < 2 && p.nactive_next) p.nactive_next[threadIdx.x] = 0;   // the list k_compact fills next
+  if (blockIdx.x == 0 && threadIdx.x < 3 && p.nactive_next) p.nactive_next[threadIdx.x] = 0;   // the list k_compact fills next
   const int blk = xchg_block(p, (XCHG_LIST_MODE & 1) != 0);
   if (blk < 0) return;
   const CbMeta m = p.meta[blk];

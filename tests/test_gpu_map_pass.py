@@ -95,3 +95,30 @@ def test_one_map_pass_fast_policy_matches_where_the_guard_allows(capi, port):
                 want = port_map(port, y, K, term)
                 for policy in (1, 2, 0):
                     assert np.array_equal(capi.debug_map16(y, K, term, policy), want), (K, amp, term, policy)
+
+
+def test_one_map_pass_tracked_policy(capi, port):
+    """policy 4 forces the tracked fast pass (fast arithmetic + a-posteriori range certificate, retry on the exact policy
+    when it fails): beyond the a-priori guard it must equal the reference whether the certificate holds (moderate
+    amplitudes, coded signals) or not (amplitudes at which the reference saturates), for every K class incl. K = 40 where
+    the re-run covers the lane, with ordinary and extreme tail metrics; policy 0 (decide) must agree."""
+    from bench import coded_inputs
+    rng = np.random.default_rng(17)
+    for K in (40, 48, 104, 512, 1056, 6144):
+        cases = [rng.integers(-amp, amp + 1, size=3 * K + 12).astype(np.int16) for amp in (700, 1500, 3000, 5000, 8000, 12000, 30000)]
+        y = rng.integers(-2500, 2501, size=3 * K + 12).astype(np.int16)
+        y[3 * K:] = np.array([32767, 32767, -32768, 32767, 32767, -32768, 32767, 32767, 32767, -32768, 32767, 32767], dtype=np.int16)
+        cases.append(y)                                                    # tail metrics far outside the body's range
+        y = rng.integers(-300, 301, size=3 * K + 12).astype(np.int16)
+        y[3 * (K // 2)] = 9000                                              # one outlier drives the maxima, the spreads stay small
+        cases.append(y)
+        if K in (512, 6144):
+            for A in (128, 256, 512, 1500):
+                cases.append(coded_inputs(K, 1, 1.08, 99 + A, A=A)[0][0])
+        for y in cases:
+            for term in (0, 1):
+                want = port_map(port, y, K, term)
+                for policy in (4, 0):
+                    got = capi.debug_map16(y, K, term, policy)
+                    d = np.nonzero(got != want)[0]
+                    assert d.size == 0, (K, int(np.abs(y).max()), term, policy, d.size, [(int(i), int(got[i]), int(want[i])) for i in d[:5]])
