@@ -997,7 +997,7 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
 #endif
 // policy of one block for this pass: 16 / 4 / 1 = untracked fast pass with that renormalisation period (the a-priori guard
 // holds), -1 = tracked fast pass (beyond the guard, range check a posteriori), 0 = exact saturating policy
-constexpr int TRACK_CERT_LIMIT = 26000;   // of 32767: a tracked pass is attempted while the decoder's previous certificate was below this
+constexpr int TRACK_CERT_LIMIT = 24000;   // of 32767: a tracked pass is attempted while the latest certificate (of either decoder) was below this
 __device__ __forceinline__ int map_policy(const CbState& st, int guard_b, int track, int term) {
   const int B = max(st.max_sys, st.max_in) + st.max_in, M = B + 1;
   if (B <= guard_b) {
@@ -1007,7 +1007,7 @@ __device__ __forceinline__ int map_policy(const CbState& st, int guard_b, int tr
   }
   // beyond the guard: try the fast path with the a-posteriori certificate unless the block has failed one before, or its
   // inputs alone (M >= 2 Gmax) leave no room for any spread
-  if (track && !(st.retry & 2) && M <= 16000 && st.cert[term] <= TRACK_CERT_LIMIT) return -1;
+  if (track && !(st.retry & 2) && M <= 16000 && max(st.cert[0], st.cert[1]) <= TRACK_CERT_LIMIT) return -1;
   return 0;
 }
 

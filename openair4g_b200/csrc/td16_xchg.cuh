@@ -65,7 +65,7 @@ constexpr int COMPACT_THREADS = 1024;
 __device__ __forceinline__ int policy_class(const CbState& st, int guard_b, int track) {
   const int B = max(st.max_sys, st.max_in) + st.max_in;
   if (B <= guard_b && ((32491 / (B + 1) - 11) >> 1) >= 1) return 0;
-  return (track && !(st.retry & 2) && B + 1 <= 16000 && max(st.cert[0], st.cert[1]) <= 26000) ? 1 : 2;
+  return (track && !(st.retry & 2) && B + 1 <= 16000 && max(st.cert[0], st.cert[1]) <= 24000) ? 1 : 2;
 }
 __global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CbState* state, int nblk, int* list, int* count, int guard_b, int track) {
   __shared__ int wsum[3][COMPACT_THREADS / 32];
