@@ -322,9 +322,11 @@ def run_b200(args):
     regimes = None
     if world == 1 and not args.no_regimes:
         regimes = {}
-        for name, sig in (("clean", 0.5), ("waterfall", 1.08)):
+        # (A = 8 keeps |LLR| <= 127; A = 128 / 256 are amplitudes of real demapper outputs: beyond the a-priori fast-path guard,
+        # decoded through tracked fast passes with an a-posteriori range certificate)
+        for name, sig, amp in (("clean", 0.5, 8), ("waterfall", 1.08, 8), ("waterfall_A128", 1.08, 128), ("waterfall_A256", 1.08, 256)):
             nd = 64
-            ys, info = coded_inputs(K, nd, sig, 4242)
+            ys, info = coded_inputs(K, nd, sig, 4242, A=amp)
             idx = (torch.arange(B, device="cuda") * 29) % nd
             y_r = torch.from_numpy(ys).cuda()[idx].contiguous()
             out_r = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
@@ -345,7 +347,7 @@ def run_b200(args):
             hist = torch.bincount(st_r.long(), minlength=MAX_ITER + 2).tolist()
             ok_mask = (st_r <= MAX_ITER).cpu().numpy()
             good = bool((out_r.cpu().numpy()[ok_mask] == info[idx.cpu().numpy()][ok_mask]).all())
-            regimes[name] = {"value": B * K * args.steps / (rms * 1e-3) / 1e6, "unit": "Mbit/s", "sigma_over_A": sig,
+            regimes[name] = {"value": B * K * args.steps / (rms * 1e-3) / 1e6, "unit": "Mbit/s", "sigma_over_A": sig, "A": amp,
                              "return_value_histogram": {str(i): h for i, h in enumerate(hist) if h},
                              "mean_iterations": float(sum(min(i, MAX_ITER) * h for i, h in enumerate(hist)) / max(sum(hist), 1)),
                              "crc_passing_blocks_equal_transmitted_bytes": good,
