@@ -1077,6 +1077,7 @@ __global__ void __maxnreg__(MAP_MAX_REGS) k_map16(MapArgs p) {
     bool ok = (sa + sb + M <= 32767);
     if (p.upd) ok = ok && (ex + Ms + Mi <= 32767);
     if (t == 0) {
+      if (p.term == 1) p.state[blk].max_ext2 = ok ? ex : -1;      // lets k_x2_16 skip its saturating forms (exact bound)
       p.state[blk].cert[p.term] = sa + sb + M;
       if (!ok) {                                    // repeat this pass on the exact policy (retry launch), and stay there
         p.state[blk].retry = 3;

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TH, DEMUX_MIN_CTAS * (XCHG_THREADS / TH) > 32 
   if (threadIdx.x == 0) {
     st->max_in = mx;
     st->max_sys = mx;
-    st->retry = 0; st->cert[0] = 0; st->cert[1] = 0;
+    st->retry = 0; st->cert[0] = 0; st->cert[1] = 0; st->max_ext2 = -1;
     // `while (iteration_cnt++ < max_iterations)` with max 0 returns 1 (reference :1201,1384)
     st->status = (m.max_iter == 0) ? 1 : 0;
     if (m.max_iter == 0 && p.status_out) p.status_out[blk] = 1;
@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(TH, X2_MIN_CTAS * (XCHG_THREADS / TH) > 32 ? 3
   // When this block satisfies the MAP fast-path guard (B <= guard) its a-posteriori
   // LLRs obey |ext2| <= 12(B+1)+276, so |ext2| + |ext| + |s0| stays inside int16 and the two
   // saturating operations below are plain adds: 4 instead of 14 instructions per word.
-  const bool nosat = (guardB <= p.guard_b) && (12 * (guardB + 1) + 276 + st->max_ext + st->max_in <= 32767);
+  // ... or when the second decoder's pass ran tracked and recorded its largest |ext2| (an exact bound)
+  const int mx2 = st->max_ext2;
+  const bool nosat = ((guardB <= p.guard_b) && (12 * (guardB + 1) + 276 + st->max_ext + st->max_in <= 32767)) ||
+                     (mx2 >= 0 && mx2 + st->max_ext + st->max_in <= 32767);
   MinMax2 mm;
   // hard decisions (iteration_cnt > 1 only, :1267): when 4 | W every uint4 of the natural-order array holds two
   // complete 4-position groups; they are parked one per byte (index n^7, n = position/4) and packed below
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(TH, X2_MIN_CTAS * (XCHG_THREADS / TH) > 32 ? 3
   }
   if (threadIdx.x == 0) {
     st->max_sys = smax;
+    st->max_ext2 = -1;                                       // consumed: valid for the pass that wrote it only
     int s = 0;
     if (pass) s = p.iter;
     else if (p.iter >= m.max_iter) s = m.max_iter + 1;

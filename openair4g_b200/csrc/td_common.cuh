@@ -39,6 +39,7 @@ struct CbState {
   int32_t  max_sys;    // max |systematic input| of the next MAP pass
   int32_t  status;     // 0 = active, otherwise the decoder's return value
   int32_t  max_ext;    // max |ext| (first decoder's a-posteriori LLRs after feedback)
+  int32_t  max_ext2;   // max |LLR| of the second decoder's last pass when that pass ran tracked and certified, else -1
   int32_t  cert[2];    // last range-certificate value (sp_a + sp_b + M) of a tracked pass of decoder 1 / 2: spreads grow from
                        // pass to pass, so a value close to the limit sends the next pass of that decoder to the exact policy
   int32_t  retry;      // bit 0: the last MAP pass ran tracked and failed its range certificate -> the retry launch repeats it

@@ -36,6 +36,12 @@ if "--json" in sys.argv:
     out, sub, blocks, K = sys.argv[a + 1], sys.argv[a + 2], int(sys.argv[a + 3]), int(sys.argv[a + 4])
     col = {k: hdr.index(k) for k in hdr}
     sel = [r for r in data if sub in r[col["Kernel Name"]]]
+    # the retry launches that follow every k_map16 launch (a few microseconds, nothing to do unless a tracked pass failed) are
+    # the same kernel: keep the launches that did a pass's worth of work
+    def _inst(r):
+        return float(r[col["smsp__inst_executed.sum"]].replace(",", ""))
+    top = max(_inst(r) for r in sel)
+    sel = [r for r in sel if _inst(r) >= 0.5 * top]
 
     def val(r, k):                                     # value in base units (ncu prints Gbyte / Mbyte / Kbyte per column)
         v = float(r[col[k]].replace(",", ""))
