@@ -32,6 +32,13 @@ def algorithmic_bytes_per_block(K):
     return 2 * (3 * K + 12) + K // 8 + 1      # read y once, write bytes + status
 
 
+def bench_config(B, Be, K):
+    """the workload description both arms print (the driver compares the two `config` objects)"""
+    row = 3 * K + 12
+    return {"workload": WORKLOAD, "blocks_per_gpu_per_step": B, "e2e_blocks_per_gpu_per_step": Be,
+            "l2": "inputs larger than L2 (%.0f MB of LLRs per GPU per step, workspace %.0f MB)" % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6)}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -179,7 +186,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mbit/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "blocks_per_gpu_per_step": per_step, "e2e_blocks_per_gpu_per_step": per_step},
+            "config": bench_config(per_step, per_step, K_BITS),
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -480,10 +487,10 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "blocks_per_gpu_per_step": B, "e2e_blocks_per_gpu_per_step": Be,
-                       "l2": "inputs larger than L2 (%.0f MB of LLRs per GPU per step, workspace %.0f MB)"
-                             % (B * row * 2 / 1e6, B * 6 * K * 2 / 1e6),
-                       "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
+            # `config` is the workload only and is identical in both arms (bench.py --impl reference); how this arm measures
+            # is in `method`
+            "config": bench_config(B, Be, K),
+            "method": {"timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
                        "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes, "tx_mirror": tx_side,
             "multicell_ul": multicell, "subframe_latency": subframes, "llr8": llr8_side,
