@@ -147,3 +147,30 @@ def test_device_resident_plan_large_batch(capi):
         assert st[i] == want[i % 12][1], i
         assert np.array_equal(out[i], want[i % 12][0]), i
     plan.close()
+
+
+def test_tracked_passes_in_whole_decodes(capi):
+    """Whole decodes at demapper-like amplitudes, i.e. beyond the a-priori guard: the passes run tracked (fast arithmetic,
+    a-posteriori range certificate), hand over to the exact policy when the certificate fails or gets close, and blocks of
+    all three classes share one batch (and hence warps and compaction lists).  Random K out of all 188 sizes, coded signals
+    at A = 100 ... 6000 in the clean / waterfall / hopeless regimes, uniform noise, 4 or 6 iterations; bytes and return
+    values against the port."""
+    from openair4g_b200.sim import txchain
+    rng = np.random.default_rng(2026)
+    Ks = txchain.k_list()
+    blocks, want = [], []
+    for i in range(480):
+        K = int(Ks[rng.integers(0, len(Ks))]) if i % 4 else (6144, 5824, 3904, 40)[(i // 4) % 4]
+        A = int(rng.choice([100, 180, 256, 400, 700, 1200, 2500, 6000]))
+        kind = i % 5
+        if kind == 4:
+            y = rng.integers(-A, A + 1, size=3 * K + 12).astype(np.int16)
+        else:
+            y, _ = vectors.llr_block(K, 5000 + i, "clean" if kind < 2 else "waterfall", A=A, sigma_over_A=(0.5, 0.8, 1.08, 1.6)[kind])
+        max_it = 4 if i % 3 == 0 else 6
+        blocks.append({"y": y, "K": K, "max_iterations": max_it, "crc_type": 1})
+        want.append(loader.port_decode16(y, K, max_it, 1))
+    blocks += [{"y": vectors.llr_block(6144, 7, "noise")[0], "K": 6144, "max_iterations": 6, "crc_type": 1}]       # one block inside the guard
+    want.append(loader.port_decode16(blocks[-1]["y"], 6144, 6, 1))
+    _check(capi, blocks, want)
+    assert len({w[1] for w in want}) >= 4                      # several different return values (2 ... max+1) were exercised
