@@ -535,7 +535,7 @@ def device_rate(capi, B, K, llr8, steps):
     return {"value": B * K * steps / (ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": ms / steps}
 
 
-def subframe_latency(capi, tbs, G, Qm, max_it, llr8=0, reps=30):
+def subframe_latency(capi, tbs, G, Qm, max_it, llr8=0, reps=30, flags=0):
     """BASELINE configs[0]/[1]: wall-clock latency of ONE subframe's transport block through the host-buffer call
     (page-locked soft bits e in -> fused front end + decoder -> bytes out), the drop-in replacement of the per-code-block
     loops of ulsch_decoding.c:1222-1369 / dlsch_decoding.c:303-453.  Inputs come from the product's own TX chain
@@ -590,7 +590,7 @@ def subframe_latency(capi, tbs, G, Qm, max_it, llr8=0, reps=30):
         for i in range(reps + 5):
             h = C.c_void_p()
             t0 = time.perf_counter()
-            if capi.lib.oai_turbo_submit_batch(descs, Cn, capi.BATCH_DL_STOP_AFTER_FAILURE if sig is not None else 0, -1, C.byref(h)) \
+            if capi.lib.oai_turbo_submit_batch(descs, Cn, flags | (capi.BATCH_DL_STOP_AFTER_FAILURE if sig is not None else 0), -1, C.byref(h)) \
                     or capi.lib.oai_turbo_wait(h):
                 raise RuntimeError("bench.py: subframe batch failed: " + capi.last_error())
             if i >= 5:

@@ -179,6 +179,13 @@ void oai_turbo_harq_pool_destroy(oai_turbo_harq_pool_t *pool);
         transport block, blocks after the first failing one report status 0xFE ("not
         decoded") and their decoded_bytes are zeroed */
 
+#define OAI_BATCH_SLIDING_WINDOW 2u  /* OPTIONAL, NOT bit-exact with the reference: the 16-bit blocks of the batch are
+        decoded by the sliding-window kernel (8...64 windows per block stitched by next-iteration initialisation, soft
+        bits scaled to 8 bits, extrinsic values clipped; one warp decodes a block out of shared memory in ONE launch).
+        Same outputs and return-value rules; decoded bits / iteration counts may differ from
+        phy_threegpplte_turbo_decoder16's near the decoding threshold -- the BLER delta against the default bit-exact
+        mode is reported in profiles/ (tools/sw_bler_delta.py).  Never selected implicitly.  8-bit blocks are unaffected. */
+
 /* Copies descriptors and inputs to the GPU and launches the whole pipeline on the
  * batch's stream; returns immediately (0) or a negative error.  gpu < 0: current device. */
 int oai_turbo_submit_batch(const oai_cb_desc_t *cbs, int ncb, unsigned flags, int gpu,
@@ -273,6 +280,9 @@ int oai_turbo_dev_plan_create(int ncb, uint16_t K, uint8_t max_iterations, uint8
  * no host synchronisation.  Returns the number of kernels launched, or < 0. */
 int oai_turbo_dev_decode(oai_turbo_dev_plan_t *plan, const int16_t *y_dev, long y_stride,
                          uint8_t *out_dev, long out_stride, uint8_t *status_dev, void *stream);
+/* flags = OAI_BATCH_SLIDING_WINDOW: later decodes of the plan run in the optional sliding-window mode (NOT bit-exact,
+ * see the flag); 0: back to the default bit-exact mode.  16-bit plans only. */
+int oai_turbo_dev_plan_set_mode(oai_turbo_dev_plan_t *plan, unsigned flags);
 void oai_turbo_dev_plan_destroy(oai_turbo_dev_plan_t *plan);
 /* Per-launch CUDA-event timing of a plan (used by bench.py for the roofline figures).
  * enable != 0 switches it on for subsequent decodes.  When ms4/count4 are non-NULL the

@@ -15,6 +15,7 @@ CRC24_A, CRC24_B, CRC16, CRC8 = 0, 1, 2, 3
 LTE_NULL = 2
 STATUS_NOT_DECODED = 0xFE
 BATCH_DL_STOP_AFTER_FAILURE = 1
+BATCH_SLIDING_WINDOW = 2          # optional, NOT bit-exact (include/oai_turbo_b200.h)
 
 if not os.path.exists(_build.LIB):
     raise ImportError(
@@ -27,7 +28,7 @@ LIB_PATH = _build.LIB
 EXPORTS = ["init_td16", "free_td16", "init_td8", "free_td8", "phy_threegpplte_turbo_decoder16",
            "phy_threegpplte_turbo_decoder8", "generate_dummy_w", "lte_rate_matching_turbo_rx",
            "sub_block_deinterleaving_turbo", "oai_turbo_submit_batch", "oai_turbo_submit_tbs", "oai_turbo_wait", "oai_ulsch_control_sizes",
-           "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy",
+           "oai_turbo_dev_plan_create", "oai_turbo_dev_decode", "oai_turbo_dev_plan_destroy", "oai_turbo_dev_plan_set_mode",
            "oai_turbo_dev_plan_profile", "oai_turbo_host_alloc", "oai_turbo_host_free", "oai_lte_segmentation_params",
            "oai_turbo_harq_pool_create", "oai_turbo_harq_pool_read", "oai_turbo_harq_pool_destroy",
            "oai_turbo_b200_version", "oai_turbo_b200_last_error", "oai_turbo_b200_launch_count",
@@ -109,6 +110,7 @@ lib.oai_turbo_host_free.restype = None
 lib.oai_turbo_dev_plan_create.argtypes = [C.c_int, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.POINTER(C.c_void_p)]
 lib.oai_turbo_dev_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
 lib.oai_turbo_dev_plan_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+lib.oai_turbo_dev_plan_set_mode.argtypes = [C.c_void_p, C.c_uint]
 lib.oai_turbo_dev_plan_destroy.argtypes = [C.c_void_p]
 lib.oai_turbo_dev_plan_destroy.restype = None
 lib.oai_turbo_debug_map16.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_void_p]
@@ -440,6 +442,11 @@ class DevPlan:
         if rc < 0:
             raise RuntimeError("oai_turbo_dev_decode failed (%d): %s" % (rc, last_error()))
         return rc
+
+    def set_mode(self, flags):
+        """BATCH_SLIDING_WINDOW: optional sliding-window mode (not bit-exact); 0: default"""
+        if lib.oai_turbo_dev_plan_set_mode(self._h, flags) != 0:
+            raise RuntimeError("oai_turbo_dev_plan_set_mode failed: " + last_error())
 
     def profile(self, enable, fetch=False):
         """Switch per-launch event timing on/off; with fetch=True returns and resets

@@ -19,6 +19,7 @@
 #include "td_common.cuh"
 #include "td16_map.cuh"
 #include "td16_xchg.cuh"
+#include "td16_sw.cuh"
 #include "rm_kernels.cuh"
 #include "td8_kernels.cuh"
 #include "tx_kernels.cuh"
@@ -82,6 +83,8 @@ struct DevCtx {
   uint16_t* t8_pool = nullptr;        // 8-bit decoder: T8 tables (C8 byte index -> C8 byte index of the QPP image)
   uint32_t t8_off[188];
   u32* crc_xp = nullptr;              // [4][32][CRC_NM] powers of x mod the CRC polynomials
+  u32* sw_tab = nullptr;              // sliding-window mode (td16_sw.cuh): interleaver tables in the window layout, all K
+  u32* sw_tab_off = nullptr;          // [769] word offset of K's table, indexed by K >> 3
   bool ok = false;
   unsigned gen = 0;                   // bumped when the tables are (re)built: cached launch graphs hold table pointers
   // rate-dematching prefix-count tables, one per (K, F) seen so far: cnt[i] = number of circular-buffer slots in [0, i)
@@ -197,6 +200,28 @@ static int ctx_get(int dev, DevCtx** out) {
       for (int rr = 0; rr < 32; ++rr)
         for (int m = 0; m < CRC_NM; ++m) xp[(t * 32 + rr) * CRC_NM + m] = pw[rr + 32 * m];
     }
+    {
+      // sliding-window mode: entry [o][t] = shared-memory halfword indices of pi(j) for j = (2t) WL + o and
+      // (2t+1) WL + o, the thread's two windows at step o
+      std::vector<u32> swt, swo(769, 0);
+      for (int i = 0; i < 188; ++i) {
+        const int K = qpp_K(i), NW = sw_windows(K), WL = K / NW, LPB = NW / 2;
+        const uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
+        swo[K >> 3] = (u32)swt.size();
+        auto idx = [&](uint64_t j) -> u32 {                // step' << 6 | ((lane' + step') & 31) << 1 | half  (sw_idx)
+          const uint64_t pj = (f1 * j + f2 * j * j) % (uint64_t)K;
+          const u32 o = (u32)(pj % WL), w = (u32)(pj / WL);
+          return (o << 6) | ((((w >> 1) + o) & 31u) << 1) | (w & 1u);
+        };
+        for (int o = 0; o < WL; ++o)
+          for (int t = 0; t < LPB; ++t) swt.push_back(idx((uint64_t)(2 * t) * WL + o) | (idx((uint64_t)(2 * t + 1) * WL + o) << 16));
+      }
+      CU(cudaMalloc(&c.sw_tab, swt.size() * sizeof(u32)));
+      CU(cudaMemcpy(c.sw_tab, swt.data(), swt.size() * sizeof(u32), cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&c.sw_tab_off, swo.size() * sizeof(u32)));
+      CU(cudaMemcpy(c.sw_tab_off, swo.data(), swo.size() * sizeof(u32), cudaMemcpyHostToDevice));
+      CU(cudaFuncSetAttribute(k_turbo_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, sw_smem_bytes(6144)));
+    }
     CU(cudaMalloc(&c.crc_xp, xp.size() * sizeof(u32)));
     CU(cudaMemcpy(c.crc_xp, xp.data(), xp.size() * sizeof(u32), cudaMemcpyHostToDevice));
     CU(cudaFuncSetAttribute(k_map16<MAP_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAP_SMEM_BYTES));
@@ -215,6 +240,7 @@ static void ctx_release_all() {
   for (DevCtx& c : g_ctx) {
     if (!c.ok) continue;
     cudaFree(c.pi_pool); cudaFree(c.t_pool); cudaFree(c.qpp_pool); cudaFree(c.t8_pool); cudaFree(c.crc_xp);
+    cudaFree(c.sw_tab); cudaFree(c.sw_tab_off); c.sw_tab = c.sw_tab_off = nullptr;
     if (c.rm_tab) cudaFree(c.rm_tab);
     c.rm_tab = nullptr; c.rm_tab_used = 0; c.rm_tab_off.clear();
     c.pi_pool = c.t_pool = c.qpp_pool = c.t8_pool = nullptr; c.crc_xp = nullptr;
@@ -306,6 +332,8 @@ struct Batch {
   DevCtx* ctx = nullptr;
   int cap = 0, n = 0, A = 0, max_iter = 0, max_K = 0;
   int cur_max_K = 6144;        // largest K of the batch that is loaded (set_meta): sizes the exchange CTAs
+  int sw_mode = 0;             // the loaded batch is decoded in the optional sliding-window mode (td16_sw.cuh)
+  int cur_sw_smem = 0;         // its shared-memory need (largest window length of the batch)
   long slot_hw = 0, ckpt_words = 0;
   CbMeta* d_meta = nullptr;
   CbState* d_state = nullptr;
@@ -323,7 +351,9 @@ struct Batch {
     unsigned gen;                      // DevCtx::gen the graph was built against
     int in8 = 0;
     int cur_K = 0;                     // largest K of the loaded batch (sizes the exchange CTAs)
+    int sw = 0;                        // sliding-window mode (and its shared-memory size)
     bool operator==(const GraphKey& o) const {
+      if (sw != o.sw) return false;
       return in == o.in && out == o.out && status == o.status && fe_rm == o.fe_rm && fe_w == o.fe_w && fe_harq == o.fe_harq &&
              lo == o.lo && n == o.n && part == o.part && max_iter == o.max_iter && max_K == o.max_K && gen == o.gen && in8 == o.in8 && cur_K == o.cur_K;
     }
@@ -369,7 +399,8 @@ struct Batch {
     n = (int)m.size();
     max_iter = 0;
     cur_max_K = 40;
-    for (auto& x : m) { if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter); cur_max_K = std::max<int>(cur_max_K, x.K); }
+    cur_sw_smem = 0;
+    for (auto& x : m) { if (x.flags & 1) max_iter = std::max<int>(max_iter, x.max_iter); cur_max_K = std::max<int>(cur_max_K, x.K); cur_sw_smem = std::max(cur_sw_smem, sw_smem_bytes(x.K)); }
     CU(cudaMemcpyAsync(d_meta, staged ? staged : (const void*)h_meta.data(), sizeof(CbMeta) * n, cudaMemcpyHostToDevice, st));
     return 0;
   }
@@ -387,7 +418,7 @@ struct Batch {
     // given block count, iteration limit and set of pointers, early exits are decided on the device -- is built once
     // as a CUDA graph and replayed.
     if (n <= GRAPH_MAX_BLOCKS && !prof.on && g_use_graphs) {
-      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen, in8, cur_max_K};
+      const GraphKey key{in_dev, out_dev, status_dev, fe_rm, fe_w, fe_harq, lo, n, part, max_iter, max_K, ctx->gen, in8, cur_max_K, sw_mode ? cur_sw_smem : 0};
       GraphEntry* ge = nullptr;
       for (auto& g : graphs) if (g.key == key) { ge = &g; break; }
       if (!ge) {
@@ -431,6 +462,21 @@ struct Batch {
     int* nact[2] = {this->d_nactive + 8 * part, this->d_nactive + 8 * part + 4};
     int cur = 0;
     if (status_dev) status_dev += lo;
+    if (sw_mode) {
+      // optional sliding-window mode: the whole decode of a block group is one warp of one launch (td16_sw.cuh)
+      if (fe_rm || in8) return fail(-3, "sliding-window mode takes the decoder input y as int16");
+      SwArgs s{};
+      s.meta = d_meta; s.state = d_state; s.nblk = n; s.in_base = in_dev; s.out_base = out_dev; s.status_out = status_dev;
+      s.tab_pool = ctx->sw_tab; s.tab_off = ctx->sw_tab_off; s.crc_xp = ctx->crc_xp;
+      prof.begin(1, st);
+      L.run(k_turbo_sw, dim3(n), dim3(32), (size_t)cur_sw_smem, s);
+      prof.end(st);
+      if (count) g_launches += 1;
+      if (!L.ok) return -101;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(-101, "kernel launch failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
     XchgArgs x{};
     x.meta = d_meta; x.state = d_state; x.ws = d_ws; x.slot_hw = slot_hw; x.A = A; x.nblk = n;
     x.pi_pool = ctx->pi_pool; x.t_pool = ctx->t_pool; x.crc_xp = ctx->crc_xp; x.in_base = in_dev; x.out_base = out_dev;
@@ -1287,7 +1333,9 @@ struct HostBatch {
     const size_t deint_smem = 3 * (32 * ((Kmax + 4 + 31) / 32)) * sizeof(int16_t);
     // when every block of the batch goes through the front end (and is a 16-bit block), sub-block deinterleaving is
     // fused into k_demux16: the decoder input y is never materialised
-    const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16);
+    const bool sw = (flags & OAI_BATCH_SLIDING_WINDOW) != 0;
+    b.sw_mode = sw ? 1 : 0;
+    const bool fuse_deint = (rm.size() == (size_t)n) && (n == n16) && !sw;
     auto front_end = [&](size_t jlo, size_t jhi, cudaStream_t fs) {   // dematch (+ deinterleave) of rm blocks [jlo, jhi) on fs
       const int cnt = (int)(jhi - jlo);
       k_rm_rx<<<cnt, RM_THREADS, 0, fs>>>(d_rm + jlo, cnt, d_w, d_e, nullptr, hp, gseq.empty() ? nullptr : d_gold, b.ctx->rm_tab);
@@ -1398,7 +1446,7 @@ struct HostBatch {
     if (parts > 1) {
       CU(cudaEventRecord(ev_setup, st));
       for (auto& s2 : st_part) CU(cudaStreamWaitEvent(s2, ev_setup, 0));
-      bool narrow = !fe_parts && host_pack_threads() > 0 && !getenv("OAI_TURBO_NO_NARROW_FEED");
+      bool narrow = !fe_parts && !sw && host_pack_threads() > 0 && !getenv("OAI_TURBO_NO_NARROW_FEED");
       if (narrow && g_pack_pause.load() > 0) { g_pack_pause.fetch_sub(1); narrow = false; }
       if (narrow) { rc = ensure_in8(in_hw); if (rc) return rc; }
       double pack_s = 0, pack_bytes = 0;
@@ -1610,6 +1658,14 @@ int oai_turbo_dev_decode(oai_turbo_dev_plan_t* p, const int16_t* y_dev, long y_s
     p->y_stride = y_stride; p->out_stride = out_stride;
   }
   return p->llr8 ? p->b8.decode8(y_dev, out_dev, status_dev, st) : p->b.decode16(y_dev, out_dev, status_dev, st);
+}
+
+int oai_turbo_dev_plan_set_mode(oai_turbo_dev_plan_t* p, unsigned flags) {
+  if (!p) return fail(-1, "null plan");
+  if (flags & ~OAI_BATCH_SLIDING_WINDOW) return fail(-1, "oai_turbo_dev_plan_set_mode: unknown flags 0x%x", flags);
+  if (p->llr8 && flags) return fail(-1, "the sliding-window mode exists for the 16-bit decoder only");
+  p->b.sw_mode = (flags & OAI_BATCH_SLIDING_WINDOW) ? 1 : 0;
+  return 0;
 }
 
 

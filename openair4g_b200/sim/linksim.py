@@ -109,13 +109,14 @@ def ul_multiplex(e, ctrl, sizes, Qm, c_init, rng, Cmux=12, Ncp=0):
 
 
 class LinkSim:
-    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1, gpu_tx=False, ul_front=None):
+    def __init__(self, cfg: LinkConfig, max_iterations=4, llr8=0, llr_scale=4.0, seed=1, gpu_tx=False, ul_front=None, decoder_flags=0):
         """gpu_tx: encode / interleave / rate-match on the GPU (oai_turbo_tx_batch) instead of the numpy TX chain.
         ul_front (uplink only): dict(O_ACK, O_RI, Or1) -- every subframe carries that control information, the harness
         hands the GPU the multiplexed, scrambled soft bits of the whole allocation (oai_ul_front_t) and the transport
         block comes back assembled (oai_turbo_submit_tbs)."""
         self.cfg, self.max_it, self.llr8, self.scale, self.gpu_tx = cfg, max_iterations, llr8, llr_scale, gpu_tx
         self.ul_front = ul_front
+        self.decoder_flags = decoder_flags               # e.g. capi.BATCH_SLIDING_WINDOW (optional mode, not bit-exact)
         self.rng = np.random.default_rng(seed)
         B = cfg.tbs + 24
         self.C, self.Cp, self.Cm, self.Kp, self.Km, self.F = tx.segmentation(B)
@@ -235,9 +236,9 @@ class LinkSim:
                                                "scr_c_init": cfg.c_init if cfg.downlink else None, "scr_offset": offs[r]}})
             t0 = time.perf_counter()
             if tbs is None:
-                outs, status = capi.decode_batch(blocks, flags=capi.BATCH_DL_STOP_AFTER_FAILURE if cfg.downlink else 0)
+                outs, status = capi.decode_batch(blocks, flags=self.decoder_flags | (capi.BATCH_DL_STOP_AFTER_FAILURE if cfg.downlink else 0))
             else:
-                outs, status, tbo = capi.decode_batch(blocks, tbs=tbs)
+                outs, status, tbo = capi.decode_batch(blocks, tbs=tbs, flags=self.decoder_flags)
                 res.setdefault("tb_results", []).append([(t[0], t[1]) for t in tbo])
             res["gpu_s"] += time.perf_counter() - t0
             st = np.array(status).reshape(idx.size, C)

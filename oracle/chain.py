@@ -90,14 +90,15 @@ def _front_end(tb, r, w, clear, e_slice):
     return d[96:96 + 3 * K + 12].copy()
 
 
-def rx_tb(tb, max_it, downlink, llr8=0, w=None, clear=1, e=None):
+def rx_tb(tb, max_it, downlink, llr8=0, w=None, clear=1, e=None, dec=None):
     """The reference's receive chain for one transport block.  Returns dict(c=[bytes per block], status=[per block or
     None when not decoded], ret, b (bytes or None), w=[HARQ buffers])."""
     seg, Ks = tb["seg"], tb["Ks"]
     Cn, F = seg[0], seg[5]
     e = tb["e"] if e is None else e
     crc_type = 0 if Cn == 1 else 1
-    dec = loader.port_decode8 if llr8 else loader.port_decode16
+    if dec is None:                                          # (tests of the optional sliding-window mode pass its model)
+        dec = loader.port_decode8 if llr8 else loader.port_decode16
     if w is None:
         w = [np.zeros(3 * 32 * ((K + 4 + 31) // 32), dtype=np.int16) for K in Ks]
     c, status, off, err = [], [], 0, False

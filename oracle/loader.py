@@ -73,6 +73,10 @@ def port():
     L.orc_lte_rate_matching_turbo.restype = C.c_uint32
     L.orc_turbo_decoder16.argtypes = [i16p, u8p, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8]
     L.orc_turbo_decoder16.restype = C.c_uint8
+    L.orc_turbo_decoder16_sw.argtypes = [i16p, u8p, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.c_void_p]
+    L.orc_turbo_decoder16_sw.restype = C.c_uint8
+    L.orc_sw_shift.argtypes = [i16p, C.c_int]
+    L.orc_sw_windows.argtypes = [C.c_int]
     L.orc_turbo_decoder8.argtypes = [i16p, u8p, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8]
     L.orc_turbo_decoder8.restype = C.c_uint8
     L.orc_log_map16.argtypes = [i16p, i16p, i16p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -218,6 +222,16 @@ def port_decode16(y, n, max_it, crc_type, F=0):
     out = np.zeros(n // 8 + 4, dtype=np.uint8)
     r = L.orc_turbo_decoder16(yy, out, n, max_it, crc_type, F)
     return out[:n // 8].copy(), int(r)
+
+
+def port_decode16_sw(y, n, max_it, crc_type, F=0, llr=False):
+    """CPU model of the optional sliding-window mode (oracle/port/td16_sw_port.c)"""
+    L = port()
+    yy = np.ascontiguousarray(y[:3 * n + 12], dtype=np.int16)
+    out = np.zeros(n // 8 + 4, dtype=np.uint8)
+    dbg = np.zeros(n, dtype=np.int32) if llr else None
+    r = L.orc_turbo_decoder16_sw(yy, out, n, max_it, crc_type, F, dbg.ctypes.data if llr else None)
+    return (out[:n // 8].copy(), int(r), dbg) if llr else (out[:n // 8].copy(), int(r))
 
 
 def ref_decode_batch(y_blocks, n, max_it, crc_type, total=None, threads=1, which=16):

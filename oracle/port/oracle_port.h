@@ -64,6 +64,12 @@ uint8_t orc_turbo_decoder16(const int16_t *y, uint8_t *decoded_bytes, uint16_t n
 void orc_log_map16(const int16_t *sys, const int16_t *par, int16_t *ext, int n, int term_flag,
                    int16_t *alpha_dump, int16_t *beta_dump);
 
+/* CPU model of the optional sliding-window mode (td16_sw_port.c; not a reference function).  Same contract. */
+uint8_t orc_turbo_decoder16_sw(const int16_t *y, uint8_t *decoded_bytes, uint16_t n, uint8_t max_iterations,
+                               uint8_t crc_type, uint8_t F, int *dbg_llr);
+int orc_sw_windows(int K);
+int orc_sw_shift(const int16_t *y, int n);
+
 /* 8-bit decoder (3gpplte_turbo_decoder_sse_8bit.c:894-1657); parity domain
  * n>=256 && n%16==0; returns 254 outside it. */
 uint8_t orc_turbo_decoder8(const int16_t *y, uint8_t *decoded_bytes, uint16_t n,
