@@ -383,6 +383,21 @@ def run_b200(args):
         llr8_side["note"] = ("device-resident, %d blocks, noise regime, 6 iterations; ratio = 8-bit / 16-bit decoder at the same K and "
                              "batch (on the reference CPU the 8-bit decoder is ~1.4x the 16-bit one, SURVEY 6)" % B8)
 
+    # ---- side measurement: the OPTIONAL sliding-window mode (north_star: reported separately, with its BLER delta) ----
+    sw_side = None
+    if world == 1 and not args.no_regimes:
+        SW = capi.BATCH_SLIDING_WINDOW
+        sw_side = {"bit_exact_with_reference": False,
+                   "device_resident": guarded(device_rate, capi, B, K, 0, args.steps, flags=SW),
+                   "dlsim_subframe_latency_ms": guarded(subframe_latency, capi, 75376, 90000, 6, 6, flags=SW),
+                   "dlsim_subframe_latency_ms_bit_exact_mode": guarded(subframe_latency, capi, 75376, 90000, 6, 6),
+                   "ulsim_subframe_latency_ms": guarded(subframe_latency, capi, 7736, 14400, 4, 6, flags=SW),
+                   "bler_delta": "profiles/r2s_sw_bler_delta.txt (tools/sw_bler_delta.py: ulsim 25 PRB MCS16 +0.11 dB at BLER 10 % / "
+                                 "+0.03 dB at 1 % with 6 iterations, +0.25 dB with 4; dlsim MCS28: no error floor, unlike the reference's "
+                                 "8-lane split)",
+                   "note": "OAI_BATCH_SLIDING_WINDOW: one warp decodes a block out of shared memory in one launch (td16_sw.cuh); never "
+                           "part of `value` / `e2e`, which are the bit-exact mode"}
+
     # ---- side measurement: TX mirror (encoder + sub-block interleaver + rate matching), device pointers ----
     tx_side = None
     if world == 1 and not args.no_regimes:
@@ -493,7 +508,7 @@ def run_b200(args):
             "method": {"timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
                        "sharding": "independent code blocks, one shard per rank, no data-path collective", "per_rank": per_rank},
             "roofline": roofline, "int_simd": int_simd, "cpu_baseline": cpu, "early_exit_regimes": regimes, "tx_mirror": tx_side,
-            "multicell_ul": multicell, "subframe_latency": subframes, "llr8": llr8_side,
+            "multicell_ul": multicell, "subframe_latency": subframes, "llr8": llr8_side, "sliding_window_mode": sw_side,
             "e2e": {"value": e2e_val, "unit": "Mbit/s", "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": e2e_d2h, "ms_per_step": 1e3 * dt / args.steps,
                     "in_flight": 1 if args.e2e_serial else 2, "serial_value": e2e_serial_val,
@@ -508,7 +523,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def device_rate(capi, B, K, llr8, steps):
+def device_rate(capi, B, K, llr8, steps, flags=0):
     """device-resident decoder throughput (noise regime, 6 iterations) of B blocks of size K; CUDA events"""
     import torch
     row = 3 * K + 12 + (4 if llr8 else 0)
@@ -518,6 +533,8 @@ def device_rate(capi, B, K, llr8, steps):
     out = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
     st = torch.zeros(B, dtype=torch.uint8, device="cuda")
     plan = capi.DevPlan(B, K, MAX_ITER, CRC_TYPE, llr8=llr8)
+    if flags:
+        plan.set_mode(flags)
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         plan.decode(y.data_ptr(), row, out.data_ptr(), K // 8, st.data_ptr(), stream)

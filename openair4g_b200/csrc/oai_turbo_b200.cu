@@ -208,13 +208,16 @@ static int ctx_get(int dev, DevCtx** out) {
         const int K = qpp_K(i), NW = sw_windows(K), WL = K / NW, LPB = NW / 2;
         const uint64_t f1 = kQpp[i][0], f2 = kQpp[i][1];
         swo[K >> 3] = (u32)swt.size();
-        auto idx = [&](uint64_t j) -> u32 {                // step' << 6 | ((lane' + step') & 31) << 1 | half  (sw_idx)
+        auto idx = [&](uint64_t j) -> u32 {                // 2 x (step' << 6 | ((lane' + step') & 31) << 1 | half)  (sw_idx)
           const uint64_t pj = (f1 * j + f2 * j * j) % (uint64_t)K;
           const u32 o = (u32)(pj % WL), w = (u32)(pj / WL);
-          return (o << 6) | ((((w >> 1) + o) & 31u) << 1) | (w & 1u);
+          return 2u * ((o << 6) | ((((w >> 1) + o) & 31u) << 1) | (w & 1u));      // byte offset of the int16 element
         };
         for (int o = 0; o < WL; ++o)
           for (int t = 0; t < LPB; ++t) swt.push_back(idx((uint64_t)(2 * t) * WL + o) | (idx((uint64_t)(2 * t + 1) * WL + o) << 16));
+        auto nat = [&](uint64_t j) -> u32 { return (u32)((f1 * j + f2 * j * j) % (uint64_t)K); };      // then pi(j) itself, same order
+        for (int o = 0; o < WL; ++o)
+          for (int t = 0; t < LPB; ++t) swt.push_back(nat((uint64_t)(2 * t) * WL + o) | (nat((uint64_t)(2 * t + 1) * WL + o) << 16));
       }
       CU(cudaMalloc(&c.sw_tab, swt.size() * sizeof(u32)));
       CU(cudaMemcpy(c.sw_tab, swt.data(), swt.size() * sizeof(u32), cudaMemcpyHostToDevice));

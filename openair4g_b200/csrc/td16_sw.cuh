@@ -22,8 +22,7 @@
 // this kernel must agree with it bit for bit (tests/test_gpu_sw.py).
 //
 // Shared memory per warp, window length WL (all arrays [step][lane], one 32-bit word = the thread's two windows):
-//   SP1 (s0 and p1 as int8 pairs) 128 WL | A, B (systematic input / output of the running pass, int16 pairs) 2 x 128 WL |
-//   P2 (int8 pairs) 64 WL | alpha checkpoints every 16 steps 1 KB per segment | window start metrics 4 KB | decoded bits
+//   S0, P1, P2 (int8 pairs) 3 x 64 WL | A, B (systematic input / output of the running pass, int16 pairs) 2 x 128 WL | alpha checkpoints every 16 steps 1 KB per segment | window start metrics 4 KB | decoded bits
 //   = 54.3 KB at WL = 96 -> 4 warps (blocks) per SM.
 #pragma once
 #include "td16_map.cuh"
@@ -59,21 +58,20 @@ __device__ __forceinline__ int sw_scale(int v, int sh) { return max(-127, min(12
 // arrays) and a walk across the lanes of one step (the recursions, the exchange) are both free of bank conflicts
 __device__ __forceinline__ int sw_idx(int o, int ln) { return (o << 5) + ((ln + o) & 31); }
 
-// parity pair of step-word idx: PH points at the int8 pairs of the running decoder (first decoder: the upper halfword of
-// the SP1 words, pm = 2 halfwords per word; second decoder: P2, pm = 1), so that ONE copy of the recursion code serves
-// both decoders (two copies do not fit the instruction cache once the warps of an SM run out of phase)
-__device__ __forceinline__ u32 sw_par(const uint16_t* __restrict__ PH, int pm, int idx) { return prmt_sx((u32)PH[idx * pm], 0x9180u); }
+// parity pair of step-word idx; PH points at the int8 pairs of the running decoder, so that ONE copy of the recursion code
+// serves both decoders (two copies do not fit the instruction cache once the warps of an SM run out of phase)
+__device__ __forceinline__ u32 sw_par(const uint16_t* __restrict__ PH, int idx) { return prmt_sx((u32)PH[idx], 0x9180u); }
 
 // forward recursion over one segment of n <= 16 steps starting at step `base` (FULL: n == 16, no per-step tests, so
 // that the instruction scheduler can overlap consecutive steps)
 template <bool FULL>
-__device__ __forceinline__ void sw_fwd_seg(u32 (&a)[8], const u32* __restrict__ IN, const uint16_t* __restrict__ PH, int pm,
+__device__ __forceinline__ void sw_fwd_seg(u32 (&a)[8], const u32* __restrict__ IN, const uint16_t* __restrict__ PH,
                                            int base, int n, int lane) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     if (FULL || i < n) {
       const int idx = sw_idx(base + i, lane);
-      const FC c = fconst(IN[idx], sw_par(PH, pm, idx));
+      const FC c = fconst(IN[idx], sw_par(PH, idx));
       alpha_fast(a, c);
       if ((i & 7) == 7) renorm(a);
     }
@@ -84,7 +82,7 @@ __device__ __forceinline__ void sw_fwd_seg(u32 (&a)[8], const u32* __restrict__ 
 //   OUT = 2 * clip(LLR - IN) | (LLR > 0)      (extrinsic value and hard decision; the exchange steps add s0)
 template <bool FULL>
 __device__ __forceinline__ void sw_bwd_seg(u32 (&a)[8], u32 (&b)[8], const u32* __restrict__ IN, u32* __restrict__ OUT,
-                                           const uint16_t* __restrict__ PH, int pm, int base, int n, int lane) {
+                                           const uint16_t* __restrict__ PH, int base, int n, int lane) {
   u32 ae[8][8];
   // recompute the alpha vectors in front of the even steps (the odd ones follow from them in the sweep below)
 #pragma unroll
@@ -96,7 +94,7 @@ __device__ __forceinline__ void sw_bwd_seg(u32 (&a)[8], u32 (&b)[8], const u32* 
       }
       if (i < 14) {                                  // (the vector in front of step 14 is the last one needed)
         const int idx = sw_idx(base + i, lane);
-        const FC c = fconst(IN[idx], sw_par(PH, pm, idx));
+        const FC c = fconst(IN[idx], sw_par(PH, idx));
         alpha_fast(a, c);
         if ((i & 7) == 7) renorm(a);
       }
@@ -113,7 +111,7 @@ __device__ __forceinline__ void sw_bwd_seg(u32 (&a)[8], u32 (&b)[8], const u32* 
       if ((i & 1) || !(FULL || i + 1 < n)) {         // not prepared by the step above
         const int idx = sw_idx(base + i, lane);
         xi = IN[idx];
-        c = fconst(xi, sw_par(PH, pm, idx));
+        c = fconst(xi, sw_par(PH, idx));
       } else {
         c = cn; xi = xn;
       }
@@ -123,7 +121,7 @@ __device__ __forceinline__ void sw_bwd_seg(u32 (&a)[8], u32 (&b)[8], const u32* 
       if (i & 1) {
         const int idp = sw_idx(base + i - 1, lane);
         xn = IN[idp];
-        cn = fconst(xn, sw_par(PH, pm, idp));
+        cn = fconst(xn, sw_par(PH, idp));
         alpha_fast(ai, cn);
       }
       const u32 e = ext_fast(ai, b, c);
@@ -136,10 +134,10 @@ __device__ __forceinline__ void sw_bwd_seg(u32 (&a)[8], u32 (&b)[8], const u32* 
   }
 }
 
-// One constituent pass of the warp's blocks.  IN / OUT: [WL][32] int16 pairs; PH, pm: the decoder's parity (sw_par); nii: [alpha | beta][8 states][32] start metrics of this decoder, updated for the next
+// One constituent pass of the warp's blocks.  IN / OUT: [WL][32] int16 pairs; PH: the decoder's parity (sw_par); nii: [alpha | beta][8 states][32] start metrics of this decoder, updated for the next
 // iteration; term: [8 states][8 blocks] tail metrics of this decoder.  The window is cut into a first segment of
 // n0 = WL - 16 (nseg - 1) steps and full 16-step segments.
-__device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict__ OUT, const uint16_t* __restrict__ PH, int pm,
+__device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict__ OUT, const uint16_t* __restrict__ PH,
                                      u32* __restrict__ CK, u32* __restrict__ nii, const int16_t* __restrict__ term,
                                      int WL, int lane, int tl, int LPB, int g) {
   const unsigned FULL = 0xffffffffu;
@@ -149,13 +147,13 @@ __device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict
   for (int s = 0; s < 8; ++s) a[s] = nii[s * 32 + lane];
 #pragma unroll
   for (int s = 0; s < 8; ++s) CK[s * 32 + lane] = a[s];
-  if (n0 == 16) sw_fwd_seg<true>(a, IN, PH, pm, 0, 16, lane);
-  else sw_fwd_seg<false>(a, IN, PH, pm, 0, n0, lane);
+  if (n0 == 16) sw_fwd_seg<true>(a, IN, PH, 0, 16, lane);
+  else sw_fwd_seg<false>(a, IN, PH, 0, n0, lane);
   for (int seg = 1; seg < nseg; ++seg) {
     renorm(a);
 #pragma unroll
     for (int s = 0; s < 8; ++s) CK[(seg * 8 + s) * 32 + lane] = a[s];
-    sw_fwd_seg<true>(a, IN, PH, pm, n0 + ((seg - 1) << 4), 16, lane);
+    sw_fwd_seg<true>(a, IN, PH, n0 + ((seg - 1) << 4), 16, lane);
   }
   renorm(a);
   // the final metrics of window w start window w+1 in the next iteration
@@ -171,18 +169,79 @@ __device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict
   for (int seg = nseg - 1; seg >= 1; --seg) {
 #pragma unroll
     for (int s = 0; s < 8; ++s) a[s] = CK[(seg * 8 + s) * 32 + lane];
-    sw_bwd_seg<true>(a, b, IN, OUT, PH, pm, n0 + ((seg - 1) << 4), 16, lane);
+    sw_bwd_seg<true>(a, b, IN, OUT, PH, n0 + ((seg - 1) << 4), 16, lane);
   }
 #pragma unroll
   for (int s = 0; s < 8; ++s) a[s] = CK[s * 32 + lane];
-  if (n0 == 16) sw_bwd_seg<true>(a, b, IN, OUT, PH, pm, 0, 16, lane);
-  else sw_bwd_seg<false>(a, b, IN, OUT, PH, pm, 0, n0, lane);
+  if (n0 == 16) sw_bwd_seg<true>(a, b, IN, OUT, PH, 0, 16, lane);
+  else sw_bwd_seg<false>(a, b, IN, OUT, PH, 0, n0, lane);
   renorm(b);
   // the metrics at the start of window w start window w-1's backward recursion in the next iteration
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     const u32 nxt = __shfl_down_sync(FULL, b[s], 1);
     nii[(8 + s) * 32 + lane] = (tl == LPB - 1) ? pack2(hi16(b[s]), term[s * 8 + g]) : __byte_perm(b[s], nxt, 0x5432);
+  }
+}
+
+// Exchange steps, batches of 8 window steps so that the table reads and the dependent shared-memory gathers of a batch
+// overlap (one warp per scheduler: no other warp hides their latency).  Table entries are BYTE offsets into the int16
+// arrays (halfword index x 2); MULTI: the warp carries several blocks, block g adds g * LPB to the lane field (mod 32).
+template <bool MULTI>
+__device__ __forceinline__ u32 sw_tab(const u32* __restrict__ tab, int i, u32 gadd) {
+  const u32 v = __ldg(tab + i);
+  return MULTI ? ((v & 0xFF83FF83u) | ((v + gadd) & 0x007C007Cu)) : v;
+}
+
+// second decoder's systematic input = (s0 + extrinsic) o pi  (TD16:1209-1231, 1354-1375)
+template <bool MULTI>
+__device__ __forceinline__ void sw_x1(u32* __restrict__ Aw, const unsigned char* __restrict__ Bb, const signed char* __restrict__ S0B,
+                                      const u32* __restrict__ tab, u32 gadd, int WL, int LPB, int lane, int tl) {
+  for (int o0 = 0; o0 < WL; o0 += 8) {
+    u32 t[8];
+    int e0[8], e1[8], s0v[8], s1v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = sw_tab<MULTI>(tab, min(o0 + j, WL - 1) * LPB + tl, gadd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u32 k0 = t[j] & 0xffffu, k1 = t[j] >> 16;
+      e0[j] = *reinterpret_cast<const int16_t*>(Bb + k0); e1[j] = *reinterpret_cast<const int16_t*>(Bb + k1);
+      s0v[j] = S0B[k0 >> 1]; s1v[j] = S0B[k1 >> 1];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (o0 + j < WL) Aw[sw_idx(o0 + j, lane)] = pack2(s0v[j] + (e0[j] >> 1), s1v[j] + (e1[j] >> 1));
+  }
+}
+
+// back to natural order: A = s0 + extrinsic (TD16:1241-1265); hard decisions one byte per natural position (tabk: pi(j))
+template <bool MULTI>
+__device__ __forceinline__ void sw_x2(unsigned char* __restrict__ Ab, const u32* __restrict__ Bw, const signed char* __restrict__ S0B,
+                                      unsigned char* __restrict__ hdb, const u32* __restrict__ tab, const u32* __restrict__ tabk,
+                                      u32 gadd, bool hd, int WL, int LPB, int lane, int tl) {
+  for (int o0 = 0; o0 < WL; o0 += 8) {
+    u32 t[8], v[8], kk[8];
+    int s0v[8], s1v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = min(o0 + j, WL - 1);
+      t[j] = sw_tab<MULTI>(tab, o * LPB + tl, gadd);
+      kk[j] = __ldg(tabk + o * LPB + tl);
+      v[j] = Bw[sw_idx(o, lane)];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0v[j] = S0B[(t[j] & 0xffffu) >> 1]; s1v[j] = S0B[t[j] >> 17]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (o0 + j < WL) {
+        *reinterpret_cast<int16_t*>(Ab + (t[j] & 0xffffu)) = (int16_t)(s0v[j] + (lo16(v[j]) >> 1));
+        *reinterpret_cast<int16_t*>(Ab + (t[j] >> 16)) = (int16_t)(s1v[j] + (hi16(v[j]) >> 1));
+        if (hd) {
+          hdb[kk[j] & 0xffffu] = (unsigned char)(v[j] & 1u);
+          hdb[kk[j] >> 16] = (unsigned char)((v[j] >> 16) & 1u);
+        }
+      }
+    }
   }
 }
 
@@ -206,8 +265,9 @@ __global__ void __launch_bounds__(32, 4) k_turbo_sw(SwArgs p) {
   CbState* st = &p.state[blk];
 
   const int nseg = (WL + 15) >> 4;
-  u32* SP1 = reinterpret_cast<u32*>(sw_smem);
-  u32* Aw = SP1 + WL * 32;
+  signed char* S0B = reinterpret_cast<signed char*>(sw_smem);          // [WL][32] int8 pairs, like the halfwords of A / B
+  uint16_t* P1 = reinterpret_cast<uint16_t*>(sw_smem) + WL * 32;
+  u32* Aw = reinterpret_cast<u32*>(sw_smem) + WL * 32;
   u32* Bw = Aw + WL * 32;
   u32* CK = Bw + WL * 32;
   u32* NII = CK + nseg * 256;
@@ -242,15 +302,15 @@ __global__ void __launch_bounds__(32, 4) k_turbo_sw(SwArgs p) {
   int sh = 0;
   while ((mean >> sh) > 24u) ++sh;
   {
-    unsigned char* sp1b = reinterpret_cast<unsigned char*>(SP1);
+    unsigned char* p1b = reinterpret_cast<unsigned char*>(P1);
     unsigned char* p2b = reinterpret_cast<unsigned char*>(P2);
     int16_t* ah = reinterpret_cast<int16_t*>(Aw);
     const u32 magic = 0xffffffffu / (u32)WL + 1u;                 // k / WL for k < 2^16
     auto put = [&](int k, int s, int pa, int pb) {
       const int w = (int)__umulhi((u32)k, magic), o = k - w * WL;
       const int e = sw_idx(o, g * LPB + (w >> 1)), h = w & 1;
-      sp1b[e * 4 + h] = (unsigned char)sw_scale(s, sh);
-      sp1b[e * 4 + 2 + h] = (unsigned char)sw_scale(pa, sh);
+      S0B[e * 2 + h] = (signed char)sw_scale(s, sh);
+      p1b[e * 2 + h] = (unsigned char)sw_scale(pa, sh);
       p2b[e * 2 + h] = (unsigned char)sw_scale(pb, sh);
       ah[e * 2 + h] = (int16_t)sw_scale(s, sh);
     };
@@ -303,82 +363,31 @@ __global__ void __launch_bounds__(32, 4) k_turbo_sw(SwArgs p) {
       NII[((d * 2 + 1) * 8 + s) * 32 + lane] = (tl == LPB - 1) ? pack2(0, TERM[(d * 8 + s) * 8 + g]) : 0u;
     }
 
-  // table entry (per halfword): step' << 6 | ((lane' + step') & 31) << 1 | half  for block 0 of the warp; block g adds
-  // g * LPB to the lane field (mod 32)
+  // table entry (per halfword): 2 x (step' << 6 | ((lane' + step') & 31) << 1 | half), the byte offset of the int16
+  // element of pi(j) in A / B, for block 0 of the warp; then, in the same order, the natural positions pi(j)
   const u32* tab = p.tab_pool + p.tab_off[K >> 3];
-  const u32 gadd = (u32)(g * LPB * 2) * 0x00010001u;
-  auto tab_at = [&](int o) -> u32 {
-    const u32 v = __ldg(tab + o * LPB + tl);
-    return (v & 0xFFC1FFC1u) | ((v + gadd) & 0x003E003Eu);
-  };
+  const u32* tabk = tab + WL * LPB;
+  const u32 gadd = (u32)(g * LPB * 4) * 0x00010001u;
   const int nwb = (K + 31) >> 5;
   const bool run = valid && (m.flags & 1);
   if (valid && !(m.flags & 1) && tl == 0) st->status = 0xFE;          // not to be decoded (like k_demux16)
   bool done = !run;
   const int my_max = run ? (int)m.max_iter : 0;
   const int mx = __reduce_max_sync(FULL, my_max);
-  const int16_t* bh = reinterpret_cast<const int16_t*>(Bw);
-  int16_t* ah = reinterpret_cast<int16_t*>(Aw);
-  const signed char* s0b = reinterpret_cast<const signed char*>(SP1);
   u32* bits = BITS + g * nwb;
   unsigned char* hdb = HD + g * K;
 
   for (int it = 1; it <= mx; ++it) {
-    sw_pass(Aw, Bw, reinterpret_cast<const uint16_t*>(SP1) + 1, 2, CK, NII, TERM, WL, lane, tl, LPB, g);
+    sw_pass(Aw, Bw, P1, CK, NII, TERM, WL, lane, tl, LPB, g);
     __syncwarp();
-    // second decoder's systematic input = (s0 + extrinsic) o pi  (TD16:1209-1231, 1354-1375); batches of 8 steps so that
-    // the table reads and the dependent shared-memory gathers of a batch overlap (one warp per scheduler: no other
-    // warp hides their latency)
-    for (int o0 = 0; o0 < WL; o0 += 8) {
-      u32 t[8];
-      int e0[8], e1[8], s0v[8], s1v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = (o0 + j < WL) ? tab_at(o0 + j) : 0u;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k0 = (int)(t[j] & 0xffffu), k1 = (int)(t[j] >> 16);
-        e0[j] = bh[k0]; e1[j] = bh[k1];
-        s0v[j] = s0b[(k0 >> 1) * 4 + (k0 & 1)]; s1v[j] = s0b[(k1 >> 1) * 4 + (k1 & 1)];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (o0 + j < WL) Aw[sw_idx(o0 + j, lane)] = pack2(s0v[j] + (e0[j] >> 1), s1v[j] + (e1[j] >> 1));
-    }
+    if (G == 1) sw_x1<false>(Aw, reinterpret_cast<const unsigned char*>(Bw), S0B, tab, 0u, WL, LPB, lane, tl);
+    else sw_x1<true>(Aw, reinterpret_cast<const unsigned char*>(Bw), S0B, tab, gadd, WL, LPB, lane, tl);
     __syncwarp();
-    sw_pass(Aw, Bw, P2, 1, CK, NII + 512, TERM + 64, WL, lane, tl, LPB, g);
+    sw_pass(Aw, Bw, P2, CK, NII + 512, TERM + 64, WL, lane, tl, LPB, g);
     __syncwarp();
     const bool hd = it > 1;                          // TD16:1267
-    // back to natural order: A = s0 + extrinsic (TD16:1241-1265), hard decisions one byte per position; batches of 8 steps
-    for (int o0 = 0; o0 < WL; o0 += 8) {
-      u32 t[8], v[8];
-      int s0v[8], s1v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool in = o0 + j < WL;
-        t[j] = in ? tab_at(o0 + j) : 0u;
-        v[j] = in ? Bw[sw_idx(o0 + j, lane)] : 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k0 = (int)(t[j] & 0xffffu), k1 = (int)(t[j] >> 16);
-        s0v[j] = s0b[(k0 >> 1) * 4 + (k0 & 1)]; s1v[j] = s0b[(k1 >> 1) * 4 + (k1 & 1)];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (o0 + j < WL) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int kh = h ? (int)(t[j] >> 16) : (int)(t[j] & 0xffffu);
-            const int vv = h ? hi16(v[j]) : lo16(v[j]);
-            ah[kh] = (int16_t)((h ? s1v[j] : s0v[j]) + (vv >> 1));
-            if (hd) {
-              const int oo = kh >> 6, ln = (((kh >> 1) & 31) - oo) & 31;
-              hdb[(2 * (ln - g * LPB) + (kh & 1)) * WL + oo] = (unsigned char)(vv & 1);
-            }
-          }
-        }
-      }
-    }
+    if (G == 1) sw_x2<false>(reinterpret_cast<unsigned char*>(Aw), Bw, S0B, hdb, tab, tabk, 0u, hd, WL, LPB, lane, tl);
+    else sw_x2<true>(reinterpret_cast<unsigned char*>(Aw), Bw, S0B, hdb, tab, tabk, gadd, hd, WL, LPB, lane, tl);
     __syncwarp();
     if (hd) {                                        // CRC of the block (TD16:1305-1351; see block_crc_check), LPB lanes per block
       typedef unsigned long long u64;
