@@ -180,8 +180,9 @@ void oai_turbo_harq_pool_destroy(oai_turbo_harq_pool_t *pool);
         decoded") and their decoded_bytes are zeroed */
 
 #define OAI_BATCH_SLIDING_WINDOW 2u  /* OPTIONAL, NOT bit-exact with the reference: the 16-bit blocks of the batch are
-        decoded by the sliding-window kernel (8...64 windows per block stitched by next-iteration initialisation, soft
-        bits scaled to 8 bits, extrinsic values clipped; one warp decodes a block out of shared memory in ONE launch).
+        decoded by the sliding-window kernel (8...64 windows per block, stitched by next-iteration initialisation and
+        32-step training recursions; soft bits scaled to 8 bits, extrinsic values clipped; one warp decodes a block out
+        of shared memory in ONE launch).
         Same outputs and return-value rules; decoded bits / iteration counts may differ from
         phy_threegpplte_turbo_decoder16's near the decoding threshold -- the BLER delta against the default bit-exact
         mode is reported in profiles/ (tools/sw_bler_delta.py).  Never selected implicitly.  8-bit blocks are unaffected. */

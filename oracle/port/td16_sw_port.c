@@ -8,8 +8,11 @@
  * (:1209-1265, :1354-1375), the hard decision / CRC / early-exit rule (:1267-1351) and the return value (:985,:1348).
  * What differs, by design:
  *   - the K trellis positions are split into NW = 8 / 16 / 32 / 64 windows (K < 512 / < 1024 / < 2048 / >= 2048) instead
- *     of 8 lanes; a window starts its forward (backward) recursion from the metrics its left (right) neighbour ended
- *     with in the PREVIOUS iteration ("next-iteration initialisation") instead of the reference's 5-step re-run;
+ *     of 8 lanes.  A window's forward (backward) recursion starts from the MORE CONFIDENT (larger max - min) of two
+ *     candidates: the metrics its left (right) neighbour ended with in the PREVIOUS iteration ("next-iteration
+ *     initialisation") and the result of a training recursion over the neighbour's last (first) min(32, WL) steps, started
+ *     from equal metrics on the CURRENT inputs -- instead of the reference's 5-step re-run.  Window 0 always starts in
+ *     state 0, the last window's backward recursion from the tail bits;
  *   - the soft bits are scaled to 8 bits first (right shift chosen from the block's mean |y|, then clipped to +-127)
  *     and the extrinsic values are clipped to +-767: with these bounds the int16 recursions cannot overflow, so the
  *     arithmetic is plain (non-saturating) integer arithmetic -- computed here in int, on the GPU in int16x2.
@@ -22,6 +25,7 @@
 
 #define SW_LC 767
 #define SW_Q  3000
+#define SW_TRAIN 32
 
 int orc_sw_windows(int K) { return K >= 2048 ? 64 : (K >= 1024 ? 32 : (K >= 512 ? 16 : 8)); }
 
@@ -73,6 +77,13 @@ static void beta_step(int *b, int g1, int g0)
   for (s = 0; s < 8; s++) b[s] = nw[s] - nw[0];
 }
 
+static int spread(const int *v)
+{
+  int mx = v[0], mn = v[0], s;
+  for (s = 1; s < 8; s++) { if (v[s] > mx) mx = v[s]; if (v[s] < mn) mn = v[s]; }
+  return mx - mn;
+}
+
 static int llr_step(const int *a, const int *b, int g1, int g0)
 {
   int m00 = imax(imax(a[0] + b[0], a[1] + b[4]), imax(a[6] + b[7], a[7] + b[3]));
@@ -101,7 +112,7 @@ static void tail_beta(const int *ts, const int *tp, int *t)
  * for decoder 1, interleaved order for decoder 2).  llr receives the a-posteriori LLR. */
 static void sw_pass(const int *in, const int *par, int *llr, int K, int NW, int *nii_a, int *nii_b, const int *term)
 {
-  int WL = K / NW, w, o, s;
+  int WL = K / NW, L = WL < SW_TRAIN ? WL : SW_TRAIN, w, o, s;
   int *alpha = (int *)malloc(sizeof(int) * 8 * (size_t)(WL + 1));
   int *na = (int *)malloc(sizeof(int) * 8 * (size_t)NW), *nb = (int *)malloc(sizeof(int) * 8 * (size_t)NW);
   memcpy(na, nii_a, sizeof(int) * 8 * (size_t)NW);
@@ -110,12 +121,22 @@ static void sw_pass(const int *in, const int *par, int *llr, int K, int NW, int 
     int a[8], b[8];
     const int *x = in + w * WL, *p = par + w * WL;
     memcpy(a, nii_a + 8 * w, sizeof(a));
+    if (w > 0) {                                                     /* training over the left neighbour's last steps */
+      int t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q;
+      for (q = w * WL - L; q < w * WL; q++) alpha_step(t, (in[q] + par[q]) >> 1, (in[q] - par[q]) >> 1);
+      if (spread(t) >= spread(a)) memcpy(a, t, sizeof(a));
+    }
     for (o = 0; o < WL; o++) {
       memcpy(alpha + 8 * o, a, sizeof(a));
       alpha_step(a, (x[o] + p[o]) >> 1, (x[o] - p[o]) >> 1);
     }
     if (w + 1 < NW) memcpy(na + 8 * (w + 1), a, sizeof(a));          /* next iteration: start of the right neighbour */
     memcpy(b, nii_b + 8 * w, sizeof(b));
+    if (w + 1 < NW) {                                                /* ... over the right neighbour's first steps */
+      int t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q;
+      for (q = (w + 1) * WL + L - 1; q >= (w + 1) * WL; q--) beta_step(t, (in[q] + par[q]) >> 1, (in[q] - par[q]) >> 1);
+      if (spread(t) >= spread(b)) memcpy(b, t, sizeof(b));
+    }
     for (o = WL - 1; o >= 0; o--) {
       int g1 = (x[o] + p[o]) >> 1, g0 = (x[o] - p[o]) >> 1;
       llr[w * WL + o] = llr_step(alpha + 8 * o, b, g1, g0);

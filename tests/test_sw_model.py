@@ -53,4 +53,4 @@ def test_model_outputs_are_frozen():
     assert h.hexdigest() == FROZEN, h.hexdigest()
 
 
-FROZEN = "a678e43a80f9e4da0170ab80d2bd6815b8501679d9379771aae3a1a6873a3a0a"
+FROZEN = "0da57dbd2cd75eccc8c0b5769b496fd786fce39d11298c837335ec7f843cbbdd"
