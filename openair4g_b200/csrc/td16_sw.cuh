@@ -430,6 +430,10 @@ __global__ void __launch_bounds__(32, 4) k_turbo_sw(SwArgs p) {
   const bool run = valid && (m.flags & 1);
   if (valid && !(m.flags & 1) && tl == 0) st->status = 0xFE;          // not to be decoded (like k_demux16)
   bool done = !run;
+  if (run && m.max_iter == 0) {                      // no iteration at all: the reference returns 1 (TD16:985,1201)
+    if (tl == 0) { st->status = 1; if (p.status_out) p.status_out[blk] = 1; }
+    done = true;
+  }
   const int my_max = run ? (int)m.max_iter : 0;
   const int mx = __reduce_max_sync(FULL, my_max);
   u32* bits = BITS + g * nwb;

@@ -119,3 +119,49 @@ def test_front_end_blocks_and_transport_blocks(capi, case):
         assert np.array_equal(b[:valid], rx["b"][:valid])
         if not noise:
             assert np.array_equal(b[:valid], tb["b"][:valid])
+
+
+def test_iteration_limits_and_mixed_decoders(capi):
+    """max_iterations 0 (nothing runs, return value 1) ... 8; 8-bit blocks of the same submit are not touched by the flag"""
+    rng = np.random.default_rng(3)
+    blocks, want = [], []
+    for i, mi in enumerate((0, 1, 2, 3, 8, 0, 8, 5)):
+        K = (6144, 1024, 512, 40)[i % 4]
+        y, _ = vectors.llr_block(K, 80 + i, "waterfall", A=10, sigma_over_A=(0.7, 1.2)[i % 2])
+        blocks.append({"y": y, "K": K, "max_iterations": mi, "crc_type": 1})
+        want.append(loader.port_decode16_sw(y, K, mi, 1))
+    for i in range(4):
+        y, _ = vectors.llr_block(2048, 90 + i, "clean", A=20, sigma_over_A=0.6)
+        blocks.append({"y": y, "K": 2048, "max_iterations": 4, "crc_type": 1, "llr8": 1})
+        want.append(loader.port_decode8(y, 2048, 4, 1))
+    outs, status = capi.decode_batch(blocks, flags=capi.BATCH_SLIDING_WINDOW)
+    for i, ((wb, wr), ob, st, b) in enumerate(zip(want, outs, status, blocks)):
+        assert st == wr, (i, st, wr)
+        if b["max_iterations"] > 1:
+            assert np.array_equal(ob, wb), i
+
+
+def test_device_resident_plan_mode_switch(capi):
+    import torch
+    K, B = 3904, 96
+    ys = np.stack([vectors.llr_block(K, 300 + i, "waterfall", A=9, sigma_over_A=(0.6, 1.05, 1.3)[i % 3])[0][:3 * K + 12] for i in range(B)])
+    y = torch.from_numpy(ys).cuda()
+    out = torch.zeros((B, K // 8), dtype=torch.uint8, device="cuda")
+    st = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    plan = capi.DevPlan(B, K, 6, 1)
+    stream = torch.cuda.current_stream().cuda_stream
+    for flags, dec in ((capi.BATCH_SLIDING_WINDOW, loader.port_decode16_sw), (0, loader.port_decode16), (capi.BATCH_SLIDING_WINDOW, loader.port_decode16_sw)):
+        plan.set_mode(flags)
+        out.zero_()
+        plan.decode(y.data_ptr(), 3 * K + 12, out.data_ptr(), K // 8, st.data_ptr(), stream)
+        torch.cuda.synchronize()
+        for i in range(B):
+            wb, wr = dec(ys[i], K, 6, 1)
+            assert int(st[i]) == wr and np.array_equal(out[i].cpu().numpy(), wb), (flags, i)
+    with pytest.raises(RuntimeError):
+        plan.set_mode(8)
+    plan.close()
+    p8 = capi.DevPlan(4, 2048, 4, 1, llr8=1)
+    with pytest.raises(RuntimeError):
+        p8.set_mode(capi.BATCH_SLIDING_WINDOW)
+    p8.close()
