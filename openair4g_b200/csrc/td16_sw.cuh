@@ -8,7 +8,7 @@
 // < 2048 / >= 2048; window length 5...96), two windows per thread, so ONE WARP decodes one K >= 2048 block (or 2 / 4 / 8
 // shorter blocks of equal K) from the soft bits to the CRC verdict with everything resident in shared memory:
 //   HBM traffic per block = its 3K+12 soft bits in, K/8 bytes out (K=6144: 37.6 KB instead of 1.28 MB),
-//   one launch per batch instead of 31, and a single block takes ~0.1 ms instead of 0.24-1.08 ms.
+//   one launch per batch instead of 31, and a single block takes 0.10-0.31 ms instead of 0.23-1.07 ms (K = 40 ... 6144).
 // Windows are stitched two ways at once: a window's forward (backward) recursion starts from the more confident (larger
 // max - min) of (a) the metrics its left (right) neighbour finished with in the previous iteration ("next-iteration
 // initialisation") and (b) the result of a 32-step training recursion over the neighbour's last (first) steps on the
@@ -21,12 +21,13 @@
 // and the extrinsic values are clipped to +-SW_LC = 767, so a systematic input is within +-894, M = 894 + 127 + 1 = 1022
 // bounds 2 Gmax and the shifted branch metrics, and the non-saturating DPX fast path of td16_map.cuh (fconst / alpha_fast
 // / beta_fast / ext_fast, renormalised every P = 8 steps) cannot wrap: (11 + 2P) M + 276 = 27 870 <= 32 767 (DESIGN.md
-// "fast-path guard" (b); the start vectors -- previous final vectors, (0,-3000,...) for window 0, the tail metrics -- have
-// spreads within the 10 Gmax + 128 the bound assumes).  A model in plain int arithmetic lives with the test infrastructure;
+// "fast-path guard" (b); the start vectors -- previous final vectors, training results, (0,-3000,...) for window 0, the tail
+// metrics -- have spreads within the 10 Gmax + 128 the bound assumes).  A model in plain int arithmetic lives with the test infrastructure;
 // this kernel must agree with it bit for bit (tests/test_gpu_sw.py).
 //
 // Shared memory per warp, window length WL (all arrays [step][lane], one 32-bit word = the thread's two windows):
-//   S0, P1, P2 (int8 pairs) 3 x 64 WL | A, B (systematic input / output of the running pass, int16 pairs) 2 x 128 WL | alpha checkpoints every 16 steps 1 KB per segment | window start metrics 4 KB | decoded bits
+//   S0, P1, P2 (int8 pairs) 3 x 64 WL | A, B (systematic input / output of the running pass, int16 pairs) 2 x 128 WL |
+//   alpha checkpoints every 16 steps 1 KB per segment | window start metrics 4 KB | decoded bits
 //   = 54.3 KB at WL = 96 -> 4 warps (blocks) per SM.
 #pragma once
 #include "td16_map.cuh"
