@@ -38,6 +38,7 @@ namespace oai {
 constexpr int SW_LC = 767;           // extrinsic clip
 constexpr int SW_Q = 3000;           // penalty of the states window 0 cannot start in
 constexpr int SW_TRAIN = 32;         // steps of the training recursions in front of / behind a window
+constexpr int SW_XB = 4;             // window steps per batch of the exchange loops
 constexpr int SW_BITS_WORDS = 192;   // decoded bits of the warp's blocks (K/32 words each)
 
 __host__ __device__ inline int sw_windows(int K) { return K >= 2048 ? 64 : (K >= 1024 ? 32 : (K >= 512 ? 16 : 8)); }
@@ -159,7 +160,7 @@ __device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict
     u32 t[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     const int lp = (tl == 0) ? lane : lane - 1;
     int cnt = 0;
-#pragma unroll 8
+#pragma unroll 4
     for (int q = WL - L; q < WL; ++q) {
       const int io = sw_idx(q, lane), ip = sw_idx(q, lp);
       const FC c = fconst(__byte_perm(IN[ip], IN[io], 0x5432), prmt_sx((u32)PH[ip] | ((u32)PH[io] << 16), 0xA291u));
@@ -199,7 +200,7 @@ __device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict
     u32 t[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     const int ln = (tl == LPB - 1) ? lane : lane + 1;
     int cnt = 0;
-#pragma unroll 8
+#pragma unroll 4
     for (int q = L - 1; q >= 0; --q) {
       const int io = sw_idx(q, lane), in = sw_idx(q, ln);
       const FC c = fconst(__byte_perm(IN[io], IN[in], 0x5432), prmt_sx((u32)PH[io] | ((u32)PH[in] << 16), 0xA291u));
@@ -230,7 +231,7 @@ __device__ __noinline__ void sw_pass(const u32* __restrict__ IN, u32* __restrict
   }
 }
 
-// Exchange steps, batches of 8 window steps so that the table reads and the dependent shared-memory gathers of a batch
+// Exchange steps, batches of SW_XB window steps so that the table reads and the dependent shared-memory gathers of a batch
 // overlap (one warp per scheduler: no other warp hides their latency).  Table entries are BYTE offsets into the int16
 // arrays (halfword index x 2); MULTI: the warp carries several blocks, block g adds g * LPB to the lane field (mod 32).
 template <bool MULTI>
@@ -245,22 +246,22 @@ __device__ __forceinline__ u32 sw_tab(const u32* __restrict__ tab, int i, u32 ga
 template <bool MULTI>
 __device__ __forceinline__ void sw_x1(u32* __restrict__ Aw, const unsigned char* __restrict__ Bb, const signed char* __restrict__ S0B,
                                       const u32* __restrict__ tab, u32 gadd, int WL, int LPB, int lane, int tl) {
-  u32 tn[8];
+  u32 tn[SW_XB];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) tn[j] = sw_tab<MULTI>(tab, min(j, WL - 1) * LPB + tl, gadd);
-  for (int o0 = 0; o0 < WL; o0 += 8) {
-    u32 t[8];
-    int e0[8], e1[8], s0v[8], s1v[8];
+  for (int j = 0; j < SW_XB; ++j) tn[j] = sw_tab<MULTI>(tab, min(j, WL - 1) * LPB + tl, gadd);
+  for (int o0 = 0; o0 < WL; o0 += SW_XB) {
+    u32 t[SW_XB];
+    int e0[SW_XB], e1[SW_XB], s0v[SW_XB], s1v[SW_XB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { t[j] = tn[j]; tn[j] = sw_tab<MULTI>(tab, min(o0 + 8 + j, WL - 1) * LPB + tl, gadd); }
+    for (int j = 0; j < SW_XB; ++j) { t[j] = tn[j]; tn[j] = sw_tab<MULTI>(tab, min(o0 + SW_XB + j, WL - 1) * LPB + tl, gadd); }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SW_XB; ++j) {
       const u32 k0 = t[j] & 0xffffu, k1 = t[j] >> 16;
       e0[j] = *reinterpret_cast<const int16_t*>(Bb + k0); e1[j] = *reinterpret_cast<const int16_t*>(Bb + k1);
       s0v[j] = S0B[k0 >> 1]; s1v[j] = S0B[k1 >> 1];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < SW_XB; ++j)
       if (o0 + j < WL) Aw[sw_idx(o0 + j, lane)] = pack2(s0v[j] + (e0[j] >> 1), s1v[j] + (e1[j] >> 1));
   }
 }
@@ -270,28 +271,28 @@ template <bool MULTI>
 __device__ __forceinline__ void sw_x2(unsigned char* __restrict__ Ab, const u32* __restrict__ Bw, const signed char* __restrict__ S0B,
                                       unsigned char* __restrict__ hdb, const u32* __restrict__ tab, const u32* __restrict__ tabk,
                                       u32 gadd, bool hd, int WL, int LPB, int lane, int tl) {
-  u32 tn[8], kn[8];
+  u32 tn[SW_XB], kn[SW_XB];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < SW_XB; ++j) {
     const int i = min(j, WL - 1) * LPB + tl;
     tn[j] = sw_tab<MULTI>(tab, i, gadd);
     kn[j] = __ldg(tabk + i);
   }
-  for (int o0 = 0; o0 < WL; o0 += 8) {
-    u32 t[8], v[8], kk[8];
-    int s0v[8], s1v[8];
+  for (int o0 = 0; o0 < WL; o0 += SW_XB) {
+    u32 t[SW_XB], v[SW_XB], kk[SW_XB];
+    int s0v[SW_XB], s1v[SW_XB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = min(o0 + 8 + j, WL - 1) * LPB + tl;
+    for (int j = 0; j < SW_XB; ++j) {
+      const int i = min(o0 + SW_XB + j, WL - 1) * LPB + tl;
       t[j] = tn[j]; kk[j] = kn[j];
       tn[j] = sw_tab<MULTI>(tab, i, gadd);
       kn[j] = __ldg(tabk + i);
       v[j] = Bw[sw_idx(min(o0 + j, WL - 1), lane)];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s0v[j] = S0B[(t[j] & 0xffffu) >> 1]; s1v[j] = S0B[t[j] >> 17]; }
+    for (int j = 0; j < SW_XB; ++j) { s0v[j] = S0B[(t[j] & 0xffffu) >> 1]; s1v[j] = S0B[t[j] >> 17]; }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SW_XB; ++j) {
       if (o0 + j < WL) {
         *reinterpret_cast<int16_t*>(Ab + (t[j] & 0xffffu)) = (int16_t)(s0v[j] + (lo16(v[j]) >> 1));
         *reinterpret_cast<int16_t*>(Ab + (t[j] >> 16)) = (int16_t)(s1v[j] + (hi16(v[j]) >> 1));
