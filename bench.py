@@ -190,7 +190,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -518,7 +518,7 @@ def run_b200(args):
                            "both bound by the host->device copy of 36.9 KB of int16 LLRs per 6144 decoded bits "
                            "(profiles/r2d_link_ceiling.txt: 55 GB/s for one GPU = 9.2 Gbit/s)"},
             "gpu_launches": launches, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -810,15 +810,32 @@ def run_llr8(args, capi, B, K, rank, world, dist):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     prof_ms, _ = plan.profile(False, fetch=True)
-    print(json.dumps({"metric": "turbo_decoded_info_mbit_per_s_8bit_decoder", "value": B * K * args.steps / (ms * 1e-3) / 1e6,
+    emit(({"metric": "turbo_decoded_info_mbit_per_s_8bit_decoder", "value": B * K * args.steps / (ms * 1e-3) / 1e6,
                       "kernel_ms": {"demux": prof_ms[0], "map": prof_ms[1], "x1": prof_ms[2], "x2": prof_ms[3]},
                       "unit": "Mbit/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                       "dtype": "int8", "data": "synthetic",
                       "config": {"workload": "8-bit decoder, K=%d, max_iterations=6, noise regime" % K, "blocks": B},
-                      "status_hist": torch.bincount(st_dev.long()).nonzero().flatten().tolist()}), flush=True)
+                      "status_hist": torch.bincount(st_dev.long()).nonzero().flatten().tolist()}))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the run, on the process's real stdout (see main)"""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print on the way (NCCL's version banner under torchrun, ...)
+    # goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
