@@ -393,8 +393,8 @@ def run_b200(args):
                    "dlsim_subframe_latency_ms_bit_exact_mode": guarded(subframe_latency, capi, 75376, 90000, 6, 6),
                    "ulsim_subframe_latency_ms": guarded(subframe_latency, capi, 7736, 14400, 4, 6, flags=SW),
                    "bler_delta": "profiles/r2s_sw_bler_delta.txt (tools/sw_bler_delta.py; same received subframes in both modes): ulsim 25 PRB "
-                                 "MCS16 -0.02 dB at BLER 10 % / 0.00 dB at 1 % with 6 iterations, -0.05 dB with 4; dlsim MCS28: BLER 0.02 at "
-                                 "19 dB and 0 from 19.5 dB where the reference's algorithm still loses 19-63 % of the transport blocks",
+                                 "MCS16 -0.03 dB at BLER 10 % / -0.08 dB at 1 % with 6 iterations, -0.06 dB with 4; dlsim MCS28: BLER 0.02 at "
+                                 "19 dB and 0.005 at 20 dB where the reference's algorithm still loses 58 / 40 % of the transport blocks",
                    "note": "OAI_BATCH_SLIDING_WINDOW: one warp decodes a block out of shared memory in one launch (td16_sw.cuh); never "
                            "part of `value` / `e2e`, which are the bit-exact mode"}
 

@@ -48,15 +48,15 @@ if __name__ == "__main__":
     quick = "--quick" in sys.argv
     t0 = time.time()
     capi.init_td16()
-    n = 100 if quick else 400
+    n = 100 if quick else 1000
     sweep("ulsim 25 PRB MCS16 (2 x K=3904, 61-step windows)", linksim.ULSIM_25PRB_MCS16, np.arange(5.5, 8.01, 0.25), n, 4)
     sweep("ulsim 25 PRB MCS16", linksim.ULSIM_25PRB_MCS16, np.arange(5.5, 8.01, 0.25), n, 6)
     sweep("ulsim 25 PRB MCS16, 2 HARQ rounds", linksim.ULSIM_25PRB_MCS16, np.arange(3.0, 6.01, 0.5), n // 2, 4, rounds=2)
     sweep("dlsim 100 PRB MCS28 TM1 (13 x K=5824, 91-step windows, code rate 0.84)", linksim.DLSIM_100PRB_MCS28, np.arange(18.0, 21.01, 0.25),
-          20 if quick else 100, 4)
-    sweep("dlsim 100 PRB MCS28 TM1", linksim.DLSIM_100PRB_MCS28, np.arange(18.0, 21.01, 0.25), 20 if quick else 100, 6)
+          20 if quick else 200, 4)
+    sweep("dlsim 100 PRB MCS28 TM1", linksim.DLSIM_100PRB_MCS28, np.arange(18.0, 21.01, 0.25), 20 if quick else 200, 6)
     # the bit-exact mode (= the reference's algorithm) keeps losing blocks at every SNR of the MCS28 sweep.  Not an effect
     # of the soft-bit scale (this harness hands over 4 x LLR): the same sweep with soft bits 8 times smaller
     sweep("dlsim 100 PRB MCS28 TM1, soft bits = 0.5 x LLR instead of 4 x", linksim.DLSIM_100PRB_MCS28, np.arange(18.0, 21.01, 0.25),
-          20 if quick else 100, 6, llr_scale=0.5)
+          20 if quick else 200, 6, llr_scale=0.5)
     print("# wall time %.0f s" % (time.time() - t0))
