@@ -1,6 +1,7 @@
 /* TEST INFRASTRUCTURE -- CPU model of the OPTIONAL sliding-window decoding mode (OAI_BATCH_SLIDING_WINDOW).
  *
- * This file does NOT restate a reference function: the sliding-window mode is this repo's own higher-parallelism
+ * PARITY UNPINNED (by construction, for this file only; every other file under oracle/port is pinned on the compiled
+ * reference): this file does NOT restate a reference function: the sliding-window mode is this repo's own higher-parallelism
  * variant of the 16-bit max-log-MAP decoder (north_star: "allowed only if it is separately reported with its BLER
  * delta against the bit-exact mode"), so there is nothing in /root/reference to pin it on.  What it shares with the
  * reference (3gpplte_turbo_decoder_sse_16bit.c) is the trellis (:292-322, :592-636), the branch metrics (:121-169,
