@@ -54,3 +54,34 @@ def test_model_outputs_are_frozen():
 
 
 FROZEN = "0da57dbd2cd75eccc8c0b5769b496fd786fce39d11298c837335ec7f843cbbdd"
+
+
+def test_reference_error_floor_on_punctured_blocks_comes_from_its_5_step_rerun(tmp_path):
+    """on heavily punctured blocks (90 % of the parity soft bits zero, the MCS28 regime) the reference's decoder
+    keeps losing blocks that are decodable.  Evidence for the cause: the same port with the lane-boundary re-run lengthened
+    from 5 to 40 steps (TD16:171,189,232-259,541-549,585-587) loses none of them, and neither does the sliding-window model."""
+    import ctypes as C
+    import os
+    import re
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "port")
+    src = open(os.path.join(here, "td16_port.c")).read()
+    long_src = re.sub(r"#define RERUN\s+\d+", "#define RERUN 40", src).replace("loopval = (n - 40) >> 3;", "loopval = (n - 320) >> 3;")
+    assert long_src != src
+    (tmp_path / "td16_long.c").write_text(long_src)
+    others = [os.path.join(here, f) for f in os.listdir(here) if f.endswith(".c") and f != "td16_port.c"]
+    lib = str(tmp_path / "liblong.so")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-I" + here, "-o", lib, str(tmp_path / "td16_long.c")] + others + ["-lm", "-lpthread"])
+    L = C.CDLL(lib)
+    L.orc_turbo_decoder16.restype = C.c_uint8
+    K, keep, lost = 5824, 10, [0, 0, 0]
+    idx = np.arange(K)
+    for i in range(60):
+        y = vectors.llr_block(K, 300 + i, "waterfall", A=40, sigma_over_A=0.48)[0].copy()
+        y[3 * idx[(idx % keep) != 0] + 1] = 0
+        y[3 * idx[((idx + keep // 2) % keep) != 0] + 2] = 0
+        out = np.zeros(K // 8 + 4, dtype=np.uint8)
+        lost[0] += loader.port_decode16(y, K, 6, 1)[1] > 6
+        lost[1] += L.orc_turbo_decoder16(y.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_uint16(K), C.c_uint8(6), C.c_uint8(1), C.c_uint8(0)) > 6
+        lost[2] += loader.port_decode16_sw(y, K, 6, 1)[1] > 6
+    assert lost[0] >= 2 and lost[1] == 0 and lost[2] == 0, lost

@@ -3,10 +3,19 @@ import sys, time
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from openair4g_b200 import capi
-from oracle import vectors
+import bench
+
+
+def gen(K, seed, regime):
+    """soft bits of one block from the product's own TX chain (clean / waterfall) or uniform noise"""
+    if regime == "noise":
+        return np.random.default_rng(seed).integers(-16, 17, size=3 * K + 12).astype(np.int16)
+    return bench.coded_inputs(K, 1, {"clean": 0.5, "waterfall": 1.08}[regime], seed)[0][0]
+
+
 capi.init_td16()
 def run(K, n, regime, iters=6, reps=20, llr8=0):
-    ys = [vectors.llr_block(K, 100 + i, regime)[0] for i in range(min(n, 13))]
+    ys = [gen(K, 100 + i, regime) for i in range(min(n, 13))]
     pad = 3 * K + 12 + (36 if llr8 else 0)
     pin = capi.PinnedArray((n, 3 * K + 12), np.int16)
     for i in range(n): pin.array[i] = ys[i % len(ys)]
@@ -17,7 +26,7 @@ def run(K, n, regime, iters=6, reps=20, llr8=0):
         t0 = time.perf_counter(); outs, st = capi.decode_batch(blocks); t.append(time.perf_counter() - t0)
     t.sort()
     print("K=%d n=%d %s llr8=%d: median %.3f ms  min %.3f ms  (status %s)" % (K, n, regime, llr8, 1e3 * t[len(t)//2], 1e3 * t[0], sorted(set(st))))
-y = vectors.llr_block(6144, 1, "clean")[0]
+y = gen(6144, 1, "clean")
 capi.phy_threegpplte_turbo_decoder16(y, 6144, 0, 0, 6, 1, 0)
 t0 = time.perf_counter()
 for _ in range(20): capi.phy_threegpplte_turbo_decoder16(y, 6144, 0, 0, 6, 1, 0)

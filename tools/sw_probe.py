@@ -28,10 +28,10 @@ def main():
         g.manual_seed(4321)
         regimes = [("noise16", torch.randint(-16, 17, (B, row), dtype=torch.int16, device="cuda", generator=g), 7)]
         if a.coded:
-            from oracle import vectors
+            import bench
             nd = 256
             for name, sig in (("waterfall", 1.08), ("clean", 0.5)):
-                ys = np.stack([vectors.llr_block(K, 70 + i, "waterfall", A=8, sigma_over_A=sig)[0][:row] for i in range(nd)])
+                ys = bench.coded_inputs(K, nd, sig, 70)[0][:, :row]       # the product's own TX chain
                 regimes.append((name, torch.from_numpy(ys).cuda().repeat((B + nd - 1) // nd, 1)[:B].contiguous(), None))
                 if name == "waterfall" and a.same:
                     for j in range(3):
