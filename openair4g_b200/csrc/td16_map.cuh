@@ -831,7 +831,11 @@ __device__ void map_pass_fast(const u32* __restrict__ sys, const u32* __restrict
   bool loaded = false;                             // sb/pb/zb/a hold segment `seg`
   for (int seg = nseg - 1; seg >= 0; --seg) {
     const int k0 = seg * S, k1 = min(W, k0 + S);
-    const bool steady = (k0 + S <= W - 6);        // all 16 steps exist and use pass-1 beta
+    // all 16 steps exist.  The last 6 steps of the lane take their LLR from the re-run below (which stores them after
+    // this sweep, in program order), so a full last segment may run the steady-state code too: its 6 LLRs from pass-1 beta
+    // are overwritten (and only make a tracked pass's recorded range a little more conservative).  Blocks with W a
+    // multiple of 16 then have no boundary segment at all (K = 512: a quarter of the steps, at 3-4x the cost per step).
+    const bool steady = (k0 + S <= W);
     if (PF > 0 && seg >= PF) {                    // warm L2 for segment seg-PF (inputs + checkpoint)
       const int cp = (seg - PF) * NCH + (t % NCH);
       l2_prefetch(sys4 + cp * 4 - t);
