@@ -55,3 +55,14 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU oracle", ""), os.path.join(dirpath, f)
+
+
+def test_flag_constants_match_the_header():
+    """the ctypes mirror's flag values are the header's #defines"""
+    from openair4g_b200 import capi
+    txt = open(os.path.join(ROOT, "include", "oai_turbo_b200.h")).read()
+    val = lambda name: int(re.search(r"#define\s+" + name + r"\s+(\d+)u", txt).group(1))
+    assert capi.BATCH_DL_STOP_AFTER_FAILURE == val("OAI_BATCH_DL_STOP_AFTER_FAILURE")
+    assert capi.BATCH_SLIDING_WINDOW == val("OAI_BATCH_SLIDING_WINDOW")
+    assert capi.TX_DEVICE_POINTERS == val("OAI_TX_DEVICE_POINTERS")
+    assert capi.BATCH_SLIDING_WINDOW & capi.BATCH_DL_STOP_AFTER_FAILURE == 0
