@@ -2,7 +2,7 @@
     python tests/soak_gpu.py [exact|sw] [seeds]
 400 blocks per seed: random K out of the 188 sizes, amplitudes 3 ... 30000, coded (clean ... hopeless) or uniform noise,
 1 ... 8 iterations, all four CRC types.  exact: bit-exact mode against the pinned port; sw: the optional sliding-window mode
-against its model.  Last run (round 2): 3200 + 3200 blocks, 0 mismatches."""
+against its model.  Last run (round 2, final kernels): 16000 + 16000 blocks, 0 mismatches."""
 import os
 import sys
 
